@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — H_eff applies/s and FP64 TFLOP/s at D=1024 (U(1)xSU(2)), BASELINE.json's metric.
+
+A "step" is ONE application of the one-site effective Hamiltonian y = GL.x.W.GR (MPSKit's
+`∂AC`, the inner operation of every Lanczos iteration of VUMPS) on the
+synthetic instance of BASELINE config C4 (two-band-like MPO with chi=96 levels, D_red=1024,
+28/25 symmetry sectors).  Environments and the MPO are plan-resident in HBM, as they are
+across the Krylov iterations of the reference.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N>1 (launched by torchrun, one rank per GPU): the unit-cell sites of the VUMPS sweep are
+independent, so rank r applies H_AC of site (r mod 4) with no data-path collective; value is
+the aggregate applies/s ("weak" scaling, replicas of the per-site problem).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+UNIT = "applies/s"
+METRIC = "H_eff (H_AC) applies/s at D=1024, U(1)xSU(2), chi=96"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--D", type=int, default=1024)
+    ap.add_argument("--chi", type=int, default=96)
+    ap.add_argument("--sym", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": "C4-synthetic: one H_AC apply, U1xSU2, D_red=%d, chi=%d MPO levels (4 nnz level pairs/row), "
+                    "d=3 multiplets, unit cell 4 (SURVEY.md 8(d))" % (args.D, args.chi),
+        "D_red": args.D, "chi": args.chi, "symmetry": "fZ2xSU2xU1" if args.sym == 0 else "fZ2xU1xU1",
+        "cache": "inputs larger than L2 (GL+GR+workspaces ~1.2 GB per apply vs 126 MB L2), no flush",
+        "parallelism": "site-parallel replicas (rank r -> unit-cell site r mod 4), no collective",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline (oracle port) — also the body of --impl reference
+# ----------------------------------------------------------------------------------------
+def cpu_case(args, chi_sample):
+    """Oracle-side construction of the same synthetic model restricted to the first
+    `chi_sample` MPO levels (bounded sample); pure numpy, no GPU involved."""
+    import numpy as np
+    from hubbardtn_b200 import sectors as PS, synthetic
+    from oracle import sectors as OS  # noqa: F401
+    from oracle.heff import HeffACPlan
+    from oracle.tensors import EnvTensor, Legs, MPOTensor, MPSTensor, Space
+
+    sym, D = args.sym, args.D
+    phys = PS.physical_space(sym, 1, 1)
+    levels = synthetic.mpo_levels(sym, chi_sample)
+    entries = synthetic.mpo_entries(sym, levels, phys, 4, synthetic.SEED)
+    Vl, Vr = Space(sym, synthetic.bond_space(sym, D, 0)), Space(sym, synthetic.bond_space(sym, D, 1))
+    P, M = Legs(sym, phys), Legs(sym, levels)
+    rng = np.random.default_rng(synthetic.SEED)
+    GL = EnvTensor("L", Vl, M, identity_levels=[0]).randomize(rng)
+    GR = EnvTensor("R", Vr, M, identity_levels=[chi_sample - 1]).randomize(rng)
+    W = MPOTensor(M, P, M, {k: v for k, v in entries.items()})
+    x = MPSTensor(Vl, P, Vr).randomize(rng)
+    return HeffACPlan(GL, W, GR, x), x
+
+
+def run_cpu_baseline(args, threads, budget_s):
+    """Times oracle applies on the host cores: BLAS threads = 1, `threads` workers over sector
+    blocks (the reference's policy, HubbardFunctions.jl:29,37).  Returns applies/s of the FULL
+    workload, extrapolated by algorithmic flops from a bounded sample of MPO levels."""
+    from threadpoolctl import threadpool_limits
+    chi_sample = min(args.chi, 16)
+    with threadpool_limits(limits=1):
+        plan, x = cpu_case(args, chi_sample)
+        t0 = time.perf_counter()
+        plan.apply(x, threads=threads)             # warm-up + duration estimate
+        one = time.perf_counter() - t0
+        n = max(1, min(20, int(budget_s / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            plan.apply(x, threads=threads)
+        dt = (time.perf_counter() - t0) / n
+    return plan.flops, dt, chi_sample, n
+
+
+def full_flops_from_sample(args, sample_flops, chi_sample, full_flops=None):
+    if full_flops is not None:
+        return full_flops
+    # levels are statistically alike: scale by the number of active (non-identity) levels
+    return sample_flops * (args.chi - 1.0) / (chi_sample - 1.0)
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = []
+    flops = chi_s = None
+    total = max(1, min(args.steps, 5))
+    for i in range(args.warmup if args.warmup < 2 else 1):
+        run_cpu_baseline(args, threads, 2.0)
+    for i in range(total):
+        flops, dt, chi_s, n = run_cpu_baseline(args, threads, max(2.0, args.cpu_seconds / total))
+        per_step.append(dt)
+    dt = sum(per_step) / len(per_step)
+    full = full_flops_from_sample(args, flops, chi_s)
+    value = 1.0 / (dt * full / flops)
+    sample = ("oracle HeffACPlan (numpy/OpenBLAS, BLAS threads=1, %d worker threads over blocks) on the same D=%d "
+              "spaces restricted to the first %d of %d MPO levels; applies/s scaled by algorithmic flops "
+              "(%.3g of %.3g)" % (threads, args.D, chi_s, args.chi, flops, full))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU restatement (oracle port), NOT MPSKit: Julia is not in the image (DESIGN.md)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from hubbardtn_b200 import device, synthetic
+    ctx = device.Context(local)
+    case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=rank % 4)
+    plan, x, y = case.plan, case.x, case.y
+    st = plan.stats
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (>=3) -------------------------------------------------------------------
+    W = max(args.warmup, 3)
+    plan.time(x, y, W)
+    # ---- FP64 peak of this GPU (roofline denominator; not in MEASURED_PEAKS.json) -----------
+    dmma_peak = ctx.probe_fp64_peak(0)
+    dfma_peak = ctx.probe_fp64_peak(1)
+    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    cublas_peak = best
+    del a, b
+    peak = max(dmma_peak, dfma_peak, cublas_peak)
+
+    # ---- timed region: exactly K applies, device time, max over ranks ----------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms = plan.time(x, y, args.steps)
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps / (ms_max * 1e-3)
+
+    # ---- per-stage times (dominant kernel = grouped_gemm_kernel, stages L and R) -----------
+    prof = plan.profile(x, y, reps=max(5, min(args.steps, 50)))
+    gemm_ms = prof["stage_L_ms"] + prof["stage_R_ms"]
+    achieved = st["flops"] / (gemm_ms * 1e-3) / 1e12
+
+    # ---- e2e: host buffers through the C ABI (pinned), H2D + D2H inside the timed region ----
+    xh = torch.from_numpy(case.x_host.copy()).pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    n = x.nelem
+    for _ in range(3):
+        plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)   # returns after the D2H copy completed
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(te.item())
+    checksum = float(yh.numpy().sum())
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"x_elems": n, "algorithmic_gflop_per_apply": st["flops"] / 1e9,
+                                             "executed_gflop_per_apply_padded": st["padded_flops"] / 1e9,
+                                             "workspace_MB": st["workspace_bytes"] / 1e6}),
+            "tflops_fp64": value * st["flops"] / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                    "checksum": checksum},
+            "gpu_launches": int(st["launches_per_apply"]) * args.steps,
+            "stages_ms": prof,
+            "roofline": {
+                "bound": "tensor", "kernel": "grouped_gemm_kernel (stage L + stage R launches)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured live on this GPU: max(DMMA.8x8x4 issue loop %.2f, DFMA loop %.2f, cuBLAS "
+                               "DGEMM 4096^3 %.2f) TFLOP/s; MEASURED_PEAKS.json has no FP64 entry"
+                               % (dmma_peak, dfma_peak, cublas_peak),
+                "whole_apply_frac": (value / world) * st["flops"] / 1e12 / peak,
+            },
+        }
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -----------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        flops_s, dt, chi_s, nrep = run_cpu_baseline(args, threads, args.cpu_seconds)
+        cpu_value = 1.0 / (dt * st["flops"] / flops_s)
+        line["cpu_baseline"] = {
+            "value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle HeffACPlan (numpy/OpenBLAS, BLAS threads=1, %d worker threads over blocks), same "
+                      "D=%d spaces, first %d of %d MPO levels, %d applies; scaled by algorithmic flops (%.3g of %.3g)"
+                      % (threads, args.D, chi_s, args.chi, nrep, flops_s, st["flops"])}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

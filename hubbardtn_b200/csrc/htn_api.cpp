@@ -1,0 +1,532 @@
+// C-ABI entry points: context, spaces, tensors, MPO, vector algebra (see include/htn.h).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <numeric>
+
+#include "htn_internal.hpp"
+
+using namespace htn;
+
+#define HTN_TRY try {
+#define HTN_CATCH(ctxptr)                                                                      \
+  }                                                                                            \
+  catch (const std::bad_alloc&) {                                                              \
+    if (ctxptr) (ctxptr)->err = "host allocation failed";                                      \
+    return HTN_ERR_OOM;                                                                        \
+  }                                                                                            \
+  catch (const std::exception& e) {                                                            \
+    if (ctxptr) (ctxptr)->err = e.what();                                                      \
+    return HTN_ERR_INVALID;                                                                    \
+  }                                                                                            \
+  catch (...) {                                                                                \
+    if (ctxptr) (ctxptr)->err = "unknown error";                                               \
+    return HTN_ERR_INVALID;                                                                    \
+  }
+
+static thread_local std::string g_noctx_err = "";
+
+static int32_t cuda_fail(htn_ctx* ctx, cudaError_t e, const char* what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  if (ctx) ctx->err = m;
+  return e == cudaErrorMemoryAllocation ? HTN_ERR_OOM : HTN_ERR_CUDA;
+}
+#define CU(ctx, call)                                          \
+  do {                                                         \
+    cudaError_t e_ = (call);                                   \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+  } while (0)
+
+extern "C" {
+
+int32_t htn_version(void) { return 100; }
+
+int32_t htn_ctx_create(int32_t device, htn_ctx** out) {
+  if (!out) return HTN_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_noctx_err = "no CUDA device available (libhtn has no CPU fallback)";
+    return HTN_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    g_noctx_err = "device index out of range";
+    return HTN_ERR_INVALID;
+  }
+  htn_ctx* c = new (std::nothrow) htn_ctx();
+  if (!c) return HTN_ERR_OOM;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_noctx_err = "cudaSetDevice/cudaStreamCreate failed";
+    delete c;
+    return HTN_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    g_noctx_err = "libhtn is built for sm_100a only";
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return HTN_ERR_NO_DEVICE;
+  }
+  cudaMallocHost(&c->red_host, 64 * sizeof(double));
+  *out = c;
+  return HTN_OK;
+}
+
+int32_t htn_ctx_destroy(htn_ctx* ctx) {
+  if (!ctx) return HTN_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->red) cudaFree(ctx->red);
+  if (ctx->red_host) cudaFreeHost(ctx->red_host);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return HTN_OK;
+}
+
+const char* htn_last_error_string(htn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
+
+int32_t htn_ctx_synchronize(htn_ctx* ctx) {
+  if (!ctx) return HTN_ERR_INVALID;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return HTN_OK;
+}
+
+// ---- spaces ---------------------------------------------------------------------------
+int32_t htn_space_create(htn_ctx* ctx, int32_t sym, int32_t nsec, const int32_t* labels, const int32_t* mult,
+                         htn_space** out) {
+  if (!ctx || !out || nsec < 0 || (nsec > 0 && (!labels || !mult))) return HTN_ERR_INVALID;
+  if (sym != HTN_SYM_SU2U1 && sym != HTN_SYM_U1U1) return ctx->fail(HTN_ERR_INVALID, "unknown symmetry kind");
+  HTN_TRY
+  std::vector<std::pair<Sector, int32_t>> v;
+  for (int i = 0; i < nsec; ++i) {
+    Sector s{labels[3 * i], labels[3 * i + 1], labels[3 * i + 2]};
+    if ((s.p != 0 && s.p != 1) || (sym == HTN_SYM_SU2U1 && s.q < 0))
+      return ctx->fail(HTN_ERR_INVALID, "invalid sector label");
+    if (mult[i] < 0) return ctx->fail(HTN_ERR_INVALID, "negative multiplicity");
+    if (mult[i] == 0) continue;
+    for (auto& pr : v)
+      if (pr.first == s) return ctx->fail(HTN_ERR_INVALID, "duplicate sector in space");
+    v.push_back({s, mult[i]});
+  }
+  std::sort(v.begin(), v.end(), [sym](auto& a, auto& b) { return canonical_less(sym, a.first, b.first); });
+  htn_space* sp = new htn_space();
+  sp->ctx = ctx;
+  sp->sym = sym;
+  for (auto& pr : v) {
+    sp->sec.push_back(pr.first);
+    sp->mult.push_back(pr.second);
+  }
+  *out = sp;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_space_destroy(htn_space* s) {
+  delete s;
+  return HTN_OK;
+}
+
+int32_t htn_space_info(const htn_space* s, int32_t* nsec, int32_t* labels, int32_t* mult) {
+  if (!s) return HTN_ERR_INVALID;
+  if (nsec) *nsec = (int32_t)s->sec.size();
+  for (size_t i = 0; i < s->sec.size(); ++i) {
+    if (labels) {
+      labels[3 * i] = s->sec[i].p;
+      labels[3 * i + 1] = s->sec[i].q;
+      labels[3 * i + 2] = s->sec[i].n;
+    }
+    if (mult) mult[i] = s->mult[i];
+  }
+  return HTN_OK;
+}
+
+int32_t htn_legs_create(htn_ctx* ctx, int32_t sym, int32_t n, const int32_t* labels, htn_legs** out) {
+  if (!ctx || !out || n < 0 || (n > 0 && !labels)) return HTN_ERR_INVALID;
+  if (sym != HTN_SYM_SU2U1 && sym != HTN_SYM_U1U1) return ctx->fail(HTN_ERR_INVALID, "unknown symmetry kind");
+  HTN_TRY
+  htn_legs* l = new htn_legs();
+  l->ctx = ctx;
+  l->sym = sym;
+  for (int i = 0; i < n; ++i) l->sec.push_back(Sector{labels[3 * i], labels[3 * i + 1], labels[3 * i + 2]});
+  *out = l;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_legs_destroy(htn_legs* l) {
+  delete l;
+  return HTN_OK;
+}
+
+// ---- tensors --------------------------------------------------------------------------
+static int32_t finalize_tensor(htn_tensor* t) {
+  htn_ctx* ctx = t->ctx;
+  int64_t off = 0, hoff = 0;
+  for (size_t i = 0; i < t->blocks.size(); ++i) {
+    Block& b = t->blocks[i];
+    b.ld = even_up(b.cols);
+    b.off = off;
+    b.hoff = hoff;
+    off = align_up(off + (int64_t)b.rows * b.ld, 16);
+    hoff += (int64_t)b.rows * b.cols;
+    t->index[std::make_tuple(b.lab[0], b.lab[1], b.lab[2])] = (int)i;
+  }
+  t->dsize = std::max<int64_t>(off, 16);
+  t->hsize = hoff;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMalloc(&t->d, t->dsize * sizeof(double)));
+  CU(ctx, cudaMemsetAsync(t->d, 0, t->dsize * sizeof(double), ctx->stream));
+  // device block table + row-chunk table
+  std::vector<DevBlock> db(t->blocks.size());
+  std::vector<int> chunks;
+  for (size_t i = 0; i < t->blocks.size(); ++i) {
+    const Block& b = t->blocks[i];
+    db[i] = DevBlock{b.off, b.hoff, b.rows, b.cols, b.ld, b.weight};
+    int rows_per = std::max(1, 4096 / std::max(1, b.ld));
+    for (int r0 = 0; r0 < b.rows; r0 += rows_per) {
+      chunks.push_back((int)i);
+      chunks.push_back(r0);
+      chunks.push_back(std::min(rows_per, b.rows - r0));
+    }
+  }
+  t->nchunks = (int)chunks.size() / 3;
+  if (!db.empty()) {
+    CU(ctx, cudaMalloc(&t->dblocks, db.size() * sizeof(DevBlock)));
+    CU(ctx, cudaMemcpyAsync(t->dblocks, db.data(), db.size() * sizeof(DevBlock), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMalloc(&t->dchunks, chunks.size() * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(t->dchunks, chunks.data(), chunks.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  return HTN_OK;
+}
+
+static htn_tensor* new_tensor(htn_ctx* ctx, int kind, int sym) {
+  htn_tensor* t = new htn_tensor();
+  t->ctx = ctx;
+  t->kind = kind;
+  t->sym = sym;
+  t->s0.ctx = t->s1.ctx = ctx;
+  t->s0.sym = t->s1.sym = sym;
+  t->legs.ctx = ctx;
+  t->legs.sym = sym;
+  return t;
+}
+
+int32_t htn_tensor_create_mps(htn_ctx* ctx, const htn_space* Vl, const htn_legs* P, const htn_space* Vr,
+                              htn_tensor** out) {
+  if (!ctx || !Vl || !P || !Vr || !out) return HTN_ERR_INVALID;
+  if (Vl->sym != P->sym || Vr->sym != P->sym) return ctx->fail(HTN_ERR_INVALID, "symmetry kinds differ");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, HTN_T_MPS, P->sym);
+  t->s0 = *Vl;
+  t->s1 = *Vr;
+  t->legs = *P;
+  // canonical block order: coupled sector r, then s, then l (oracle/tensors.py:mps_keys)
+  for (int r = 0; r < (int)Vr->sec.size(); ++r)
+    for (int s = 0; s < (int)P->sec.size(); ++s)
+      for (int l = 0; l < (int)Vl->sec.size(); ++l)
+        if (allowed(t->sym, Vl->sec[l], P->sec[s], Vr->sec[r])) {
+          Block b{};
+          b.lab[0] = l;
+          b.lab[1] = s;
+          b.lab[2] = r;
+          b.rows = Vl->mult[l];
+          b.cols = Vr->mult[r];
+          b.weight = sdim(t->sym, Vr->sec[r]);
+          t->blocks.push_back(b);
+        }
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_tensor_create_bond(htn_ctx* ctx, const htn_space* V, htn_tensor** out) {
+  if (!ctx || !V || !out) return HTN_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, HTN_T_BOND, V->sym);
+  t->s0 = *V;
+  t->s1 = *V;
+  for (int c = 0; c < (int)V->sec.size(); ++c) {
+    Block b{};
+    b.lab[0] = b.lab[1] = b.lab[2] = c;
+    b.rows = b.cols = V->mult[c];
+    b.weight = sdim(t->sym, V->sec[c]);
+    t->blocks.push_back(b);
+  }
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, const htn_legs* M,
+                              int32_t identity_level, htn_tensor** out) {
+  if (!ctx || !V || !M || !out) return HTN_ERR_INVALID;
+  if (side != HTN_SIDE_LEFT && side != HTN_SIDE_RIGHT) return ctx->fail(HTN_ERR_INVALID, "bad side");
+  if (V->sym != M->sym) return ctx->fail(HTN_ERR_INVALID, "symmetry kinds differ");
+  if (identity_level >= (int)M->sec.size()) return ctx->fail(HTN_ERR_INVALID, "identity_level out of range");
+  if (identity_level >= 0) {
+    Sector s = M->sec[identity_level];
+    if (s.p != 0 || s.q != 0 || s.n != 0) return ctx->fail(HTN_ERR_INVALID, "identity level must carry the trivial sector");
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, side == HTN_SIDE_LEFT ? HTN_T_ENVL : HTN_T_ENVR, V->sym);
+  t->s0 = *V;
+  t->s1 = *V;
+  t->legs = *M;
+  t->identity_level = identity_level;
+  const int nv = (int)V->sec.size();
+  // canonical order: level, then first bond index, then second (oracle/tensors.py:envl_keys/envr_keys)
+  for (int a = 0; a < (int)M->sec.size(); ++a)
+    for (int i = 0; i < nv; ++i)
+      for (int j = 0; j < nv; ++j) {
+        // left : (a, l'=i, l=j), l' in a(x)l ; right: (b, r=i, r'=j), r' in b(x)r
+        bool ok = side == HTN_SIDE_LEFT ? allowed(t->sym, M->sec[a], V->sec[j], V->sec[i])
+                                        : allowed(t->sym, M->sec[a], V->sec[i], V->sec[j]);
+        if (!ok) continue;
+        Block b{};
+        b.lab[0] = a;
+        b.lab[1] = i;
+        b.lab[2] = j;
+        b.rows = V->mult[i];
+        b.cols = V->mult[j];
+        b.weight = sdim(t->sym, V->sec[side == HTN_SIDE_LEFT ? i : j]);
+        t->blocks.push_back(b);
+      }
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_tensor_create_like(const htn_tensor* src, htn_tensor** out) {
+  if (!src || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = src->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, src->kind, src->sym);
+  t->s0 = src->s0;
+  t->s1 = src->s1;
+  t->legs = src->legs;
+  t->identity_level = src->identity_level;
+  t->blocks = src->blocks;
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_tensor_destroy(htn_tensor* t) {
+  if (!t) return HTN_OK;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->d) cudaFree(t->d);
+  if (t->dblocks) cudaFree(t->dblocks);
+  if (t->dchunks) cudaFree(t->dchunks);
+  delete t;
+  return HTN_OK;
+}
+
+int32_t htn_tensor_blocktable(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels,
+                              int32_t* rows, int32_t* cols, int64_t* offsets) {
+  if (!t) return HTN_ERR_INVALID;
+  if (nblocks) *nblocks = (int32_t)t->blocks.size();
+  if (nelem) *nelem = t->hsize;
+  for (size_t i = 0; i < t->blocks.size(); ++i) {
+    const Block& b = t->blocks[i];
+    if (labels) {
+      labels[3 * i] = b.lab[0];
+      labels[3 * i + 1] = b.lab[1];
+      labels[3 * i + 2] = b.lab[2];
+    }
+    if (rows) rows[i] = b.rows;
+    if (cols) cols[i] = b.cols;
+    if (offsets) offsets[i] = b.hoff;
+  }
+  return HTN_OK;
+}
+
+static int32_t ensure_stage(htn_ctx* ctx, int64_t n) {
+  if (ctx->stage_cap >= n) return HTN_OK;
+  if (ctx->stage) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_cap = 0;
+  }
+  int64_t cap = std::max<int64_t>(n, 1 << 20);
+  CU(ctx, cudaMalloc(&ctx->stage, cap * sizeof(double)));
+  ctx->stage_cap = cap;
+  return HTN_OK;
+}
+
+int32_t htn_upload_locked(htn_tensor* t, const double* host, int64_t nelem) {
+  htn_ctx* ctx = t->ctx;
+  if (nelem != t->hsize) return ctx->fail(HTN_ERR_SHAPE, "upload: element count does not match the block table");
+  if (nelem == 0) return HTN_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int32_t rc = ensure_stage(ctx, nelem);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(ctx->stage, host, nelem * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  launch_pack(t->dblocks, t->dchunks, t->nchunks, ctx->stage, t->d, ctx->stream);
+  CU(ctx, cudaGetLastError());
+  return HTN_OK;
+}
+
+int32_t htn_download_locked(const htn_tensor* t, double* host, int64_t nelem) {
+  htn_ctx* ctx = t->ctx;
+  if (nelem != t->hsize) return ctx->fail(HTN_ERR_SHAPE, "download: element count does not match the block table");
+  if (nelem == 0) return HTN_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int32_t rc = ensure_stage(ctx, nelem);
+  if (rc) return rc;
+  launch_unpack(t->dblocks, t->dchunks, t->nchunks, t->d, ctx->stage, ctx->stream);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(host, ctx->stage, nelem * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return HTN_OK;
+}
+
+int32_t htn_tensor_upload(htn_tensor* t, const double* host, int64_t nelem) {
+  if (!t || (!host && nelem > 0)) return HTN_ERR_INVALID;
+  std::lock_guard<std::mutex> g(t->ctx->mu);
+  int32_t rc = htn_upload_locked(t, host, nelem);
+  if (rc) return rc;
+  // the host buffer belongs to the caller: do not return before the copy has read it
+  CU(t->ctx, cudaStreamSynchronize(t->ctx->stream));
+  return HTN_OK;
+}
+
+int32_t htn_tensor_download(const htn_tensor* t, double* host, int64_t nelem) {
+  if (!t || (!host && nelem > 0)) return HTN_ERR_INVALID;
+  std::lock_guard<std::mutex> g(t->ctx->mu);
+  return htn_download_locked(t, host, nelem);
+}
+
+// ---- MPO ------------------------------------------------------------------------------
+int32_t htn_mpo_create(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, const htn_legs* Mr, int32_t nnz,
+                       const int32_t* idx, const int32_t* clabel, const double* val, htn_mpo** out) {
+  if (!ctx || !Ml || !P || !Mr || !out || nnz < 0 || (nnz > 0 && (!idx || !clabel || !val))) return HTN_ERR_INVALID;
+  if (Ml->sym != P->sym || Mr->sym != P->sym) return ctx->fail(HTN_ERR_INVALID, "symmetry kinds differ");
+  HTN_TRY
+  htn_mpo* w = new htn_mpo();
+  w->ctx = ctx;
+  w->sym = P->sym;
+  w->Ml = *Ml;
+  w->P = *P;
+  w->Mr = *Mr;
+  for (int i = 0; i < nnz; ++i) {
+    MpoEntry e{idx[4 * i], idx[4 * i + 1], idx[4 * i + 2], idx[4 * i + 3],
+               Sector{clabel[3 * i], clabel[3 * i + 1], clabel[3 * i + 2]}, val[i]};
+    bool in_range = e.a >= 0 && e.a < (int)Ml->sec.size() && e.b >= 0 && e.b < (int)Mr->sec.size() && e.sp >= 0 &&
+                    e.sp < (int)P->sec.size() && e.s >= 0 && e.s < (int)P->sec.size();
+    if (!in_range) {
+      delete w;
+      return ctx->fail(HTN_ERR_INVALID, "MPO entry index out of range");
+    }
+    if (!allowed(w->sym, Ml->sec[e.a], P->sec[e.sp], e.c) || !allowed(w->sym, P->sec[e.s], Mr->sec[e.b], e.c)) {
+      delete w;
+      return ctx->fail(HTN_ERR_INVALID, "MPO entry violates the fusion rules");
+    }
+    w->entries.push_back(e);
+  }
+  *out = w;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_mpo_destroy(htn_mpo* w) {
+  delete w;
+  return HTN_OK;
+}
+
+// ---- vector algebra -------------------------------------------------------------------
+static bool same_structure(const htn_tensor* x, const htn_tensor* y) {
+  if (x->kind != y->kind || x->sym != y->sym || x->blocks.size() != y->blocks.size() || x->dsize != y->dsize)
+    return false;
+  for (size_t i = 0; i < x->blocks.size(); ++i) {
+    const Block &a = x->blocks[i], &b = y->blocks[i];
+    if (a.lab[0] != b.lab[0] || a.lab[1] != b.lab[1] || a.lab[2] != b.lab[2] || a.rows != b.rows || a.cols != b.cols)
+      return false;
+  }
+  return true;
+}
+
+bool htn_same_structure(const htn_tensor* x, const htn_tensor* y) { return same_structure(x, y); }
+
+int32_t htn_tensor_dot(const htn_tensor* x, const htn_tensor* y, double* out) {
+  if (!x || !y || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = x->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!same_structure(x, y)) return ctx->fail(HTN_ERR_SHAPE, "dot: tensors differ in structure");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (x->nchunks == 0) {
+    *out = 0.0;
+    return HTN_OK;
+  }
+  if (ctx->red_cap < x->nchunks + 1) {
+    if (ctx->red) cudaFree(ctx->red);
+    ctx->red_cap = std::max<int64_t>(x->nchunks + 1, 4096);
+    CU(ctx, cudaMalloc(&ctx->red, ctx->red_cap * sizeof(double)));
+  }
+  launch_dot(x->dblocks, x->dchunks, x->nchunks, x->d, y->d, ctx->red + 1, ctx->red, ctx->stream);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(ctx->red_host, ctx->red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = ctx->red_host[0];
+  return HTN_OK;
+}
+
+int32_t htn_tensor_axpby(double alpha, const htn_tensor* x, double beta, htn_tensor* y) {
+  if (!x || !y) return HTN_ERR_INVALID;
+  htn_ctx* ctx = x->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!same_structure(x, y)) return ctx->fail(HTN_ERR_SHAPE, "axpby: tensors differ in structure");
+  CU(ctx, cudaSetDevice(ctx->device));
+  launch_axpby(alpha, x->d, beta, y->d, x->dsize, ctx->stream);
+  CU(ctx, cudaGetLastError());
+  return HTN_OK;
+}
+
+// ---- test hooks -----------------------------------------------------------------------
+int32_t htn_network_coefficient(int32_t sym, const int32_t* L, double* out) {
+  if (!L || !out) return HTN_ERR_INVALID;
+  auto S = [&](int i) { return Sector{L[3 * i], L[3 * i + 1], L[3 * i + 2]}; };
+  *out = network(sym, S(0), S(1), S(2), S(3), S(4), S(5), S(6), S(7), S(8));
+  return HTN_OK;
+}
+
+int32_t htn_probe_fp64_peak(htn_ctx* ctx, int32_t which, double* tflops) {
+  if (!ctx || !tflops) return HTN_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  *tflops = probe_fp64(which, ctx->sm_count, ctx->stream);
+  CU(ctx, cudaGetLastError());
+  return HTN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// sm_100a device kernels of the H_eff hot path.
+//
+//  * grouped_gemm_kernel : persistent grouped FP64 tensor-core GEMM with K-segments.  Every
+//    work item is one <=64x64 output tile of one symmetry-sector block; its K loop runs over
+//    a list of segments (A_seg, B_seg, K_seg, coef), i.e. over (MPO level, sector) pairs.
+//    Replaces the per-coupled-sector BLAS `zgemm` calls TensorKit issues for `∂AC`
+//    (MKL_jll 2025.0.1 zgemm, Manifest.toml:716).  FP64 has no
+//    tcgen05/UMMA kind on sm_100a; the tensor path is DMMA.8x8x4 (mma.sync.m8n8k4.f64),
+//    operands staged global -> shared with 16-byte cp.async in a 3-stage ring.
+//  * mix_kernel : stage W, block-wise linear combinations U = sum coef * T with the SU(2)
+//    recoupling coefficients (the O(D^2) part of the apply).
+//  * pack / unpack / dot / axpby : arena <-> packed host layout and Krylov vector algebra
+//    with the TensorKit inner product (weights = quantum dimension of the coupled sector).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "htn_internal.hpp"
+
+namespace htn {
+
+// ------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------
+// grouped GEMM
+// ------------------------------------------------------------------------------------
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 128;
+constexpr int LDAS = BK + 4;  // 20 doubles: (g*20 + t) mod 16 distinct over a half warp
+constexpr int LDBS = BN + 4;  // 68 doubles: (t*68 + g) mod 16 distinct over a half warp
+constexpr int A_STAGE = BM * LDAS;
+constexpr int B_STAGE = BK * LDBS;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+
+struct SegCursor {
+  int seg;  // current segment
+  int k0;   // chunk start inside the segment
+};
+
+__global__ void __launch_bounds__(NTHREADS, 4)
+grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
+                    Bases bases) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const GemmItem item = items[it];
+    const int mt = item.mt, nt = item.nt;
+    // atoms this warp owns (warp-uniform)
+    int mi = (mt - wm * 32 + 7) >> 3;
+    mi = mi < 0 ? 0 : (mi > 4 ? 4 : mi);
+    int nj = (nt - wn * 32 + 7) >> 3;
+    nj = nj < 0 ? 0 : (nj > 4 ? 4 : nj);
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // ---- producer: issue the loads of one chunk into stage `st` -----------------------
+    SegCursor pc{item.seg_begin, 0};
+    GemmSeg pseg = segs[pc.seg];
+    auto issue = [&](int st) {
+      const double* Ag = resolve(pseg.a_off, pseg.a_base, bases);
+      const double* Bg = resolve(pseg.b_off, pseg.b_base, bases);
+      const int K = pseg.K, k0 = pc.k0;
+      double* as = As + st * A_STAGE;
+      double* bs = Bs + st * B_STAGE;
+#pragma unroll
+      for (int q = 0; q < (BM * BK / 2) / NTHREADS; ++q) {  // 4
+        int sid = tid + q * NTHREADS;
+        int row = sid >> 3, sg = sid & 7;
+        int k = k0 + sg * 2;
+        int bytes = (row < mt) ? (K - k) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? (Ag + (long long)row * pseg.lda + k) : Ag;
+        cp_async16(as + row * LDAS + sg * 2, src, bytes);
+      }
+#pragma unroll
+      for (int q = 0; q < (BK * BN / 2) / NTHREADS; ++q) {  // 4
+        int sid = tid + q * NTHREADS;
+        int row = sid >> 5, sg = sid & 31;
+        int k = k0 + row;
+        int bytes = (k < K) ? (nt - sg * 2) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? (Bg + (long long)k * pseg.ldb + sg * 2) : Bg;
+        cp_async16(bs + row * LDBS + sg * 2, src, bytes);
+      }
+      // advance the producer cursor
+      pc.k0 += BK;
+      if (pc.k0 >= K) {
+        pc.k0 = 0;
+        pc.seg++;
+        if (pc.seg < item.seg_end) pseg = segs[pc.seg];
+      }
+    };
+
+    const int nchunks = item.nchunks;
+    int issued = 0;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (issued < nchunks) {
+        issue(s);
+        ++issued;
+      }
+      cp_async_commit();
+    }
+
+    // ---- consumer ---------------------------------------------------------------------
+    SegCursor cc{item.seg_begin, 0};
+    int cK = segs[cc.seg].K;
+    double coef = segs[cc.seg].coef;
+    for (int c = 0; c < nchunks; ++c) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      if (issued < nchunks) {
+        issue((c + STAGES - 1) % STAGES);
+        ++issued;
+      }
+      cp_async_commit();
+
+      const double* as = As + (c % STAGES) * A_STAGE + (wm * 32 + g) * LDAS + t;
+      const double* bs = Bs + (c % STAGES) * B_STAGE + t * LDBS + wn * 32 + g;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (i < mi) ? as[i * 8 * LDAS + kk * 4] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = (j < nj) ? bs[kk * 4 * LDBS + j * 8] : 0.0;
+        if (coef != 1.0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] *= coef;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < mi) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < nj) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+          }
+        }
+      }
+      // advance the consumer cursor
+      cc.k0 += BK;
+      if (cc.k0 >= cK) {
+        cc.k0 = 0;
+        cc.seg++;
+        if (cc.seg < item.seg_end) {
+          cK = segs[cc.seg].K;
+          coef = segs[cc.seg].coef;
+        }
+      }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue ---------------------------------------------------------------------
+    double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
+    const int ldc = item.ldc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int row = wm * 32 + i * 8 + g;
+      if (i < mi && row < mt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int col = wn * 32 + j * 8 + 2 * t;
+          if (j < nj && col < nt) {
+            double* p = C + (long long)row * ldc + col;
+            if (col + 1 < nt) {
+              double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+              if (item.beta) {
+                double2 o = *reinterpret_cast<double2*>(p);
+                v.x += o.x;
+                v.y += o.y;
+              }
+              *reinterpret_cast<double2*>(p) = v;
+            } else {
+              double v = acc[i][j][0];
+              if (item.beta) v += *p;
+              *p = v;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // all warps done with smem before the next item's prologue refills it
+  }
+}
+
+int gemm_max_ctas_per_sm() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, grouped_gemm_kernel, NTHREADS, GEMM_SMEM_BYTES);
+  cached = n > 0 ? n : 1;
+  return cached;
+}
+
+void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, Bases bases, int grid,
+                 cudaStream_t st) {
+  if (nitems <= 0) return;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    attr = true;
+  }
+  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases);
+}
+
+// ------------------------------------------------------------------------------------
+// stage W: block linear combinations
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ tg, const MixSrc* __restrict__ src,
+                                                  const MixChunk* __restrict__ chunks, Bases bases) {
+  const MixChunk ch = chunks[blockIdx.x];
+  const MixTarget T = tg[ch.target];
+  double* dst = const_cast<double*>(resolve(T.off, T.base, bases));
+  const int end = min(T.nelem, ch.elem0 + MIX_CHUNK);
+  // all blocks have even ld and 16-byte aligned offsets: work in double2
+  for (int e = ch.elem0 + 2 * threadIdx.x; e < end; e += 2 * blockDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int s = T.src_begin; s < T.src_end; ++s) {
+      const MixSrc S = src[s];
+      const double2 v = *reinterpret_cast<const double2*>(resolve(S.off, S.base, bases) + e);
+      acc.x = fma(S.coef, v.x, acc.x);
+      acc.y = fma(S.coef, v.y, acc.y);
+    }
+    *reinterpret_cast<double2*>(dst + e) = acc;
+  }
+}
+
+void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, Bases bases,
+                cudaStream_t st) {
+  if (nchunks <= 0) return;
+  mix_kernel<<<nchunks, 256, 0, st>>>(tg, src, chunks, bases);
+}
+
+// ------------------------------------------------------------------------------------
+// pack / unpack (packed host layout <-> padded arena), dot, axpby
+// chunk table: int3-like triples (block, row0, nrows)
+// ------------------------------------------------------------------------------------
+__global__ void pack_kernel(const DevBlock* __restrict__ blocks, const int* __restrict__ chunks,
+                            const double* __restrict__ packed, double* __restrict__ padded) {
+  const int b = chunks[3 * blockIdx.x], r0 = chunks[3 * blockIdx.x + 1], nr = chunks[3 * blockIdx.x + 2];
+  const DevBlock B = blocks[b];
+  const int n = nr * B.cols;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    int r = r0 + e / B.cols, c = e % B.cols;
+    padded[B.off + (long long)r * B.ld + c] = packed[B.hoff + (long long)r * B.cols + c];
+  }
+}
+
+__global__ void unpack_kernel(const DevBlock* __restrict__ blocks, const int* __restrict__ chunks,
+                              const double* __restrict__ padded, double* __restrict__ packed) {
+  const int b = chunks[3 * blockIdx.x], r0 = chunks[3 * blockIdx.x + 1], nr = chunks[3 * blockIdx.x + 2];
+  const DevBlock B = blocks[b];
+  const int n = nr * B.cols;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    int r = r0 + e / B.cols, c = e % B.cols;
+    packed[B.hoff + (long long)r * B.cols + c] = padded[B.off + (long long)r * B.ld + c];
+  }
+}
+
+void launch_pack(const DevBlock* blocks, const int* chunks, int nchunks, const double* packed, double* padded,
+                 cudaStream_t st) {
+  if (nchunks > 0) pack_kernel<<<nchunks, 256, 0, st>>>(blocks, chunks, packed, padded);
+}
+void launch_unpack(const DevBlock* blocks, const int* chunks, int nchunks, const double* padded, double* packed,
+                   cudaStream_t st) {
+  if (nchunks > 0) unpack_kernel<<<nchunks, 256, 0, st>>>(blocks, chunks, padded, packed);
+}
+
+// deterministic two-pass weighted dot: partial[chunk] then a single-CTA ordered sum
+__global__ void dot_partial_kernel(const DevBlock* __restrict__ blocks, const int* __restrict__ chunks,
+                                   const double* __restrict__ x, const double* __restrict__ y,
+                                   double* __restrict__ partial) {
+  const int b = chunks[3 * blockIdx.x], r0 = chunks[3 * blockIdx.x + 1], nr = chunks[3 * blockIdx.x + 2];
+  const DevBlock B = blocks[b];
+  // rows are padded with zeros, so the flat padded range can be reduced directly
+  const long long base = B.off + (long long)r0 * B.ld;
+  const int n = nr * B.ld;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) acc = fma(x[base + e], y[base + e], acc);
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[w];
+    partial[blockIdx.x] = s * B.weight;
+  }
+}
+
+__global__ void dot_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) acc += partial[e];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+void launch_dot(const DevBlock* blocks, const int* chunks, int nchunks, const double* x, const double* y,
+                double* partial, double* out, cudaStream_t st) {
+  dot_partial_kernel<<<nchunks, 256, 0, st>>>(blocks, chunks, x, y, partial);
+  dot_final_kernel<<<1, 256, 0, st>>>(partial, nchunks, out);
+}
+
+__global__ void axpby_kernel(double alpha, const double* __restrict__ x, double beta, double* __restrict__ y,
+                             long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = (beta == 0.0) ? alpha * x[i] : fma(alpha, x[i], beta * y[i]);
+}
+
+void launch_axpby(double alpha, const double* x, double beta, double* y, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  axpby_kernel<<<grid, 256, 0, st>>>(alpha, x, beta, y, n);
+}
+
+// ------------------------------------------------------------------------------------
+// FP64 peak probes (roofline denominators measured on the box)
+// ------------------------------------------------------------------------------------
+template <int ITER>
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double* out) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+template <int ITER>
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double* out) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * threadIdx.x;
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 123.456) out[0] = s;
+}
+
+double probe_fp64(int which, int sm_count, cudaStream_t st) {
+  constexpr int ITER = 4096;
+  double* d = nullptr;
+  cudaMalloc(&d, 8);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    if (which == 0)
+      probe_dmma_kernel<ITER><<<grid, threads, 0, st>>>(d);
+    else
+      probe_dfma_kernel<ITER><<<grid, threads, 0, st>>>(d);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = which == 0 ? (double)grid * (threads / 32) * ITER * 8.0 * (2.0 * 8 * 8 * 4)
+                              : (double)grid * threads * ITER * 16.0 * 2.0;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
+}  // namespace htn

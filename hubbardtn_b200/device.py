@@ -1,0 +1,271 @@
+"""Host-side object layer over the C ABI (numpy in / numpy out, no arithmetic here).
+
+Mirrors the objects HubbardTN hands to MPSKit at the drop-in boundary
+(src/HubbardFunctions.jl:1010-1027): graded spaces (`Vect[I](...)`, HF:248-251), site
+tensors of an `InfiniteMPS`, the per-site MPO tensor of an `InfiniteMPOHamiltonian`, the
+environments, and the effective-Hamiltonian operator.  All numbers live on the GPU in the
+library's arena; this layer only moves packed host arrays across the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib
+
+
+def _i32arr(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Context:
+    """One CUDA device + stream + staging buffers (htn_ctx)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.htn_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise L.HtnError(rc, L.last_error(None))
+        self.h = h
+        self.device = device
+
+    def synchronize(self):
+        L.check(lib.htn_ctx_synchronize(self.h), self.h)
+
+    def probe_fp64_peak(self, which: int = 0) -> float:
+        out = C.c_double()
+        L.check(lib.htn_probe_fp64_peak(self.h, which, C.byref(out)), self.h)
+        return out.value
+
+    def close(self):
+        if self.h:
+            lib.htn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Space:
+    """Graded bond space: {sector label (p,q,n): multiplicity}; stored in canonical order."""
+
+    def __init__(self, ctx: Context, sym: int, mults: dict):
+        self.ctx, self.sym = ctx, sym
+        labels = [tuple(k) for k in mults.keys()]
+        lab, plab = _i32arr(np.array(labels, dtype=np.int32).reshape(-1, 3))
+        mul, pmul = _i32arr(list(mults.values()))
+        h = C.c_void_p()
+        L.check(lib.htn_space_create(ctx.h, sym, len(labels), plab, pmul, C.byref(h)), ctx.h)
+        self.h = h
+        n = C.c_int32()
+        L.check(lib.htn_space_info(h, C.byref(n), None, None), ctx.h)
+        lab2 = np.zeros((n.value, 3), dtype=np.int32)
+        mul2 = np.zeros(n.value, dtype=np.int32)
+        L.check(lib.htn_space_info(h, C.byref(n), lab2.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   mul2.ctypes.data_as(C.POINTER(C.c_int32))), ctx.h)
+        self.sectors = [tuple(int(v) for v in row) for row in lab2]
+        self.mult = [int(v) for v in mul2]
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.htn_space_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Legs:
+    """Ordered single multiplets: the physical space or the MPO virtual levels."""
+
+    def __init__(self, ctx: Context, sym: int, sectors):
+        self.ctx, self.sym = ctx, sym
+        self.sectors = [tuple(int(v) for v in s) for s in sectors]
+        lab, plab = _i32arr(np.array(self.sectors, dtype=np.int32).reshape(-1, 3))
+        h = C.c_void_p()
+        L.check(lib.htn_legs_create(ctx.h, sym, len(self.sectors), plab, C.byref(h)), ctx.h)
+        self.h = h
+
+    def __len__(self):
+        return len(self.sectors)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.htn_legs_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Tensor:
+    """Block-sparse tensor resident in HBM.  `table` = list of (labels, rows, cols, offset)
+    describing the packed host layout used by upload()/download()."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+        nb, ne = C.c_int32(), C.c_int64()
+        L.check(lib.htn_tensor_blocktable(handle, C.byref(nb), C.byref(ne), None, None, None, None), ctx.h)
+        self.nblocks, self.nelem = nb.value, ne.value
+        lab = np.zeros((self.nblocks, 3), dtype=np.int32)
+        rows = np.zeros(self.nblocks, dtype=np.int32)
+        cols = np.zeros(self.nblocks, dtype=np.int32)
+        offs = np.zeros(self.nblocks, dtype=np.int64)
+        pi32 = C.POINTER(C.c_int32)
+        L.check(lib.htn_tensor_blocktable(handle, C.byref(nb), C.byref(ne), lab.ctypes.data_as(pi32),
+                                          rows.ctypes.data_as(pi32), cols.ctypes.data_as(pi32),
+                                          offs.ctypes.data_as(C.POINTER(C.c_int64))), ctx.h)
+        self.labels, self.rows, self.cols, self.offsets = lab, rows, cols, offs
+
+    # -- constructors --------------------------------------------------------------------
+    @staticmethod
+    def mps(ctx, Vl: Space, P: Legs, Vr: Space) -> "Tensor":
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_mps(ctx.h, Vl.h, P.h, Vr.h, C.byref(h)), ctx.h)
+        return Tensor(ctx, h)
+
+    @staticmethod
+    def bond(ctx, V: Space) -> "Tensor":
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_bond(ctx.h, V.h, C.byref(h)), ctx.h)
+        return Tensor(ctx, h)
+
+    @staticmethod
+    def env(ctx, side: int, V: Space, M: Legs, identity_level: int = -1) -> "Tensor":
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_env(ctx.h, side, V.h, M.h, identity_level, C.byref(h)), ctx.h)
+        return Tensor(ctx, h)
+
+    def like(self) -> "Tensor":
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_like(self.h, C.byref(h)), self.ctx.h)
+        return Tensor(self.ctx, h)
+
+    # -- data movement -------------------------------------------------------------------
+    def upload(self, packed: np.ndarray):
+        packed = np.ascontiguousarray(packed, dtype=np.float64)
+        L.check(lib.htn_tensor_upload(self.h, packed.ctypes.data, packed.size), self.ctx.h)
+        return self
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.nelem, dtype=np.float64)
+        L.check(lib.htn_tensor_download(self.h, out.ctypes.data, out.size), self.ctx.h)
+        return out
+
+    def block_views(self, packed: np.ndarray) -> dict:
+        """{(label0,label1,label2): 2-D view into `packed`}."""
+        out = {}
+        for i in range(self.nblocks):
+            o, r, c = int(self.offsets[i]), int(self.rows[i]), int(self.cols[i])
+            out[tuple(int(v) for v in self.labels[i])] = packed[o:o + r * c].reshape(r, c)
+        return out
+
+    # -- vector algebra ------------------------------------------------------------------
+    def dot(self, other: "Tensor") -> float:
+        out = C.c_double()
+        L.check(lib.htn_tensor_dot(self.h, other.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def axpby(self, alpha: float, x: "Tensor", beta: float):
+        """self = alpha * x + beta * self"""
+        L.check(lib.htn_tensor_axpby(alpha, x.h, beta, self.h), self.ctx.h)
+        return self
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.htn_tensor_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Mpo:
+    """One site of the MPO Hamiltonian in reduced form: entries {(a,s',s,b,c): w}."""
+
+    def __init__(self, ctx: Context, Ml: Legs, P: Legs, Mr: Legs, entries: dict):
+        self.ctx, self.Ml, self.P, self.Mr = ctx, Ml, P, Mr
+        keys = list(entries.keys())
+        idx = np.array([[k[0], k[1], k[2], k[3]] for k in keys], dtype=np.int32).reshape(-1, 4)
+        cl = np.array([list(k[4]) for k in keys], dtype=np.int32).reshape(-1, 3)
+        val = np.array([entries[k] for k in keys], dtype=np.float64)
+        h = C.c_void_p()
+        L.check(lib.htn_mpo_create(ctx.h, Ml.h, P.h, Mr.h, len(keys),
+                                   idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   cl.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   val.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)), ctx.h)
+        self.h = h
+        self.nnz = len(keys)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.htn_mpo_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+PLAN_STAT_NAMES = ["flops", "flops_L", "flops_R", "n_gemm_L", "n_gemm_R", "n_mix_targets",
+                   "n_mix_sources", "workspace_bytes", "n_tiles_L", "n_tiles_R", "padded_flops",
+                   "launches_per_apply"]
+
+
+class HeffAC:
+    """y = H_AC x  (MPSKit `AC_hamiltonian`): plan over fixed GL, W, GR."""
+
+    def __init__(self, ctx: Context, GL: Tensor, W: Mpo, GR: Tensor, like: Tensor):
+        self.ctx, self.GL, self.W, self.GR = ctx, GL, W, GR   # keep GL/GR alive
+        h = C.c_void_p()
+        L.check(lib.htn_plan_heff_ac(ctx.h, GL.h, W.h, GR.h, like.h, C.byref(h)), ctx.h)
+        self.h = h
+        st = (C.c_double * 12)()
+        L.check(lib.htn_plan_stats(h, st, 12), ctx.h)
+        self.stats = dict(zip(PLAN_STAT_NAMES, [float(v) for v in st]))
+        self.nelem = like.nelem
+
+    def apply(self, x: Tensor, y: Tensor):
+        L.check(lib.htn_heff_apply(self.h, x.h, y.h), self.ctx.h)
+        return y
+
+    def apply_host(self, x_host: np.ndarray, y_host: np.ndarray):
+        """Reference-facing call with HOST buffers (upload, apply, download)."""
+        assert x_host.dtype == np.float64 and y_host.dtype == np.float64
+        L.check(lib.htn_heff_apply_host(self.h, x_host.ctypes.data, y_host.ctypes.data, x_host.size),
+                self.ctx.h)
+        return y_host
+
+    def apply_host_ptr(self, x_ptr: int, y_ptr: int, nelem: int):
+        L.check(lib.htn_heff_apply_host(self.h, x_ptr, y_ptr, nelem), self.ctx.h)
+
+    def time(self, x: Tensor, y: Tensor, reps: int) -> float:
+        """Device time (ms, CUDA events on the library stream) of `reps` back-to-back applies."""
+        ms = C.c_float()
+        L.check(lib.htn_heff_time(self.h, x.h, y.h, reps, C.byref(ms)), self.ctx.h)
+        return ms.value
+
+    def profile(self, x: Tensor, y: Tensor, reps: int = 10):
+        ms = (C.c_float * 4)()
+        L.check(lib.htn_plan_profile(self.h, x.h, y.h, reps, ms), self.ctx.h)
+        return {"total_ms": ms[0], "stage_L_ms": ms[1], "stage_W_ms": ms[2], "stage_R_ms": ms[3]}
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.htn_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def network_coefficient(sym: int, nine_labels) -> float:
+    lab, plab = _i32arr(np.array(nine_labels, dtype=np.int32).reshape(9, 3))
+    out = C.c_double()
+    L.check(lib.htn_network_coefficient(sym, plab, C.byref(out)))
+    return out.value

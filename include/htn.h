@@ -1,0 +1,151 @@
+/* htn.h — C ABI of the B200-native hot path behind HubbardTN's MPSKit calls.
+ *
+ * The reference (DaanVrancken/HubbardTN) has no FFI layer: its hot path is reached by
+ * Julia dispatch into MPSKit 0.13.1 at src/HubbardFunctions.jl:1010 (IDMRG2), :1012/:1017
+ * (VUMPS), :1013/:1016/:1018/:1363-1365 (changebonds) and :1025-1027 (VUMPS &
+ * GradientGrassmann).  This header declares the entry points a Julia `ccall` shim (shown
+ * in INTEGRATION.md) binds instead.  Each entry point cites the reference interface it
+ * replaces.  Conventions:
+ *   - plain pointers and sizes only; every function returns int32_t:
+ *       0 = ok, >0 = finished but not converged (result usable), <0 = hard error;
+ *     no exception ever crosses the boundary; htn_last_error_string() explains <0;
+ *   - the library owns all device memory; the caller owns every host buffer it passes;
+ *   - handles are opaque and freed explicitly (htn_*_destroy); a context may be used from
+ *     any host thread, one call at a time (internal mutex);
+ *   - there is NO CPU fallback: without a CUDA device htn_ctx_create fails with
+ *     HTN_ERR_NO_DEVICE.
+ *
+ * Sector labels are int32 triples (p, q1, n):
+ *   HTN_SYM_SU2U1: (fermion parity, 2j, U(1) charge)   fZ2 x SU2 x U1  (HubbardFunctions.jl:250;
+ *                  the fZ2 x SU2 mu-models of :342 use n = 0)
+ *   HTN_SYM_U1U1 : (fermion parity, 2Sz, U(1) charge)   fZ2 x U1 x U1   (HubbardFunctions.jl:247)
+ * Block data are real FP64 (the reference stores ComplexF64 but every operator entry of the
+ * ground-state path is real: HubbardFunctions.jl:264-290,302-336).
+ */
+#ifndef HTN_H
+#define HTN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTN_OK 0
+#define HTN_NOT_CONVERGED 1
+#define HTN_ERR_INVALID (-1)
+#define HTN_ERR_NO_DEVICE (-2)
+#define HTN_ERR_CUDA (-3)
+#define HTN_ERR_OOM (-4)
+#define HTN_ERR_SHAPE (-5)
+
+#define HTN_SYM_SU2U1 0
+#define HTN_SYM_U1U1 1
+
+#define HTN_SIDE_LEFT 0
+#define HTN_SIDE_RIGHT 1
+
+/* tensor kinds (block label layout in htn_tensor_blocktable) */
+#define HTN_T_MPS 0  /* A / AC : (V_l (x) P) <- V_r   labels (l, s, r)   block [n_l , n_r ] */
+#define HTN_T_BOND 1 /* C      : V <- V               labels (c, c, c)   block [n_c , n_c ] */
+#define HTN_T_ENVL 2 /* GL     : (bra, level, ket)    labels (a, l', l)  block [n_l', n_l ] */
+#define HTN_T_ENVR 3 /* GR     : (ket, level, bra)    labels (b, r, r')  block [n_r , n_r'] */
+
+typedef struct htn_ctx htn_ctx;
+typedef struct htn_space htn_space;   /* graded bond space  (TensorKit GradedSpace)          */
+typedef struct htn_legs htn_legs;     /* list of single multiplets: physical space or the     */
+                                      /* MPO virtual levels (BlockTensorKit SumSpace)         */
+typedef struct htn_tensor htn_tensor; /* block-sparse tensor in the HBM arena                 */
+typedef struct htn_mpo htn_mpo;       /* one site of an InfiniteMPOHamiltonian (reduced form) */
+typedef struct htn_plan htn_plan;     /* H_eff application plan (MPSKit derivative operator)  */
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Replaces: module initialisation of the reference (BLAS/thread policy, HubbardFunctions.jl:1-55). */
+int32_t htn_ctx_create(int32_t device, htn_ctx** out);
+int32_t htn_ctx_destroy(htn_ctx* ctx);
+const char* htn_last_error_string(htn_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL */
+int32_t htn_version(void);
+int32_t htn_ctx_synchronize(htn_ctx* ctx);
+
+/* ---- spaces ------------------------------------------------------------------------- */
+/* Replaces: Vect[I](sector => multiplicity ...) (HubbardFunctions.jl:248,251,261,282,343).
+ * Sectors are stored in the canonical order (sorted; see DESIGN.md "Block tables"); the
+ * caller may pass them in any order. */
+int32_t htn_space_create(htn_ctx* ctx, int32_t sym, int32_t nsec, const int32_t* labels /*[nsec][3]*/,
+                         const int32_t* mult /*[nsec]*/, htn_space** out);
+int32_t htn_space_destroy(htn_space* s);
+int32_t htn_space_info(const htn_space* s, int32_t* nsec, int32_t* labels /*[nsec][3] or NULL*/,
+                       int32_t* mult /*[nsec] or NULL*/);
+/* ordered multiplets, one each (order is kept as given) */
+int32_t htn_legs_create(htn_ctx* ctx, int32_t sym, int32_t n, const int32_t* labels /*[n][3]*/,
+                        htn_legs** out);
+int32_t htn_legs_destroy(htn_legs* l);
+
+/* ---- tensors ------------------------------------------------------------------------ */
+/* Replaces: TensorMap(zeros, T, codomain <- domain) and the InfiniteMPS site tensors
+ * (HubbardFunctions.jl:264-290, 958, 990); storage = packed HBM arena + block table. */
+int32_t htn_tensor_create_mps(htn_ctx* ctx, const htn_space* Vl, const htn_legs* P, const htn_space* Vr,
+                              htn_tensor** out);
+int32_t htn_tensor_create_bond(htn_ctx* ctx, const htn_space* V, htn_tensor** out);
+/* identity_level >= 0 flags the level that holds the unit tensor (GL[1] / GR[chi]); -1: none */
+int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, const htn_legs* M,
+                              int32_t identity_level, htn_tensor** out);
+int32_t htn_tensor_create_like(const htn_tensor* t, htn_tensor** out);
+int32_t htn_tensor_destroy(htn_tensor* t);
+/* Block table: nblocks rows of (label0,label1,label2) POSITIONS into the spaces, rows, cols,
+ * packed host offset (elements, row-major blocks back to back, no padding).  Pass NULL
+ * arrays to query nblocks / nelem only. */
+int32_t htn_tensor_blocktable(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels,
+                              int32_t* rows, int32_t* cols, int64_t* offsets);
+/* host <-> device, packed host layout as described by htn_tensor_blocktable */
+int32_t htn_tensor_upload(htn_tensor* t, const double* host, int64_t nelem);
+int32_t htn_tensor_download(const htn_tensor* t, double* host, int64_t nelem);
+
+/* ---- MPO ---------------------------------------------------------------------------- */
+/* Replaces: one site tensor of the InfiniteMPOHamiltonian built by @mpoham
+ * (HubbardFunctions.jl:435-465).  entry i: (a, s', s, b) = idx[i][0..3] positions into
+ * (Ml, P, P, Mr); coupled sector label c = clabel[i][0..2]; reduced value val[i]. */
+int32_t htn_mpo_create(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, const htn_legs* Mr,
+                       int32_t nnz, const int32_t* idx /*[nnz][4]*/, const int32_t* clabel /*[nnz][3]*/,
+                       const double* val, htn_mpo** out);
+int32_t htn_mpo_destroy(htn_mpo* w);
+
+/* ---- H_eff -------------------------------------------------------------------------- */
+/* Replaces: MPSKit `AC_hamiltonian(site, psi, H, psi, envs)` / `∂AC` reached from
+ * find_groundstate at HubbardFunctions.jl:1012,1017,1027.  The plan references GL, GR (not
+ * copied; they must outlive the plan) and copies W. `like` fixes the block structure of x,y. */
+int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
+                         const htn_tensor* like, htn_plan** out);
+int32_t htn_plan_destroy(htn_plan* p);
+/* y = H_AC x on the device (x, y created with the plan's `like` structure; x != y) */
+int32_t htn_heff_apply(htn_plan* p, const htn_tensor* x, htn_tensor* y);
+/* same through host buffers: upload x, apply, download y (the e2e path of bench.py) */
+int32_t htn_heff_apply_host(htn_plan* p, const double* x_host, double* y_host, int64_t nelem);
+/* plan statistics: stats[0]=algorithmic flops, [1]=stage-L flops, [2]=stage-R
+ * flops, [3]=#stage-L GEMMs, [4]=#stage-R GEMM segments, [5]=#mix targets, [6]=#mix sources,
+ * [7]=workspace bytes, [8]=#stage-L tiles, [9]=#stage-R tiles, [10]=padded (executed) flops,
+ * [11]=kernel launches per apply */
+int32_t htn_plan_stats(const htn_plan* p, double* stats, int32_t n);
+/* time `reps` applies with CUDA events on the library stream: ms[0]=total per apply,
+ * ms[1..3] = stage L / W / R per apply (each stage timed in its own pass) */
+int32_t htn_plan_profile(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_t reps, float* ms /*[4]*/);
+
+/* `reps` back-to-back applies bracketed by two CUDA events on the library stream (device time
+ * of the whole timed region, ms) — what bench.py reports as ms_per_step * steps */
+int32_t htn_heff_time(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_t reps, float* ms_total);
+
+/* ---- vector algebra on tensors of identical structure (KrylovKit inner products) ------ */
+/* <x,y> = sum_blocks dim(coupled sector) tr(x^T y)   (TensorKit inner product) */
+int32_t htn_tensor_dot(const htn_tensor* x, const htn_tensor* y, double* out);
+int32_t htn_tensor_axpby(double alpha, const htn_tensor* x, double beta, htn_tensor* y); /* y = a x + b y */
+
+/* ---- test hooks --------------------------------------------------------------------- */
+/* recoupling network N(l',s',r'; l,s,r; a,b,c) of DESIGN.md (labels are int32 triples) */
+int32_t htn_network_coefficient(int32_t sym, const int32_t* nine_labels /*[9][3]*/, double* out);
+/* FP64 peak probes (dependent-free DMMA.8x8x4 / DFMA loops): TFLOP/s on the ctx device */
+int32_t htn_probe_fp64_peak(htn_ctx* ctx, int32_t which /*0=DMMA,1=DFMA*/, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTN_H */

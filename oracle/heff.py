@@ -34,10 +34,11 @@ from .tensors import BondTensor, EnvTensor, MPOTensor, MPSTensor
 @lru_cache(maxsize=None)
 def _network_su2(jlp, jsp, jrp, jl, js, jr, ja, jb, jc) -> float:
     g = S._cg_su2
-    return float(np.einsum(
+    v = float(np.einsum(
         "ptq,alp,lsr,atc,sbc,brq->",
         g(jlp, jsp, jrp), g(ja, jl, jlp), g(jl, js, jr), g(ja, jsp, jc), g(js, jb, jc),
         g(jb, jr, jrp), optimize=True))
+    return 0.0 if abs(v) < 1e-14 else v   # same zero threshold as csrc/htn_sectors.cpp
 
 
 def network(kind, clp, csp, crp, cl, cs, cr, ca, cb, cc) -> float:
@@ -157,22 +158,48 @@ class HeffACPlan:
                            for (b, lp, sp, rp, r) in self.u_list)
         self.flops = self.flops_L + self.flops_R
 
-    def apply(self, x: MPSTensor) -> MPSTensor:
+    def apply(self, x: MPSTensor, threads: int = 1) -> MPSTensor:
+        """threads > 1: worker threads over sector blocks with single-threaded BLAS — the
+        reference's CPU policy (HubbardFunctions.jl:29 BLAS threads = 1, :37 scheduler)."""
         GL, GR = self.GL, self.GR
-        T = [GL.blocks[(a, lp, l)] @ x.blocks[(l, s, r)] for (a, lp, l, s, r) in self.t_list]
-        y = x.zeros_like()
-        U = [None] * len(self.u_list)
-        for dst, srcs in self.mix.items():
+        if threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(threads)
+            pmap = lambda f, it: list(pool.map(f, it, chunksize=8))  # noqa: E731
+        else:
+            pool = None
+            pmap = lambda f, it: [f(v) for v in it]  # noqa: E731
+        T = pmap(lambda k: GL.blocks[(k[0], k[1], k[2])] @ x.blocks[(k[2], k[3], k[4])], self.t_list)
+
+        def mix_one(item):
+            dst, srcs = item
             acc = None
             for (kind, i), cf in srcs:
                 blk = T[i] if kind == "T" else x.blocks[i]
                 acc = cf * blk if acc is None else acc + cf * blk
+            return dst, acc
+
+        y = x.zeros_like()
+        U = [None] * len(self.u_list)
+        for dst, acc in pmap(mix_one, list(self.mix.items())):
             if dst[0] == "Y":
                 y.blocks[dst[1]] += acc
             else:
                 U[dst[1]] = acc
-        for i, (b, lp, sp, rp, r) in enumerate(self.u_list):
-            y.blocks[(lp, sp, rp)] += U[i] @ GR.blocks[(b, r, rp)]
+        if not hasattr(self, "_by_y"):
+            self._by_y = {}
+            for i, (b, lp, sp, rp, r) in enumerate(self.u_list):
+                self._by_y.setdefault((lp, sp, rp), []).append((i, (b, r, rp)))
+
+        def stage_r(item):
+            ky, lst = item
+            acc = y.blocks[ky]
+            for i, kgr in lst:
+                acc += U[i] @ GR.blocks[kgr]
+
+        pmap(stage_r, list(self._by_y.items()))
+        if pool is not None:
+            pool.shutdown()
         return y
 
 

@@ -55,7 +55,7 @@ def synthetic_bond_space(kind: int, D: int, btype: int = 0) -> Space:
     tot = sum(w.values())
     mult = {s: int(round(D * v / tot)) for s, v in w.items()}
     mult = {s: n for s, n in mult.items() if n > 0}
-    big = max(mult, key=lambda s: (mult[s], -S.sort_key(kind, s)[0][0]))
+    big = max(mult, key=lambda s: (mult[s], -abs(s[2]), -abs(s[1])))
     mult[big] += D - sum(mult.values())
     return Space(kind, mult)
 

@@ -1,0 +1,133 @@
+"""Parity of the CUDA H_AC path (through the C ABI) against the oracle on identical inputs.
+
+Tolerance: FP64, relative 1e-12 per apply on O(1) data (north star: observables to 1e-10
+relative; a single apply must sit well below that).  Block tables must agree exactly.
+"""
+import numpy as np
+import pytest
+
+from hubbardtn_b200 import device, sectors as PS, synthetic
+from oracle import bridge
+from oracle import heff as oheff
+from oracle.tensors import inner
+from util import oracle_view, rel_err, table
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _apply_and_compare(case, naive=True):
+    ov = oracle_view(case)
+    case.plan.apply(case.x, case.y)
+    y_gpu = case.y.download()
+    if naive:
+        y_ref = oheff.heff_ac_apply_naive(ov["GL"], ov["W"], ov["GR"], ov["x"])
+    else:
+        y_ref = oheff.HeffACPlan(ov["GL"], ov["W"], ov["GR"], ov["x"]).apply(ov["x"])
+    ref = bridge.mps_to_packed(y_ref, table(case.y))
+    assert np.abs(ref).max() > 1e-3
+    assert rel_err(y_gpu, ref) < TOL
+    return ov, y_gpu, ref
+
+
+@pytest.mark.parametrize("sym,D,chi", [(PS.SU2U1, 24, 7), (PS.U1U1, 24, 7), (PS.SU2U1, 96, 12),
+                                       (PS.U1U1, 130, 9), (PS.SU2U1, 7, 3), (PS.SU2U1, 1, 2)])
+def test_heff_ac_matches_oracle(ctx, sym, D, chi):
+    case = synthetic.HeffCase(ctx, sym, D=D, chi=chi)
+    ov, y_gpu, ref = _apply_and_compare(case, naive=True)
+    # flop count of the plan == oracle's GEMM-list count (SURVEY 8(d) algorithmic flops)
+    oplan = oheff.HeffACPlan(ov["GL"], ov["W"], ov["GR"], ov["x"])
+    assert case.plan.stats["flops"] == oplan.flops
+    assert case.plan.stats["n_gemm_L"] == len(oplan.t_list)
+    assert case.plan.stats["n_gemm_R"] == len(oplan.u_list)
+
+
+def test_heff_ac_dense_anchor(ctx):
+    """GPU result == dense, symmetry-free contraction (independent of the oracle's planner)."""
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=20, chi=6)
+    ov = oracle_view(case)
+    case.plan.apply(case.x, case.y)
+    y = bridge.mps_from_packed(ov["Vl"], ov["P"], ov["Vr"], table(case.y), case.y.download())
+    yd = oheff.heff_ac_apply_dense(ov["GL"], ov["W"], ov["GR"], ov["x"])
+    assert np.abs(y.to_dense() - yd).max() < 1e-11 * np.abs(yd).max()
+
+
+def test_heff_ac_host_path_and_repeatability(ctx):
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=64, chi=10)
+    case.plan.apply(case.x, case.y)
+    y1 = case.y.download()
+    y_host = np.empty_like(case.x_host)
+    case.plan.apply_host(case.x_host, y_host)
+    assert np.array_equal(y1, y_host)            # same kernels, same order: bit-identical
+    case.plan.apply(case.x, case.y)
+    assert np.array_equal(y1, case.y.download())  # deterministic (no atomics)
+
+
+def test_heff_ac_medium_vs_oracle_plan(ctx):
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=256, chi=24)
+    _apply_and_compare(case, naive=False)
+
+
+def test_heff_ac_full_size_properties(ctx):
+    """BASELINE config C4 shape (D=1024, chi=96): linearity and a block-subset oracle check."""
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=1024, chi=96)
+    st = case.plan.stats
+    assert 1.5e10 < st["flops"] < 4e10          # ~23 GF per apply
+    x, y = case.x, case.y
+    case.plan.apply(x, y)
+    y1 = y.download()
+    z = x.like().upload(synthetic.random_packed(x.nelem, 77))
+    hz = x.like()
+    case.plan.apply(z, hz)
+    y2 = hz.download()
+    comb = x.like()
+    comb.axpby(0.5, x, 0.0)
+    comb.axpby(-2.0, z, 1.0)
+    hc = x.like()
+    case.plan.apply(comb, hc)
+    assert rel_err(hc.download(), 0.5 * y1 - 2.0 * y2) < 1e-12
+    # oracle check on a subset of output blocks (terms restricted to those blocks)
+    ov = oracle_view(case)
+    terms = oheff.heff_ac_terms(ov["GL"], ov["W"], ov["GR"], ov["x"])
+    views = case.y.block_views(y1)
+    keys = sorted(views.keys(), key=lambda k: views[k].size)
+    pick = [keys[0], keys[len(keys) // 2], keys[-1]]
+    for ky in pick:
+        acc = np.zeros(views[ky].shape)
+        for (k0, kgl, kx, kgr, cf) in terms:
+            if k0 == ky:
+                acc += cf * (ov["GL"].blocks[kgl] @ ov["x"].blocks[kx] @ ov["GR"].blocks[kgr])
+        assert rel_err(views[ky], acc) < 1e-11
+
+
+def test_blocktables_match_oracle_order(ctx):
+    case = synthetic.HeffCase(ctx, PS.U1U1, D=40, chi=5)
+    oracle_view(case)   # asserts sector order + block order + offsets inside
+
+
+def test_dot_axpby_match_oracle(ctx):
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=96, chi=4)
+    ov = oracle_view(case)
+    z_host = synthetic.random_packed(case.x.nelem, 5)
+    z = case.x.like().upload(z_host)
+    zo = bridge.mps_from_packed(ov["Vl"], ov["P"], ov["Vr"], table(z), z_host)
+    ref = inner(ov["x"], zo)
+    assert abs(case.x.dot(z) - ref) < 1e-12 * abs(ref) + 1e-12
+    z.axpby(0.25, case.x, -1.5)
+    assert rel_err(z.download(), 0.25 * case.x_host - 1.5 * z_host) < 1e-15
+
+
+def test_error_paths(ctx):
+    from hubbardtn_b200 import _lib
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=16, chi=4)
+    other = synthetic.HeffCase(ctx, PS.SU2U1, D=24, chi=4)
+    with pytest.raises(_lib.HtnError) as ei:
+        case.plan.apply(other.x, case.y)
+    assert ei.value.code == _lib.HTN_ERR_SHAPE
+    with pytest.raises(_lib.HtnError):
+        case.plan.apply(case.x, case.x)
+    with pytest.raises(_lib.HtnError):
+        case.x.upload(np.zeros(3))
+    with pytest.raises(_lib.HtnError):
+        device.Space(ctx, 0, {(0, -1, 0): 2})
