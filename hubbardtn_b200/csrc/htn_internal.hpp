@@ -118,7 +118,7 @@ struct htn_mpo {
 // ---- device work tables (shared between planner and kernels) ---------------------------
 namespace htn {
 
-enum Base { B_GL = 0, B_GR = 1, B_X = 2, B_Y = 3, B_T = 4, B_U = 5, B_COUNT = 6 };
+enum Base { B_GL = 0, B_GR = 1, B_X = 2, B_Y = 3, B_T = 4, B_U = 5, B_P = 6, B_COUNT = 7 };
 
 // References in the device tables are resolved by a post-pass of the planner: arrays that
 // live as long as the plan (GL, GR, T, U) become absolute pointers (REF_ABS); the apply's
@@ -149,6 +149,8 @@ struct GemmItem {
   int seg_begin, seg_end;
   int nchunks;  // sum over segments of ceil(K / BK)
   int beta;     // 0: overwrite, 1: accumulate
+  int layout;   // 0: flex = M, strips over N ; 1: flex = N, strips over M (htn_kernels.cu)
+  int pad_;
 };
 
 struct MixSrc {
@@ -195,7 +197,8 @@ struct htn_plan {
   htn_tensor* like;  // private structural copy (no data use)
   double* T = nullptr;
   double* U = nullptr;
-  int64_t t_elems = 0, u_elems = 0;
+  double* Pp = nullptr;  // split-K partial outputs of stage R: nsplit_max copies of the y layout
+  int64_t t_elems = 0, u_elems = 0, p_elems = 0;
   // device tables
   htn::GemmItem* itemsL = nullptr;
   htn::GemmSeg* segsL = nullptr;
@@ -205,8 +208,8 @@ struct htn_plan {
   int nitemsR = 0, nsegsR = 0;
   htn::MixTarget* mixT = nullptr;
   htn::MixSrc* mixS = nullptr;
-  htn::MixChunk* mixC = nullptr;
-  int nmixT = 0, nmixS = 0, nmixC = 0;
+  htn::MixChunk* mixC = nullptr;   // chunks [0, nmixCU) -> U targets, [nmixCU, nmixC) -> y targets
+  int nmixT = 0, nmixS = 0, nmixC = 0, nmixCU = 0;
   int gridL = 0, gridR = 0;
   double stats[12] = {0};
   // host staging tensors for htn_heff_apply_host

@@ -49,10 +49,68 @@ constexpr int A_STAGE = BM * LDAS;
 constexpr int B_STAGE = BK * LDBS;
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
 
-struct SegCursor {
-  int seg;  // current segment
-  int k0;   // chunk start inside the segment
-};
+// Work distribution inside a CTA (4 warps).  A tile is MA x NA DMMA atoms (8x8 each, <= 8x8
+// atoms).  One dimension is "fixed": it is cut into 4 strips of 2 atoms, one strip per warp
+// role; the other ("flex") dimension has 1..8 atoms and every warp covers all of it.  All
+// warps therefore do the same work, block extents are padded only to the atom size 8, and
+// the inner loop is straight-line code specialised on the flex extent (no predication).
+//   layout 0 (LAY_A): flex = M (rows), fixed = N: role w owns col atoms 2w, 2w+1
+//   layout 1 (LAY_B): flex = N (cols), fixed = M: role w owns row atoms 2w, 2w+1
+// acc[flex atom][fixed atom f][2 values of the DMMA C fragment].
+template <int FLEX, bool LAYB>
+__device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __restrict__ as,
+                                       const double* __restrict__ bs, int kk) {
+  // as -> A stage + (g * LDAS + t) [+ role offset for LAY_B]; bs -> B stage + (t * LDBS + g) [+ role offset for LAY_A]
+  double fx[FLEX], ff[2];
+  if (!LAYB) {
+#pragma unroll
+    for (int i = 0; i < FLEX; ++i) fx[i] = as[i * 8 * LDAS + kk * 4];
+    ff[0] = bs[kk * 4 * LDBS];
+    ff[1] = bs[kk * 4 * LDBS + 8];
+#pragma unroll
+    for (int i = 0; i < FLEX; ++i) {
+      dmma884(acc[i][0][0], acc[i][0][1], fx[i], ff[0]);
+      dmma884(acc[i][1][0], acc[i][1][1], fx[i], ff[1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < FLEX; ++j) fx[j] = bs[kk * 4 * LDBS + j * 8];
+    ff[0] = as[kk * 4];
+    ff[1] = as[8 * LDAS + kk * 4];
+#pragma unroll
+    for (int j = 0; j < FLEX; ++j) {
+      dmma884(acc[j][0][0], acc[j][0][1], ff[0], fx[j]);
+      dmma884(acc[j][1][0], acc[j][1][1], ff[1], fx[j]);
+    }
+  }
+}
+
+template <int FLEX, bool LAYB>
+__device__ __forceinline__ void mma_chunk(double (&acc)[8][2][2], const double* __restrict__ as,
+                                          const double* __restrict__ bs, int nk4) {
+  if (nk4 == BK / 4) {
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, kk);
+  } else {
+#pragma unroll 1
+    for (int kk = 0; kk < nk4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, kk);
+  }
+}
+
+template <bool LAYB>
+__device__ __forceinline__ void mma_dispatch(int flex, double (&acc)[8][2][2], const double* as, const double* bs,
+                                             int nk4) {
+  switch (flex) {
+    case 1: mma_chunk<1, LAYB>(acc, as, bs, nk4); break;
+    case 2: mma_chunk<2, LAYB>(acc, as, bs, nk4); break;
+    case 3: mma_chunk<3, LAYB>(acc, as, bs, nk4); break;
+    case 4: mma_chunk<4, LAYB>(acc, as, bs, nk4); break;
+    case 5: mma_chunk<5, LAYB>(acc, as, bs, nk4); break;
+    case 6: mma_chunk<6, LAYB>(acc, as, bs, nk4); break;
+    case 7: mma_chunk<7, LAYB>(acc, as, bs, nk4); break;
+    default: mma_chunk<8, LAYB>(acc, as, bs, nk4); break;
+  }
+}
 
 __global__ void __launch_bounds__(NTHREADS, 4)
 grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
@@ -64,30 +122,29 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;
 
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
     const GemmItem item = items[it];
     const int mt = item.mt, nt = item.nt;
-    // atoms this warp owns (warp-uniform)
-    int mi = (mt - wm * 32 + 7) >> 3;
-    mi = mi < 0 ? 0 : (mi > 4 ? 4 : mi);
-    int nj = (nt - wn * 32 + 7) >> 3;
-    nj = nj < 0 ? 0 : (nj > 4 ? 4 : nj);
+    const bool layb = item.layout != 0;
+    // rotate the strip a warp owns from item to item so that partially filled strips do not
+    // always land on the same SM sub-partition (warp id % 4)
+    const int role = (warp + it) & 3;
+    const int flex = ((layb ? nt : mt) + 7) >> 3;
+    const int fixed_ext = layb ? mt : nt;
+    const bool active = role * 16 < fixed_ext;  // warp-uniform: this strip holds data
 
-    double acc[4][4][2];
+    double acc[8][2][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int i = 0; i < 8; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
 
     // ---- producer: issue the loads of one chunk into stage `st` -----------------------
-    SegCursor pc{item.seg_begin, 0};
-    GemmSeg pseg = segs[pc.seg];
+    int pseg_i = item.seg_begin, pk0 = 0;
+    GemmSeg pseg = segs[pseg_i];
     auto issue = [&](int st) {
       const double* Ag = resolve(pseg.a_off, pseg.a_base, bases);
       const double* Bg = resolve(pseg.b_off, pseg.b_base, bases);
-      const int K = pseg.K, k0 = pc.k0;
+      const int K = pseg.K, k0 = pk0;
       double* as = As + st * A_STAGE;
       double* bs = Bs + st * B_STAGE;
 #pragma unroll
@@ -110,12 +167,11 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
         const double* src = bytes ? (Bg + (long long)k * pseg.ldb + sg * 2) : Bg;
         cp_async16(bs + row * LDBS + sg * 2, src, bytes);
       }
-      // advance the producer cursor
-      pc.k0 += BK;
-      if (pc.k0 >= K) {
-        pc.k0 = 0;
-        pc.seg++;
-        if (pc.seg < item.seg_end) pseg = segs[pc.seg];
+      pk0 += BK;
+      if (pk0 >= K) {
+        pk0 = 0;
+        pseg_i++;
+        if (pseg_i < item.seg_end) pseg = segs[pseg_i];
       }
     };
 
@@ -131,9 +187,10 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
     }
 
     // ---- consumer ---------------------------------------------------------------------
-    SegCursor cc{item.seg_begin, 0};
-    int cK = segs[cc.seg].K;
-    double coef = segs[cc.seg].coef;
+    int cseg_i = item.seg_begin, ck0 = 0;
+    int cK = segs[cseg_i].K;
+    const int a_role = layb ? role * 16 * LDAS : 0;
+    const int b_role = layb ? 0 : role * 16;
     for (int c = 0; c < nchunks; ++c) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
@@ -143,66 +200,52 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
       }
       cp_async_commit();
 
-      const double* as = As + (c % STAGES) * A_STAGE + (wm * 32 + g) * LDAS + t;
-      const double* bs = Bs + (c % STAGES) * B_STAGE + t * LDBS + wn * 32 + g;
-#pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (i < mi) ? as[i * 8 * LDAS + kk * 4] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = (j < nj) ? bs[kk * 4 * LDBS + j * 8] : 0.0;
-        if (coef != 1.0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] *= coef;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < mi) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < nj) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-          }
-        }
+      int krem = cK - ck0;
+      const int nk4 = krem >= BK ? BK / 4 : (krem + 3) >> 2;
+      if (active) {
+        const double* as = As + (c % STAGES) * A_STAGE + g * LDAS + t + a_role;
+        const double* bs = Bs + (c % STAGES) * B_STAGE + t * LDBS + g + b_role;
+        if (layb)
+          mma_dispatch<true>(flex, acc, as, bs, nk4);
+        else
+          mma_dispatch<false>(flex, acc, as, bs, nk4);
       }
-      // advance the consumer cursor
-      cc.k0 += BK;
-      if (cc.k0 >= cK) {
-        cc.k0 = 0;
-        cc.seg++;
-        if (cc.seg < item.seg_end) {
-          cK = segs[cc.seg].K;
-          coef = segs[cc.seg].coef;
-        }
+      ck0 += BK;
+      if (ck0 >= cK) {
+        ck0 = 0;
+        cseg_i++;
+        if (cseg_i < item.seg_end) cK = segs[cseg_i].K;
       }
     }
     cp_async_wait<0>();
 
     // ---- epilogue ---------------------------------------------------------------------
-    double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
-    const int ldc = item.ldc;
+    if (active) {
+      double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
+      const int ldc = item.ldc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int row = wm * 32 + i * 8 + g;
-      if (i < mi && row < mt) {
+      for (int x = 0; x < 8; ++x) {
+        if (x < flex) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int col = wn * 32 + j * 8 + 2 * t;
-          if (j < nj && col < nt) {
-            double* p = C + (long long)row * ldc + col;
-            if (col + 1 < nt) {
-              double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-              if (item.beta) {
-                double2 o = *reinterpret_cast<double2*>(p);
-                v.x += o.x;
-                v.y += o.y;
+          for (int f = 0; f < 2; ++f) {
+            const int ra = layb ? (role * 2 + f) : x;  // row atom
+            const int ca = layb ? x : (role * 2 + f);  // col atom
+            const int row = ra * 8 + g, col = ca * 8 + 2 * t;
+            if (row < mt && col < nt) {
+              double* p = C + (long long)row * ldc + col;
+              if (col + 1 < nt) {
+                double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
+                if (item.beta) {
+                  double2 o = *reinterpret_cast<double2*>(p);
+                  v.x += o.x;
+                  v.y += o.y;
+                }
+                *reinterpret_cast<double2*>(p) = v;
+              } else {
+                double v = acc[x][f][0];
+                if (item.beta) v += *p;
+                *p = v;
               }
-              *reinterpret_cast<double2*>(p) = v;
-            } else {
-              double v = acc[i][j][0];
-              if (item.beta) v += *p;
-              *p = v;
             }
           }
         }
@@ -233,6 +276,7 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, Bases b
   grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases);
 }
 
+// ------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------
 // stage W: block linear combinations
 // ------------------------------------------------------------------------------------

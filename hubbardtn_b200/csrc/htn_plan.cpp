@@ -30,25 +30,71 @@ bool htn_same_structure(const htn_tensor* x, const htn_tensor* y);
 
 namespace {
 
-struct Tile {
-  int o, n;
+struct TileSpec {
+  int mo, mn, no, nn, layout;
 };
 
-// split an extent into near-equal tiles of at most `maxt`, each a multiple of 8 (DMMA atom)
-std::vector<Tile> split_extent(int n, int maxt) {
-  std::vector<Tile> out;
-  int atoms = (n + 7) / 8;
-  int per = maxt / 8;
-  int nt = (atoms + per - 1) / per;
-  int base = atoms / nt, rem = atoms % nt;
-  int o = 0;
+// near-equal split of an extent into pieces of at most 64, each a multiple of the DMMA atom (8)
+std::vector<std::pair<int, int>> split_flex(int n) {
+  std::vector<std::pair<int, int>> out;
+  int atoms = (n + 7) / 8, nt = (atoms + 7) / 8;
+  int base = atoms / nt, rem = atoms % nt, o = 0;
   for (int i = 0; i < nt; ++i) {
-    int a = base + (i < rem ? 1 : 0);
-    int len = std::min(8 * a, n - o);
+    int len = std::min(8 * (base + (i < rem ? 1 : 0)), n - o);
     out.push_back({o, len});
     o += len;
   }
   return out;
+}
+
+// pipe cost (executed DMMA atoms, 2 per active strip and flex atom) + a small charge for idle strips
+double tile_cost(int flex_ext, int fixed_ext) {
+  int flex = (flex_ext + 7) / 8, strips = (fixed_ext + 15) / 16;
+  return flex * 2.0 * strips + 0.25 * flex * 2.0 * (4 - strips);
+}
+
+// Cover an M x N block with CTA tiles (see the layout comment in htn_kernels.cu).  Variant 0:
+// full 64-column tiles in layout A (rows split flexibly) + the remaining columns as layout-B
+// tiles (64-row strips, flex = remaining columns).  Variant 1: the transpose.  Cheapest wins.
+std::vector<TileSpec> tile_block(int M, int N) {
+  std::vector<TileSpec> best;
+  double best_cost = 1e300;
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<TileSpec> v;
+    double cost = 0;
+    if (variant == 0) {
+      int nfull = N / 64, rn = N % 64;
+      for (int j = 0; j < nfull; ++j)
+        for (auto& pm : split_flex(M)) {
+          v.push_back({pm.first, pm.second, j * 64, 64, 0});
+          cost += tile_cost(pm.second, 64);
+        }
+      if (rn)
+        for (int mo = 0; mo < M; mo += 64) {
+          int mn = std::min(64, M - mo);
+          v.push_back({mo, mn, nfull * 64, rn, 1});
+          cost += tile_cost(rn, mn);
+        }
+    } else {
+      int mfull = M / 64, rm = M % 64;
+      for (int i = 0; i < mfull; ++i)
+        for (auto& pn : split_flex(N)) {
+          v.push_back({i * 64, 64, pn.first, pn.second, 1});
+          cost += tile_cost(pn.second, 64);
+        }
+      if (rm)
+        for (int no = 0; no < N; no += 64) {
+          int nn = std::min(64, N - no);
+          v.push_back({mfull * 64, rm, no, nn, 0});
+          cost += tile_cost(rm, nn);
+        }
+    }
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = v;
+    }
+  }
+  return best;
 }
 
 struct WsBlock {  // workspace block (T or U)
@@ -77,6 +123,7 @@ int32_t htn_plan_destroy(htn_plan* p) {
   cudaStreamSynchronize(p->ctx->stream);
   cudaFree(p->T);
   cudaFree(p->U);
+  cudaFree(p->Pp);
   cudaFree(p->itemsL);
   cudaFree(p->segsL);
   cudaFree(p->itemsR);
@@ -223,31 +270,31 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
       const Block& xb = like->blocks[like->find(l, s, r)];
       const WsBlock& w = tb[ti];
       flopsL += 2.0 * w.rows * w.cols * gl.cols;
-      for (Tile tm : split_extent(w.rows, GEMM_BM))
-        for (Tile tn : split_extent(w.cols, GEMM_BN)) {
-          GemmSeg sg{};
-          sg.a_base = B_GL;
-          sg.a_off = gl.off + (int64_t)tm.o * gl.ld;
-          sg.lda = gl.ld;
-          sg.b_base = B_X;
-          sg.b_off = xb.off + tn.o;
-          sg.ldb = xb.ld;
-          sg.K = gl.cols;
-          sg.coef = 1.0;
-          GemmItem it{};
-          it.c_base = B_T;
-          it.c_off = w.off + (int64_t)tm.o * w.ld + tn.o;
-          it.ldc = w.ld;
-          it.mt = tm.n;
-          it.nt = tn.n;
-          it.seg_begin = (int)segsL.size();
-          it.seg_end = it.seg_begin + 1;
-          it.nchunks = (sg.K + GEMM_BK - 1) / GEMM_BK;
-          it.beta = 0;
-          segsL.push_back(sg);
-          itemsL.push_back(it);
-          padded += 2.0 * ((tm.n + 7) / 8 * 8) * ((tn.n + 7) / 8 * 8) * (double)it.nchunks * GEMM_BK;
-        }
+      for (const TileSpec& ts : tile_block(w.rows, w.cols)) {
+        GemmSeg sg{};
+        sg.a_base = B_GL;
+        sg.a_off = gl.off + (int64_t)ts.mo * gl.ld;
+        sg.lda = gl.ld;
+        sg.b_base = B_X;
+        sg.b_off = xb.off + ts.no;
+        sg.ldb = xb.ld;
+        sg.K = gl.cols;
+        sg.coef = 1.0;
+        GemmItem it{};
+        it.c_base = B_T;
+        it.c_off = w.off + (int64_t)ts.mo * w.ld + ts.no;
+        it.ldc = w.ld;
+        it.mt = ts.mn;
+        it.nt = ts.nn;
+        it.layout = ts.layout;
+        it.seg_begin = (int)segsL.size();
+        it.seg_end = it.seg_begin + 1;
+        it.nchunks = (sg.K + GEMM_BK - 1) / GEMM_BK;
+        it.beta = 0;
+        segsL.push_back(sg);
+        itemsL.push_back(it);
+        padded += 2.0 * ((ts.mn + 7) / 8 * 8) * ((ts.nn + 7) / 8 * 8) * ((sg.K + 3) / 4 * 4.0);
+      }
     }
 
     // ---- stage R work list: one item per y tile, K-segments over all (b,r) ---------------
@@ -259,43 +306,75 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     }
     std::vector<GemmItem> itemsR;
     std::vector<GemmSeg> segsR;
+    // split-K: a y block has few tiles but a K loop over every (level, sector) pair; cut the
+    // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy
+    // of the y tile (summed in fixed order by the final mix => deterministic)
+    const int SPLIT_CHUNKS = 40, SPLIT_MAX = 32;
+    std::vector<int> ysplits(like->blocks.size(), 0);
+    int nsplit_max = 0;
     for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
       if (y_u[yi].empty()) continue;
       const Block& yb = like->blocks[yi];
       std::sort(y_u[yi].begin(), y_u[yi].end(), [&](int i, int j) { return ukeys[i] < ukeys[j]; });
-      for (Tile tm : split_extent(yb.rows, GEMM_BM))
-        for (Tile tn : split_extent(yb.cols, GEMM_BN)) {
+      int total_chunks = 0;
+      for (int ui : y_u[yi]) total_chunks += (ub[ui].cols + GEMM_BK - 1) / GEMM_BK;
+      int nsplit = std::max(1, std::min({SPLIT_MAX, (total_chunks + SPLIT_CHUNKS / 2) / SPLIT_CHUNKS,
+                                         (int)y_u[yi].size()}));
+      ysplits[yi] = nsplit;
+      nsplit_max = std::max(nsplit_max, nsplit);
+      // cut points over the segment list (balanced by chunk count)
+      std::vector<int> cut(nsplit + 1, 0);
+      {
+        int acc = 0, sidx = 1;
+        for (size_t q = 0; q < y_u[yi].size(); ++q) {
+          acc += (ub[y_u[yi][q]].cols + GEMM_BK - 1) / GEMM_BK;
+          while (sidx < nsplit && acc >= (long long)total_chunks * sidx / nsplit) cut[sidx++] = (int)q + 1;
+        }
+        for (; sidx <= nsplit; ++sidx) cut[sidx] = (int)y_u[yi].size();
+        for (int q = 1; q <= nsplit; ++q) cut[q] = std::max(cut[q], cut[q - 1]);
+      }
+      for (const TileSpec& ts : tile_block(yb.rows, yb.cols))
+        for (int sp_i = 0; sp_i < nsplit; ++sp_i) {
+          if (cut[sp_i + 1] == cut[sp_i]) continue;
           GemmItem it{};
-          it.c_base = B_Y;
-          it.c_off = yb.off + (int64_t)tm.o * yb.ld + tn.o;
+          it.c_base = B_P;
+          it.c_off = (int64_t)sp_i * like->dsize + yb.off + (int64_t)ts.mo * yb.ld + ts.no;
           it.ldc = yb.ld;
-          it.mt = tm.n;
-          it.nt = tn.n;
+          it.mt = ts.mn;
+          it.nt = ts.nn;
+          it.layout = ts.layout;
           it.seg_begin = (int)segsR.size();
-          it.beta = 1;
+          it.beta = 0;
           it.nchunks = 0;
-          for (int ui : y_u[yi]) {
+          for (int q = cut[sp_i]; q < cut[sp_i + 1]; ++q) {
+            int ui = y_u[yi][q];
             int b, lp, sp, rp, r;
             std::tie(b, lp, sp, rp, r) = ukeys[ui];
             const Block& gr = GR->blocks[GR->find(b, r, rp)];
             const WsBlock& w = ub[ui];
             GemmSeg sg{};
             sg.a_base = B_U;
-            sg.a_off = w.off + (int64_t)tm.o * w.ld;
+            sg.a_off = w.off + (int64_t)ts.mo * w.ld;
             sg.lda = w.ld;
             sg.b_base = B_GR;
-            sg.b_off = gr.off + tn.o;
+            sg.b_off = gr.off + ts.no;
             sg.ldb = gr.ld;
             sg.K = gr.rows;
             sg.coef = 1.0;
             segsR.push_back(sg);
             it.nchunks += (sg.K + GEMM_BK - 1) / GEMM_BK;
+            padded += 2.0 * ((ts.mn + 7) / 8 * 8) * ((ts.nn + 7) / 8 * 8) * ((sg.K + 3) / 4 * 4.0);
           }
           it.seg_end = (int)segsR.size();
           itemsR.push_back(it);
-          padded += 2.0 * ((tm.n + 7) / 8 * 8) * ((tn.n + 7) / 8 * 8) * (double)it.nchunks * GEMM_BK;
         }
+      // partial copies become extra sources of the y block in the final mix; a split whose
+      // segment range is empty never writes its copy, so only non-empty splits are listed
+      for (int sp_i = 0; sp_i < nsplit; ++sp_i)
+        if (cut[sp_i + 1] > cut[sp_i])
+          ysrc[yi].push_back(Src{B_P, (int64_t)sp_i * like->dsize + yb.off, 1.0});
     }
+    p->p_elems = std::max<int64_t>((int64_t)nsplit_max * like->dsize, 16);
     for (size_t ui = 0; ui < ub.size(); ++ui) {
       int b, lp, sp, rp, r;
       std::tie(b, lp, sp, rp, r) = ukeys[ui];
@@ -323,6 +402,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
       for (int e = 0; e < nelem; e += MIX_CHUNK) mixC.push_back(MixChunk{ti, e});
     };
     for (size_t ui = 0; ui < ub.size(); ++ui) add_target(B_U, ub[ui].off, ub[ui].rows * ub[ui].ld, usrc[ui]);
+    const int nmixCU = (int)mixC.size();
     for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
       const Block& yb = like->blocks[yi];
       add_target(B_Y, yb.off, yb.rows * yb.ld, ysrc[yi]);
@@ -331,7 +411,8 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     // ---- upload ------------------------------------------------------------------------------
     cudaSetDevice(ctx->device);
     if (cudaMalloc(&p->T, p->t_elems * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&p->U, p->u_elems * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&p->U, p->u_elems * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&p->Pp, p->p_elems * sizeof(double)) != cudaSuccess) {
       htn_plan_destroy(p);
       return ctx->fail(HTN_ERR_OOM, "plan_heff_ac: workspace allocation failed");
     }
@@ -343,6 +424,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
           case B_GR: b = GR->d; break;
           case B_T: b = p->T; break;
           case B_U: b = p->U; break;
+          case B_P: b = p->Pp; break;
           case B_X: base = REF_X; return;
           case B_Y: base = REF_Y; return;
         }
@@ -361,6 +443,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     }
     cudaMemset(p->T, 0, p->t_elems * sizeof(double));
     cudaMemset(p->U, 0, p->u_elems * sizeof(double));
+    cudaMemset(p->Pp, 0, p->p_elems * sizeof(double));
     if ((rc = to_device(ctx, itemsL, &p->itemsL)) || (rc = to_device(ctx, segsL, &p->segsL)) ||
         (rc = to_device(ctx, itemsR, &p->itemsR)) || (rc = to_device(ctx, segsR, &p->segsR)) ||
         (rc = to_device(ctx, mixT, &p->mixT)) || (rc = to_device(ctx, mixS, &p->mixS)) ||
@@ -375,6 +458,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     p->nmixT = (int)mixT.size();
     p->nmixS = (int)mixS.size();
     p->nmixC = (int)mixC.size();
+    p->nmixCU = nmixCU;
     const int cap = ctx->sm_count * gemm_max_ctas_per_sm();
     p->gridL = std::max(1, std::min(p->nitemsL, cap));
     p->gridR = std::max(1, std::min(p->nitemsR, cap));
@@ -385,11 +469,11 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     p->stats[4] = (double)ub.size();
     p->stats[5] = (double)mixT.size();
     p->stats[6] = (double)mixS.size();
-    p->stats[7] = (double)(p->t_elems + p->u_elems) * sizeof(double);
+    p->stats[7] = (double)(p->t_elems + p->u_elems + p->p_elems) * sizeof(double);
     p->stats[8] = (double)itemsL.size();
     p->stats[9] = (double)itemsR.size();
     p->stats[10] = padded;
-    p->stats[11] = (p->nitemsL > 0) + (p->nmixC > 0) + (p->nitemsR > 0);
+    p->stats[11] = (p->nitemsL > 0) + (p->nmixCU > 0) + (p->nitemsR > 0) + (p->nmixC > p->nmixCU);
   } catch (const std::bad_alloc&) {
     if (p) htn_plan_destroy(p);
     return ctx->fail(HTN_ERR_OOM, "plan_heff_ac: host allocation failed");
@@ -408,15 +492,16 @@ static int32_t check_xy(htn_plan* p, const htn_tensor* x, const htn_tensor* y) {
   return HTN_OK;
 }
 
-// stage mask: 1 = L, 2 = W, 4 = R
+// stage mask: 1 = L (T = GL.x), 2 = W (U = mix T), 4 = R (partials = U.GR), 8 = final mix (y)
 static int32_t run_stages(htn_plan* p, const htn_tensor* x, htn_tensor* y, int mask) {
   htn_ctx* ctx = p->ctx;
   Bases bs;
   bs.x = x->d;
   bs.y = y->d;
   if (mask & 1) launch_gemm(p->itemsL, p->segsL, p->nitemsL, bs, p->gridL, ctx->stream);
-  if (mask & 2) launch_mix(p->mixT, p->mixS, p->mixC, p->nmixC, bs, ctx->stream);
+  if (mask & 2) launch_mix(p->mixT, p->mixS, p->mixC, p->nmixCU, bs, ctx->stream);
   if (mask & 4) launch_gemm(p->itemsR, p->segsR, p->nitemsR, bs, p->gridR, ctx->stream);
+  if (mask & 8) launch_mix(p->mixT, p->mixS, p->mixC + p->nmixCU, p->nmixC - p->nmixCU, bs, ctx->stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("heff_apply launch: ") + cudaGetErrorString(e));
   return HTN_OK;
@@ -428,7 +513,7 @@ int32_t htn_heff_apply(htn_plan* p, const htn_tensor* x, htn_tensor* y) {
   int32_t rc = check_xy(p, x, y);
   if (rc) return rc;
   cudaSetDevice(p->ctx->device);
-  return run_stages(p, x, y, 7);
+  return run_stages(p, x, y, 15);
 }
 
 int32_t htn_heff_apply_host(htn_plan* p, const double* x_host, double* y_host, int64_t nelem) {
@@ -442,7 +527,7 @@ int32_t htn_heff_apply_host(htn_plan* p, const double* x_host, double* y_host, i
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   if ((rc = htn_upload_locked(p->hx, x_host, nelem))) return rc;
-  if ((rc = run_stages(p, p->hx, p->hy, 7))) return rc;
+  if ((rc = run_stages(p, p->hx, p->hy, 15))) return rc;
   return htn_download_locked(p->hy, y_host, nelem);
 }
 
@@ -458,7 +543,7 @@ int32_t htn_heff_time(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_t r
   cudaEventCreate(&e1);
   cudaStreamSynchronize(ctx->stream);
   cudaEventRecord(e0, ctx->stream);
-  for (int r = 0; r < reps && rc == HTN_OK; ++r) rc = run_stages(p, x, y, 7);
+  for (int r = 0; r < reps && rc == HTN_OK; ++r) rc = run_stages(p, x, y, 15);
   cudaEventRecord(e1, ctx->stream);
   cudaError_t e = cudaEventSynchronize(e1);
   if (rc == HTN_OK && e != cudaSuccess) rc = ctx->fail(HTN_ERR_CUDA, std::string("heff_time: ") + cudaGetErrorString(e));
@@ -486,7 +571,7 @@ int32_t htn_plan_profile(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int masks[4] = {7, 1, 2, 4};
+  const int masks[4] = {15, 1, 2 | 8, 4};
   for (int k = 0; k < 4; ++k) {
     cudaStreamSynchronize(ctx->stream);
     cudaEventRecord(e0, ctx->stream);
@@ -502,7 +587,7 @@ int32_t htn_plan_profile(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  if (rc == HTN_OK) rc = run_stages(p, x, y, 7);  // leave y = H x behind
+  if (rc == HTN_OK) rc = run_stages(p, x, y, 15);  // leave y = H x behind
   return rc;
 }
 

@@ -40,6 +40,8 @@ def bond_space(sym: int, D: int, btype: int) -> dict:
     tot = sum(w.values())
     mult = {s: int(round(D * v / tot)) for s, v in w.items()}
     mult = {s: n for s, n in mult.items() if n > 0}
+    if not mult:                       # D too small for any rounded multiplicity
+        mult = {max(w, key=lambda s: w[s]): 0}
     big = max(mult, key=lambda s: (mult[s], -abs(s[2]), -abs(s[1])))
     mult[big] += D - sum(mult.values())
     return mult

@@ -55,6 +55,8 @@ def synthetic_bond_space(kind: int, D: int, btype: int = 0) -> Space:
     tot = sum(w.values())
     mult = {s: int(round(D * v / tot)) for s, v in w.items()}
     mult = {s: n for s, n in mult.items() if n > 0}
+    if not mult:                       # D too small for any rounded multiplicity
+        mult = {max(w, key=lambda s: w[s]): 0}
     big = max(mult, key=lambda s: (mult[s], -abs(s[2]), -abs(s[1])))
     mult[big] += D - sum(mult.values())
     return Space(kind, mult)
