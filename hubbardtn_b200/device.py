@@ -41,9 +41,11 @@ class Context:
         return out.value
 
     def close(self):
+        """Destroy the context.  Handles created from it become inert (their destructors
+        check `ctx.h`); the C ABI itself requires children to be destroyed first."""
         if self.h:
-            lib.htn_ctx_destroy(self.h)
-            self.h = None
+            h, self.h = self.h, None
+            lib.htn_ctx_destroy(h)
 
     def __del__(self):
         try:
@@ -74,9 +76,9 @@ class Space:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:      # a closed context has already released the device
                 lib.htn_space_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -97,9 +99,9 @@ class Legs:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:      # a closed context has already released the device
                 lib.htn_legs_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -179,9 +181,9 @@ class Tensor:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:      # a closed context has already released the device
                 lib.htn_tensor_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -205,9 +207,9 @@ class Mpo:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:      # a closed context has already released the device
                 lib.htn_mpo_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -257,9 +259,9 @@ class HeffAC:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:      # a closed context has already released the device
                 lib.htn_plan_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
