@@ -133,13 +133,16 @@ __host__ __device__ inline const double* resolve(long long v, int base, const Ba
 }
 
 // one K-segment of a grouped GEMM work item:  C_tile += coef * A_seg[mt x K] * B_seg[K x nt]
+// If nsrc > 0 the A operand is not read from one array but assembled on the fly as
+// sum_j srcs[src_begin + j].coef * (source block j) -- the stage-W recoupling mix fused into the
+// operand load of stage R (all sources share the shape and leading dimension lda).
 struct GemmSeg {
-  long long a_off, b_off;  // element offsets from the bases
+  long long a_off, b_off;  // element offsets from the bases (or absolute pointers, see Ref)
   int a_base, b_base;
   int lda, ldb;
   int K;
+  int nsrc, src_begin;
   int pad_;
-  double coef;
 };
 
 struct GemmItem {
@@ -167,13 +170,11 @@ struct MixTarget {
 };
 
 struct MixChunk {
-  int target, elem0;
+  int target, elem0, nelem, pad_;
 };
 
-constexpr int MIX_CHUNK = 4096;
-
-void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, Bases bases, int grid,
-                 cudaStream_t st);
+void launch_gemm(const GemmItem* items, const GemmSeg* segs, const MixSrc* srcs, int nitems, Bases bases,
+                 int grid, cudaStream_t st);
 void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, Bases bases,
                 cudaStream_t st);
 void launch_pack(const DevBlock* blocks, const int* chunks, int nchunks, const double* packed, double* padded,
@@ -196,9 +197,9 @@ struct htn_plan {
   const htn_tensor* GR;
   htn_tensor* like;  // private structural copy (no data use)
   double* T = nullptr;
-  double* U = nullptr;
+  htn::MixSrc* gsrcs = nullptr;  // fused stage-W sources of the stage-R A operand
   double* Pp = nullptr;  // split-K partial outputs of stage R: nsplit_max copies of the y layout
-  int64_t t_elems = 0, u_elems = 0, p_elems = 0;
+  int64_t t_elems = 0, u_elems = 0, p_elems = 0;  // u_elems: size U would have (never materialised)
   // device tables
   htn::GemmItem* itemsL = nullptr;
   htn::GemmSeg* segsL = nullptr;

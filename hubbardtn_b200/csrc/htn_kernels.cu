@@ -41,26 +41,51 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // grouped GEMM
 // ------------------------------------------------------------------------------------
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 3;
-constexpr int NTHREADS = 128;
+constexpr int STAGES = 4;
+constexpr int NCONS_WARPS = 4, NPROD_WARPS = 4;
+constexpr int NPROD = NPROD_WARPS * 32;
+constexpr int NTHREADS = (NCONS_WARPS + NPROD_WARPS) * 32;
 constexpr int LDAS = BK + 4;  // 20 doubles: (g*20 + t) mod 16 distinct over a half warp
 constexpr int LDBS = BN + 4;  // 68 doubles: (t*68 + g) mod 16 distinct over a half warp
 constexpr int A_STAGE = BM * LDAS;
 constexpr int B_STAGE = BK * LDBS;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double) + 2 * STAGES * 8 + STAGES * 4 + 64;
 
-// Work distribution inside a CTA (4 warps).  A tile is MA x NA DMMA atoms (8x8 each, <= 8x8
-// atoms).  One dimension is "fixed": it is cut into 4 strips of 2 atoms, one strip per warp
-// role; the other ("flex") dimension has 1..8 atoms and every warp covers all of it.  All
-// warps therefore do the same work, block extents are padded only to the atom size 8, and
-// the inner loop is straight-line code specialised on the flex extent (no predication).
+// ---- mbarrier helpers (producer/consumer ring; CTA scope) ----------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive once all cp.async issued so far by this thread have landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// Work distribution inside a CTA.  Warps 0-3 are CONSUMERS (DMMA only), warps 4-7 PRODUCERS
+// (operand staging).  A tile is MA x NA DMMA atoms (8x8 each, <= 8x8 atoms).  One dimension is
+// "fixed": it is cut into 4 strips of 2 atoms, one strip per consumer role; the other ("flex")
+// dimension has 1..8 atoms and every consumer covers all of it.  All consumers therefore do the
+// same work, block extents are padded only to the atom size 8, and the inner loop is
+// straight-line code specialised on the flex extent (no predication).
 //   layout 0 (LAY_A): flex = M (rows), fixed = N: role w owns col atoms 2w, 2w+1
 //   layout 1 (LAY_B): flex = N (cols), fixed = M: role w owns row atoms 2w, 2w+1
 // acc[flex atom][fixed atom f][2 values of the DMMA C fragment].
 template <int FLEX, bool LAYB>
 __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __restrict__ as,
                                        const double* __restrict__ bs, int kk) {
-  // as -> A stage + (g * LDAS + t) [+ role offset for LAY_B]; bs -> B stage + (t * LDBS + g) [+ role offset for LAY_A]
   double fx[FLEX], ff[2];
   if (!LAYB) {
 #pragma unroll
@@ -112,146 +137,220 @@ __device__ __forceinline__ void mma_dispatch(int flex, double (&acc)[8][2][2], c
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 4)
-grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
-                    Bases bases) {
+__global__ void __launch_bounds__(NTHREADS, 2)
+grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs,
+                    const MixSrc* __restrict__ srcs, int nitems, Bases bases) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + STAGES * B_STAGE);
+  uint64_t* empty = full + STAGES;
+  int* meta = reinterpret_cast<int*>(empty + STAGES);  // nk4 of the chunk held by each stage
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
 
-  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const GemmItem item = items[it];
-    const int mt = item.mt, nt = item.nt;
-    const bool layb = item.layout != 0;
-    // rotate the strip a warp owns from item to item so that partially filled strips do not
-    // always land on the same SM sub-partition (warp id % 4)
-    const int role = (warp + it) & 3;
-    const int flex = ((layb ? nt : mt) + 7) >> 3;
-    const int fixed_ext = layb ? mt : nt;
-    const bool active = role * 16 < fixed_ext;  // warp-uniform: this strip holds data
-
-    double acc[8][2][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-
-    // ---- producer: issue the loads of one chunk into stage `st` -----------------------
-    int pseg_i = item.seg_begin, pk0 = 0;
-    GemmSeg pseg = segs[pseg_i];
-    auto issue = [&](int st) {
-      const double* Ag = resolve(pseg.a_off, pseg.a_base, bases);
-      const double* Bg = resolve(pseg.b_off, pseg.b_base, bases);
-      const int K = pseg.K, k0 = pk0;
-      double* as = As + st * A_STAGE;
-      double* bs = Bs + st * B_STAGE;
-#pragma unroll
-      for (int q = 0; q < (BM * BK / 2) / NTHREADS; ++q) {  // 4
-        int sid = tid + q * NTHREADS;
-        int row = sid >> 3, sg = sid & 7;
-        int k = k0 + sg * 2;
-        int bytes = (row < mt) ? (K - k) * 8 : 0;
-        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-        const double* src = bytes ? (Ag + (long long)row * pseg.lda + k) : Ag;
-        cp_async16(as + row * LDAS + sg * 2, src, bytes);
-      }
-#pragma unroll
-      for (int q = 0; q < (BK * BN / 2) / NTHREADS; ++q) {  // 4
-        int sid = tid + q * NTHREADS;
-        int row = sid >> 5, sg = sid & 31;
-        int k = k0 + row;
-        int bytes = (k < K) ? (nt - sg * 2) * 8 : 0;
-        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-        const double* src = bytes ? (Bg + (long long)k * pseg.ldb + sg * 2) : Bg;
-        cp_async16(bs + row * LDBS + sg * 2, src, bytes);
-      }
-      pk0 += BK;
-      if (pk0 >= K) {
-        pk0 = 0;
-        pseg_i++;
-        if (pseg_i < item.seg_end) pseg = segs[pseg_i];
-      }
-    };
-
-    const int nchunks = item.nchunks;
-    int issued = 0;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-      if (issued < nchunks) {
-        issue(s);
-        ++issued;
-      }
-      cp_async_commit();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 2 * NPROD);   // per producer thread: one plain arrive + one cp.async arrive
+      mbar_init(&empty[s], NCONS_WARPS);  // one elected lane per consumer warp
     }
+  }
+  __syncthreads();
+  if (blockIdx.x >= nitems) return;
 
-    // ---- consumer ---------------------------------------------------------------------
-    int cseg_i = item.seg_begin, ck0 = 0;
-    int cK = segs[cseg_i].K;
-    const int a_role = layb ? role * 16 * LDAS : 0;
-    const int b_role = layb ? 0 : role * 16;
-    for (int c = 0; c < nchunks; ++c) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      if (issued < nchunks) {
-        issue((c + STAGES - 1) % STAGES);
-        ++issued;
+  int stage = 0;
+  unsigned phase = 0;
+
+  if (warp >= NCONS_WARPS) {
+    // =========================== PRODUCER ===========================================
+    const int ptid = tid - NCONS_WARPS * 32;
+    int it = blockIdx.x;
+    GemmItem item = items[it];
+    while (true) {
+      const int itn = it + gridDim.x;
+      GemmItem next_item = item;
+      if (itn < nitems) next_item = items[itn];  // prefetch: consumed at the next iteration
+      const int mt = item.mt, nt = item.nt;
+      GemmSeg sg = segs[item.seg_begin];
+      for (int si = item.seg_begin; si < item.seg_end; ++si) {
+        GemmSeg sg_next = sg;
+        if (si + 1 < item.seg_end) sg_next = segs[si + 1];
+        const int K = sg.K;
+        const double* Bg = resolve(sg.b_off, sg.b_base, bases);
+        const double* Ag = sg.nsrc ? nullptr : resolve(sg.a_off, sg.a_base, bases);
+        for (int k0 = 0; k0 < K; k0 += BK) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          double* as = As + stage * A_STAGE;
+          double* bs = Bs + stage * B_STAGE;
+          // ---- B operand: 16 x 64 chunk, 16-byte cp.async with zero fill ------------------
+#pragma unroll
+          for (int q = 0; q < (BK * BN / 2) / NPROD; ++q) {  // 4
+            int sid = ptid + q * NPROD;
+            int row = sid >> 5, sgm = sid & 31;
+            int k = k0 + row;
+            int bytes = (k < K) ? (nt - sgm * 2) * 8 : 0;
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+            const double* src = bytes ? (Bg + (long long)k * sg.ldb + sgm * 2) : Bg;
+            cp_async16(bs + row * LDBS + sgm * 2, src, bytes);
+          }
+          if (sg.nsrc == 0) {
+            // ---- A operand straight from one array ----------------------------------------
+#pragma unroll
+            for (int q = 0; q < (BM * BK / 2) / NPROD; ++q) {  // 4
+              int sid = ptid + q * NPROD;
+              int row = sid >> 3, sgm = sid & 7;
+              int k = k0 + sgm * 2;
+              int bytes = (row < mt) ? (K - k) * 8 : 0;
+              bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+              const double* src = bytes ? (Ag + (long long)row * sg.lda + k) : Ag;
+              cp_async16(as + row * LDAS + sgm * 2, src, bytes);
+            }
+          } else {
+            // ---- A operand = sum_j coef_j * source_j (fused stage W) ------------------------
+            double2 acc2[4];
+            long long off[4];
+            bool ok[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              int sid = ptid + q * NPROD;
+              int row = sid >> 3, k = k0 + (sid & 7) * 2;
+              ok[q] = row < mt && k < K;  // (k+1 may be the zero pad column when K is odd)
+              off[q] = sg.a_off + (long long)row * sg.lda + k;
+              acc2[q] = make_double2(0.0, 0.0);
+            }
+            const MixSrc* sp = srcs + sg.src_begin;
+            int j = 0;
+            for (; j + 2 <= sg.nsrc; j += 2) {
+              const MixSrc s0 = sp[j], s1 = sp[j + 1];
+              const double* p0 = resolve(s0.off, s0.base, bases);
+              const double* p1 = resolve(s1.off, s1.base, bases);
+              double2 v0[4], v1[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v0[q] = ok[q] ? __ldg(reinterpret_cast<const double2*>(p0 + off[q])) : make_double2(0.0, 0.0);
+                v1[q] = ok[q] ? __ldg(reinterpret_cast<const double2*>(p1 + off[q])) : make_double2(0.0, 0.0);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                acc2[q].x = fma(s0.coef, v0[q].x, acc2[q].x);
+                acc2[q].y = fma(s0.coef, v0[q].y, acc2[q].y);
+                acc2[q].x = fma(s1.coef, v1[q].x, acc2[q].x);
+                acc2[q].y = fma(s1.coef, v1[q].y, acc2[q].y);
+              }
+            }
+            if (j < sg.nsrc) {
+              const MixSrc s0 = sp[j];
+              const double* p0 = resolve(s0.off, s0.base, bases);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                double2 v = ok[q] ? __ldg(reinterpret_cast<const double2*>(p0 + off[q])) : make_double2(0.0, 0.0);
+                acc2[q].x = fma(s0.coef, v.x, acc2[q].x);
+                acc2[q].y = fma(s0.coef, v.y, acc2[q].y);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              int sid = ptid + q * NPROD;
+              *reinterpret_cast<double2*>(as + (sid >> 3) * LDAS + (sid & 7) * 2) = acc2[q];
+            }
+          }
+          if (ptid == 0) {
+            int krem = K - k0;
+            meta[stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
+          }
+          cp_async_mbar_arrive(&full[stage]);
+          mbar_arrive(&full[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        sg = sg_next;
       }
-      cp_async_commit();
+      if (itn >= nitems) break;
+      it = itn;
+      item = next_item;
+    }
+  } else {
+    // =========================== CONSUMER ===========================================
+    const int g = lane >> 2, t = lane & 3;
+    int it = blockIdx.x;
+    GemmItem item = items[it];
+    while (true) {
+      const int itn = it + gridDim.x;
+      GemmItem next_item = item;
+      if (itn < nitems) next_item = items[itn];
+      const int mt = item.mt, nt = item.nt;
+      const bool layb = item.layout != 0;
+      // rotate the strip a warp owns from item to item so that partially filled strips do not
+      // always land on the same SM sub-partition (warp id % 4)
+      const int role = (warp + it) & 3;
+      const int flex = ((layb ? nt : mt) + 7) >> 3;
+      const bool active = role * 16 < (layb ? mt : nt);  // warp-uniform: this strip holds data
+      const int a_role = layb ? role * 16 * LDAS : 0;
+      const int b_role = layb ? 0 : role * 16;
 
-      int krem = cK - ck0;
-      const int nk4 = krem >= BK ? BK / 4 : (krem + 3) >> 2;
+      double acc[8][2][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+
+      const int nchunks = item.nchunks;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        if (active) {
+          const int nk4 = meta[stage];
+          const double* as = As + stage * A_STAGE + g * LDAS + t + a_role;
+          const double* bs = Bs + stage * B_STAGE + t * LDBS + g + b_role;
+          if (layb)
+            mma_dispatch<true>(flex, acc, as, bs, nk4);
+          else
+            mma_dispatch<false>(flex, acc, as, bs, nk4);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+
+      // ---- epilogue -------------------------------------------------------------------
       if (active) {
-        const double* as = As + (c % STAGES) * A_STAGE + g * LDAS + t + a_role;
-        const double* bs = Bs + (c % STAGES) * B_STAGE + t * LDBS + g + b_role;
-        if (layb)
-          mma_dispatch<true>(flex, acc, as, bs, nk4);
-        else
-          mma_dispatch<false>(flex, acc, as, bs, nk4);
-      }
-      ck0 += BK;
-      if (ck0 >= cK) {
-        ck0 = 0;
-        cseg_i++;
-        if (cseg_i < item.seg_end) cK = segs[cseg_i].K;
-      }
-    }
-    cp_async_wait<0>();
-
-    // ---- epilogue ---------------------------------------------------------------------
-    if (active) {
-      double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
-      const int ldc = item.ldc;
+        double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
+        const int ldc = item.ldc;
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        if (x < flex) {
+        for (int x = 0; x < 8; ++x) {
+          if (x < flex) {
 #pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            const int ra = layb ? (role * 2 + f) : x;  // row atom
-            const int ca = layb ? x : (role * 2 + f);  // col atom
-            const int row = ra * 8 + g, col = ca * 8 + 2 * t;
-            if (row < mt && col < nt) {
-              double* p = C + (long long)row * ldc + col;
-              if (col + 1 < nt) {
-                double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
-                if (item.beta) {
-                  double2 o = *reinterpret_cast<double2*>(p);
-                  v.x += o.x;
-                  v.y += o.y;
+            for (int f = 0; f < 2; ++f) {
+              const int ra = layb ? (role * 2 + f) : x;  // row atom
+              const int ca = layb ? x : (role * 2 + f);  // col atom
+              const int row = ra * 8 + g, col = ca * 8 + 2 * t;
+              if (row < mt && col < nt) {
+                double* p = C + (long long)row * ldc + col;
+                if (col + 1 < nt) {
+                  double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
+                  if (item.beta) {
+                    double2 o = *reinterpret_cast<double2*>(p);
+                    v.x += o.x;
+                    v.y += o.y;
+                  }
+                  *reinterpret_cast<double2*>(p) = v;
+                } else {
+                  double v = acc[x][f][0];
+                  if (item.beta) v += *p;
+                  *p = v;
                 }
-                *reinterpret_cast<double2*>(p) = v;
-              } else {
-                double v = acc[x][f][0];
-                if (item.beta) v += *p;
-                *p = v;
               }
             }
           }
         }
       }
+      if (itn >= nitems) break;
+      it = itn;
+      item = next_item;
     }
-    __syncthreads();  // all warps done with smem before the next item's prologue refills it
   }
 }
 
@@ -265,37 +364,68 @@ int gemm_max_ctas_per_sm() {
   return cached;
 }
 
-void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, Bases bases, int grid,
-                 cudaStream_t st) {
+void launch_gemm(const GemmItem* items, const GemmSeg* segs, const MixSrc* srcs, int nitems, Bases bases,
+                 int grid, cudaStream_t st) {
   if (nitems <= 0) return;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
     attr = true;
   }
-  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases);
+  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, srcs, nitems, bases);
 }
 
 // ------------------------------------------------------------------------------------
+// final mix: y = sum coef * (T block | x block | split-K partial).  One CTA per chunk of a
+// target; chunk sizes shrink with the number of sources so that every CTA streams a similar
+// number of bytes; source descriptors are staged in shared memory; loads are unrolled x4.
 // ------------------------------------------------------------------------------------
-// stage W: block linear combinations
-// ------------------------------------------------------------------------------------
+constexpr int MIX_MAX_SRC_SMEM = 128;
+
 __global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ tg, const MixSrc* __restrict__ src,
                                                   const MixChunk* __restrict__ chunks, Bases bases) {
+  __shared__ const double* sptr[MIX_MAX_SRC_SMEM];
+  __shared__ double scoef[MIX_MAX_SRC_SMEM];
   const MixChunk ch = chunks[blockIdx.x];
   const MixTarget T = tg[ch.target];
   double* dst = const_cast<double*>(resolve(T.off, T.base, bases));
-  const int end = min(T.nelem, ch.elem0 + MIX_CHUNK);
-  // all blocks have even ld and 16-byte aligned offsets: work in double2
-  for (int e = ch.elem0 + 2 * threadIdx.x; e < end; e += 2 * blockDim.x) {
-    double2 acc = make_double2(0.0, 0.0);
-    for (int s = T.src_begin; s < T.src_end; ++s) {
-      const MixSrc S = src[s];
-      const double2 v = *reinterpret_cast<const double2*>(resolve(S.off, S.base, bases) + e);
-      acc.x = fma(S.coef, v.x, acc.x);
-      acc.y = fma(S.coef, v.y, acc.y);
+  const int nsrc = T.src_end - T.src_begin;
+  const int end = ch.elem0 + ch.nelem;
+  for (int s0 = 0; s0 < nsrc || s0 == 0; s0 += MIX_MAX_SRC_SMEM) {
+    const int ns = min(MIX_MAX_SRC_SMEM, nsrc - s0);
+    __syncthreads();
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+      const MixSrc S = src[T.src_begin + s0 + s];
+      sptr[s] = resolve(S.off, S.base, bases);
+      scoef[s] = S.coef;
     }
-    *reinterpret_cast<double2*>(dst + e) = acc;
+    __syncthreads();
+    // all blocks have even ld and 16-byte aligned offsets: work in double2
+    for (int e = ch.elem0 + 2 * threadIdx.x; e < end; e += 2 * blockDim.x) {
+      double2 acc = (s0 == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<double2*>(dst + e);
+      int s = 0;
+      for (; s + 4 <= ns; s += 4) {
+        const double2 v0 = __ldg(reinterpret_cast<const double2*>(sptr[s] + e));
+        const double2 v1 = __ldg(reinterpret_cast<const double2*>(sptr[s + 1] + e));
+        const double2 v2 = __ldg(reinterpret_cast<const double2*>(sptr[s + 2] + e));
+        const double2 v3 = __ldg(reinterpret_cast<const double2*>(sptr[s + 3] + e));
+        acc.x = fma(scoef[s], v0.x, acc.x);
+        acc.y = fma(scoef[s], v0.y, acc.y);
+        acc.x = fma(scoef[s + 1], v1.x, acc.x);
+        acc.y = fma(scoef[s + 1], v1.y, acc.y);
+        acc.x = fma(scoef[s + 2], v2.x, acc.x);
+        acc.y = fma(scoef[s + 2], v2.y, acc.y);
+        acc.x = fma(scoef[s + 3], v3.x, acc.x);
+        acc.y = fma(scoef[s + 3], v3.y, acc.y);
+      }
+      for (; s < ns; ++s) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(sptr[s] + e));
+        acc.x = fma(scoef[s], v.x, acc.x);
+        acc.y = fma(scoef[s], v.y, acc.y);
+      }
+      *reinterpret_cast<double2*>(dst + e) = acc;
+    }
+    if (nsrc == 0) break;
   }
 }
 
@@ -305,6 +435,7 @@ void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, 
   mix_kernel<<<nchunks, 256, 0, st>>>(tg, src, chunks, bases);
 }
 
+// ------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------
 // pack / unpack (packed host layout <-> padded arena), dot, axpby
 // chunk table: int3-like triples (block, row0, nrows)

@@ -122,7 +122,7 @@ int32_t htn_plan_destroy(htn_plan* p) {
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
   cudaFree(p->T);
-  cudaFree(p->U);
+  cudaFree(p->gsrcs);
   cudaFree(p->Pp);
   cudaFree(p->itemsL);
   cudaFree(p->segsL);
@@ -279,7 +279,8 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
         sg.b_off = xb.off + ts.no;
         sg.ldb = xb.ld;
         sg.K = gl.cols;
-        sg.coef = 1.0;
+        sg.nsrc = 0;
+        sg.src_begin = 0;
         GemmItem it{};
         it.c_base = B_T;
         it.c_off = w.off + (int64_t)ts.mo * w.ld + ts.no;
@@ -306,6 +307,12 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     }
     std::vector<GemmItem> itemsR;
     std::vector<GemmSeg> segsR;
+    std::vector<MixSrc> gsrcs;  // mix sources of the (virtual) U blocks, read by the stage-R producers
+    std::vector<int> usrc_begin(ub.size(), 0);
+    for (size_t ui = 0; ui < ub.size(); ++ui) {
+      usrc_begin[ui] = (int)gsrcs.size();
+      for (const Src& sc : usrc[ui]) gsrcs.push_back(MixSrc{sc.off, sc.base, 0, sc.coef});
+    }
     // split-K: a y block has few tiles but a K loop over every (level, sector) pair; cut the
     // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy
     // of the y tile (summed in fixed order by the final mix => deterministic)
@@ -353,14 +360,16 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
             const Block& gr = GR->blocks[GR->find(b, r, rp)];
             const WsBlock& w = ub[ui];
             GemmSeg sg{};
-            sg.a_base = B_U;
-            sg.a_off = w.off + (int64_t)ts.mo * w.ld;
+            // A operand = sum_j coef_j * source_j, rows ts.mo.. of every source block (fused stage W)
+            sg.a_base = B_X;  // unused when nsrc > 0
+            sg.a_off = (int64_t)ts.mo * w.ld;
             sg.lda = w.ld;
+            sg.nsrc = (int)usrc[ui].size();
+            sg.src_begin = usrc_begin[ui];
             sg.b_base = B_GR;
             sg.b_off = gr.off + ts.no;
             sg.ldb = gr.ld;
             sg.K = gr.rows;
-            sg.coef = 1.0;
             segsR.push_back(sg);
             it.nchunks += (sg.K + GEMM_BK - 1) / GEMM_BK;
             padded += 2.0 * ((ts.mn + 7) / 8 * 8) * ((ts.nn + 7) / 8 * 8) * ((sg.K + 3) / 4 * 4.0);
@@ -399,10 +408,12 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
       t.src_end = (int)mixS.size();
       int ti = (int)mixT.size();
       mixT.push_back(t);
-      for (int e = 0; e < nelem; e += MIX_CHUNK) mixC.push_back(MixChunk{ti, e});
+      // ~16k element-sources per CTA, chunk a multiple of 512 elements (256 threads x double2)
+      int per = 16384 / std::max<int>(1, (int)srcs.size());
+      per = std::max(512, std::min(8192, per / 512 * 512));
+      for (int e = 0; e < nelem; e += per) mixC.push_back(MixChunk{ti, e, std::min(per, nelem - e), 0});
     };
-    for (size_t ui = 0; ui < ub.size(); ++ui) add_target(B_U, ub[ui].off, ub[ui].rows * ub[ui].ld, usrc[ui]);
-    const int nmixCU = (int)mixC.size();
+    const int nmixCU = 0;  // stage W for the U blocks is fused into stage R (no separate launch)
     for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
       const Block& yb = like->blocks[yi];
       add_target(B_Y, yb.off, yb.rows * yb.ld, ysrc[yi]);
@@ -411,7 +422,6 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     // ---- upload ------------------------------------------------------------------------------
     cudaSetDevice(ctx->device);
     if (cudaMalloc(&p->T, p->t_elems * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&p->U, p->u_elems * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&p->Pp, p->p_elems * sizeof(double)) != cudaSuccess) {
       htn_plan_destroy(p);
       return ctx->fail(HTN_ERR_OOM, "plan_heff_ac: workspace allocation failed");
@@ -423,7 +433,6 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
           case B_GL: b = GL->d; break;
           case B_GR: b = GR->d; break;
           case B_T: b = p->T; break;
-          case B_U: b = p->U; break;
           case B_P: b = p->Pp; break;
           case B_X: base = REF_X; return;
           case B_Y: base = REF_Y; return;
@@ -433,20 +442,20 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
       };
       for (auto* segs : {&segsL, &segsR})
         for (GemmSeg& sg : *segs) {
-          fix(sg.a_off, sg.a_base);
+          if (sg.nsrc == 0) fix(sg.a_off, sg.a_base);
           fix(sg.b_off, sg.b_base);
         }
+      for (MixSrc& sc : gsrcs) fix(sc.off, sc.base);
       for (auto* items : {&itemsL, &itemsR})
         for (GemmItem& it : *items) fix(it.c_off, it.c_base);
       for (MixTarget& t : mixT) fix(t.off, t.base);
       for (MixSrc& sc : mixS) fix(sc.off, sc.base);
     }
     cudaMemset(p->T, 0, p->t_elems * sizeof(double));
-    cudaMemset(p->U, 0, p->u_elems * sizeof(double));
     cudaMemset(p->Pp, 0, p->p_elems * sizeof(double));
     if ((rc = to_device(ctx, itemsL, &p->itemsL)) || (rc = to_device(ctx, segsL, &p->segsL)) ||
         (rc = to_device(ctx, itemsR, &p->itemsR)) || (rc = to_device(ctx, segsR, &p->segsR)) ||
-        (rc = to_device(ctx, mixT, &p->mixT)) || (rc = to_device(ctx, mixS, &p->mixS)) ||
+        (rc = to_device(ctx, gsrcs, &p->gsrcs)) || (rc = to_device(ctx, mixT, &p->mixT)) || (rc = to_device(ctx, mixS, &p->mixS)) ||
         (rc = to_device(ctx, mixC, &p->mixC))) {
       htn_plan_destroy(p);
       return rc;
@@ -468,8 +477,8 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     p->stats[3] = (double)tb.size();
     p->stats[4] = (double)ub.size();
     p->stats[5] = (double)mixT.size();
-    p->stats[6] = (double)mixS.size();
-    p->stats[7] = (double)(p->t_elems + p->u_elems + p->p_elems) * sizeof(double);
+    p->stats[6] = (double)(mixS.size() + gsrcs.size());
+    p->stats[7] = (double)(p->t_elems + p->p_elems) * sizeof(double);
     p->stats[8] = (double)itemsL.size();
     p->stats[9] = (double)itemsR.size();
     p->stats[10] = padded;
@@ -498,9 +507,9 @@ static int32_t run_stages(htn_plan* p, const htn_tensor* x, htn_tensor* y, int m
   Bases bs;
   bs.x = x->d;
   bs.y = y->d;
-  if (mask & 1) launch_gemm(p->itemsL, p->segsL, p->nitemsL, bs, p->gridL, ctx->stream);
+  if (mask & 1) launch_gemm(p->itemsL, p->segsL, p->gsrcs, p->nitemsL, bs, p->gridL, ctx->stream);
   if (mask & 2) launch_mix(p->mixT, p->mixS, p->mixC, p->nmixCU, bs, ctx->stream);
-  if (mask & 4) launch_gemm(p->itemsR, p->segsR, p->nitemsR, bs, p->gridR, ctx->stream);
+  if (mask & 4) launch_gemm(p->itemsR, p->segsR, p->gsrcs, p->nitemsR, bs, p->gridR, ctx->stream);
   if (mask & 8) launch_mix(p->mixT, p->mixS, p->mixC + p->nmixCU, p->nmixC - p->nmixCU, bs, ctx->stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("heff_apply launch: ") + cudaGetErrorString(e));
