@@ -197,7 +197,8 @@ struct htn_plan {
   const htn_tensor* GR;
   htn_tensor* like;  // private structural copy (no data use)
   double* T = nullptr;
-  htn::MixSrc* gsrcs = nullptr;  // fused stage-W sources of the stage-R A operand
+  htn::MixSrc* gsrcs = nullptr;  // fused stage-W sources of the stage-R A operand (HTN_FUSE_W=1)
+  double* U = nullptr;
   double* Pp = nullptr;  // split-K partial outputs of stage R: nsplit_max copies of the y layout
   int64_t t_elems = 0, u_elems = 0, p_elems = 0;  // u_elems: size U would have (never materialised)
   // device tables

@@ -12,6 +12,7 @@
 //   stage R  grouped GEMM : y[l',s',r']    += sum_{b,r} U[b,l',s',r',r] . GR[b,r,r']
 // Identity environment levels (GL[1] = 1, GR[chi] = 1) are elided exactly.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -123,6 +124,7 @@ int32_t htn_plan_destroy(htn_plan* p) {
   cudaStreamSynchronize(p->ctx->stream);
   cudaFree(p->T);
   cudaFree(p->gsrcs);
+  cudaFree(p->U);
   cudaFree(p->Pp);
   cudaFree(p->itemsL);
   cudaFree(p->segsL);
@@ -307,7 +309,11 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     }
     std::vector<GemmItem> itemsR;
     std::vector<GemmSeg> segsR;
-    std::vector<MixSrc> gsrcs;  // mix sources of the (virtual) U blocks, read by the stage-R producers
+    // HTN_FUSE_W=1: assemble U inside the stage-R operand load instead of materialising it
+    // (measured slower on B200 at D=1024: the producers become latency-bound; kept selectable)
+    const char* fw = getenv("HTN_FUSE_W");
+    const bool fuse_w = fw && fw[0] == '1';
+    std::vector<MixSrc> gsrcs;  // mix sources of the U blocks when fused into stage R
     std::vector<int> usrc_begin(ub.size(), 0);
     for (size_t ui = 0; ui < ub.size(); ++ui) {
       usrc_begin[ui] = (int)gsrcs.size();
@@ -360,12 +366,19 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
             const Block& gr = GR->blocks[GR->find(b, r, rp)];
             const WsBlock& w = ub[ui];
             GemmSeg sg{};
-            // A operand = sum_j coef_j * source_j, rows ts.mo.. of every source block (fused stage W)
-            sg.a_base = B_X;  // unused when nsrc > 0
-            sg.a_off = (int64_t)ts.mo * w.ld;
             sg.lda = w.ld;
-            sg.nsrc = (int)usrc[ui].size();
-            sg.src_begin = usrc_begin[ui];
+            if (fuse_w) {
+              // A operand = sum_j coef_j * source_j, rows ts.mo.. of every source block
+              sg.a_base = B_X;  // unused when nsrc > 0
+              sg.a_off = (int64_t)ts.mo * w.ld;
+              sg.nsrc = (int)usrc[ui].size();
+              sg.src_begin = usrc_begin[ui];
+            } else {
+              sg.a_base = B_U;
+              sg.a_off = w.off + (int64_t)ts.mo * w.ld;
+              sg.nsrc = 0;
+              sg.src_begin = 0;
+            }
             sg.b_base = B_GR;
             sg.b_off = gr.off + ts.no;
             sg.ldb = gr.ld;
@@ -413,7 +426,9 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
       per = std::max(512, std::min(8192, per / 512 * 512));
       for (int e = 0; e < nelem; e += per) mixC.push_back(MixChunk{ti, e, std::min(per, nelem - e), 0});
     };
-    const int nmixCU = 0;  // stage W for the U blocks is fused into stage R (no separate launch)
+    if (!fuse_w)
+      for (size_t ui = 0; ui < ub.size(); ++ui) add_target(B_U, ub[ui].off, ub[ui].rows * ub[ui].ld, usrc[ui]);
+    const int nmixCU = (int)mixC.size();
     for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
       const Block& yb = like->blocks[yi];
       add_target(B_Y, yb.off, yb.rows * yb.ld, ysrc[yi]);
@@ -422,7 +437,8 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     // ---- upload ------------------------------------------------------------------------------
     cudaSetDevice(ctx->device);
     if (cudaMalloc(&p->T, p->t_elems * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&p->Pp, p->p_elems * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&p->Pp, p->p_elems * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&p->U, (fuse_w ? 16 : p->u_elems) * sizeof(double)) != cudaSuccess) {
       htn_plan_destroy(p);
       return ctx->fail(HTN_ERR_OOM, "plan_heff_ac: workspace allocation failed");
     }
@@ -434,6 +450,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
           case B_GR: b = GR->d; break;
           case B_T: b = p->T; break;
           case B_P: b = p->Pp; break;
+          case B_U: b = p->U; break;
           case B_X: base = REF_X; return;
           case B_Y: base = REF_Y; return;
         }
@@ -478,7 +495,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     p->stats[4] = (double)ub.size();
     p->stats[5] = (double)mixT.size();
     p->stats[6] = (double)(mixS.size() + gsrcs.size());
-    p->stats[7] = (double)(p->t_elems + p->p_elems) * sizeof(double);
+    p->stats[7] = (double)(p->t_elems + p->p_elems + (fuse_w ? 0 : p->u_elems)) * sizeof(double);
     p->stats[8] = (double)itemsL.size();
     p->stats[9] = (double)itemsR.size();
     p->stats[10] = padded;
