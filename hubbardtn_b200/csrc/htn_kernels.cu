@@ -41,8 +41,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // grouped GEMM
 // ------------------------------------------------------------------------------------
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
-constexpr int NCONS_WARPS = 4, NPROD_WARPS = 4;
+constexpr int STAGES = 3;
+constexpr int NCONS_WARPS = 4, NPROD_WARPS = 1;
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NTHREADS = (NCONS_WARPS + NPROD_WARPS) * 32;
 constexpr int LDAS = BK + 4;  // 20 doubles: (g*20 + t) mod 16 distinct over a half warp
@@ -122,49 +122,123 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[8][2][2], const double* 
   }
 }
 
-template <bool LAYB>
-__device__ __forceinline__ void mma_dispatch(int flex, double (&acc)[8][2][2], const double* as, const double* bs,
-                                             int nk4) {
-  switch (flex) {
-    case 1: mma_chunk<1, LAYB>(acc, as, bs, nk4); break;
-    case 2: mma_chunk<2, LAYB>(acc, as, bs, nk4); break;
-    case 3: mma_chunk<3, LAYB>(acc, as, bs, nk4); break;
-    case 4: mma_chunk<4, LAYB>(acc, as, bs, nk4); break;
-    case 5: mma_chunk<5, LAYB>(acc, as, bs, nk4); break;
-    case 6: mma_chunk<6, LAYB>(acc, as, bs, nk4); break;
-    case 7: mma_chunk<7, LAYB>(acc, as, bs, nk4); break;
-    default: mma_chunk<8, LAYB>(acc, as, bs, nk4); break;
+struct Ring {
+  double* As;
+  double* Bs;
+  uint64_t* full;
+  uint64_t* empty;
+  int* meta;
+  int stage;
+  unsigned phase;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// Consumer side of one work item, fully specialised on the tile shape: waits for the staged
+// chunks, issues the DMMAs, releases the stages, then stores the accumulators.
+template <int FLEX, bool LAYB>
+__device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int role, int lane, const Bases& bases) {
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = item.mt, nt = item.nt;
+  const bool active = role * 16 < (LAYB ? mt : nt);  // warp-uniform: this strip holds data
+  const int a_role = (LAYB ? role * 16 * LDAS : 0) + g * LDAS + t;
+  const int b_role = (LAYB ? 0 : role * 16) + t * LDBS + g;
+
+  double acc[8][2][2];
+#pragma unroll
+  for (int i = 0; i < FLEX; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+
+  const int nchunks = item.nchunks;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    mbar_wait(&rg.full[rg.stage], rg.phase);
+    if (active) {
+      const int nk4 = rg.meta[rg.stage];
+      mma_chunk<FLEX, LAYB>(acc, rg.As + rg.stage * A_STAGE + a_role, rg.Bs + rg.stage * B_STAGE + b_role, nk4);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rg.empty[rg.stage]);
+    rg.advance();
+  }
+
+  if (active) {
+    double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
+    const int ldc = item.ldc;
+    const bool beta = item.beta != 0;
+#pragma unroll
+    for (int x = 0; x < FLEX; ++x) {
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const int ra = LAYB ? (role * 2 + f) : x;  // row atom
+        const int ca = LAYB ? x : (role * 2 + f);  // col atom
+        const int row = ra * 8 + g, col = ca * 8 + 2 * t;
+        if (row < mt && col < nt) {
+          double* p = C + (long long)row * ldc + col;
+          if (col + 1 < nt) {
+            double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
+            if (beta) {
+              double2 o = *reinterpret_cast<double2*>(p);
+              v.x += o.x;
+              v.y += o.y;
+            }
+            *reinterpret_cast<double2*>(p) = v;
+          } else {
+            double v = acc[x][f][0];
+            if (beta) v += *p;
+            *p = v;
+          }
+        }
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <bool LAYB>
+__device__ __forceinline__ void consume_dispatch(int flex, const GemmItem& item, Ring& rg, int role, int lane,
+                                                 const Bases& bases) {
+  switch (flex) {
+    case 1: consume_item<1, LAYB>(item, rg, role, lane, bases); break;
+    case 2: consume_item<2, LAYB>(item, rg, role, lane, bases); break;
+    case 3: consume_item<3, LAYB>(item, rg, role, lane, bases); break;
+    case 4: consume_item<4, LAYB>(item, rg, role, lane, bases); break;
+    case 5: consume_item<5, LAYB>(item, rg, role, lane, bases); break;
+    case 6: consume_item<6, LAYB>(item, rg, role, lane, bases); break;
+    case 7: consume_item<7, LAYB>(item, rg, role, lane, bases); break;
+    default: consume_item<8, LAYB>(item, rg, role, lane, bases); break;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3)
 grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs,
                     const MixSrc* __restrict__ srcs, int nitems, Bases bases) {
   extern __shared__ __align__(16) double smem[];
-  double* As = smem;
-  double* Bs = smem + STAGES * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + STAGES * B_STAGE);
-  uint64_t* empty = full + STAGES;
-  int* meta = reinterpret_cast<int*>(empty + STAGES);  // nk4 of the chunk held by each stage
+  Ring rg;
+  rg.As = smem;
+  rg.Bs = smem + STAGES * A_STAGE;
+  rg.full = reinterpret_cast<uint64_t*>(rg.Bs + STAGES * B_STAGE);
+  rg.empty = rg.full + STAGES;
+  rg.meta = reinterpret_cast<int*>(rg.empty + STAGES);  // nk4 of the chunk held by each stage
+  rg.stage = 0;
+  rg.phase = 0;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 2 * NPROD);   // per producer thread: one plain arrive + one cp.async arrive
-      mbar_init(&empty[s], NCONS_WARPS);  // one elected lane per consumer warp
+      mbar_init(&rg.full[s], 2 * NPROD);     // per producer thread: one plain arrive + one cp.async arrive
+      mbar_init(&rg.empty[s], NCONS_WARPS);  // one elected lane per consumer warp
     }
   }
   __syncthreads();
   if (blockIdx.x >= nitems) return;
 
-  int stage = 0;
-  unsigned phase = 0;
-
   if (warp >= NCONS_WARPS) {
-    // =========================== PRODUCER ===========================================
-    const int ptid = tid - NCONS_WARPS * 32;
+    // =========================== PRODUCER (one warp) ================================
     int it = blockIdx.x;
     GemmItem item = items[it];
     while (true) {
@@ -180,91 +254,72 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
         const double* Bg = resolve(sg.b_off, sg.b_base, bases);
         const double* Ag = sg.nsrc ? nullptr : resolve(sg.a_off, sg.a_base, bases);
         for (int k0 = 0; k0 < K; k0 += BK) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          double* as = As + stage * A_STAGE;
-          double* bs = Bs + stage * B_STAGE;
-          // ---- B operand: 16 x 64 chunk, 16-byte cp.async with zero fill ------------------
+          mbar_wait(&rg.empty[rg.stage], rg.phase ^ 1u);
+          double* as = rg.As + rg.stage * A_STAGE;
+          double* bs = rg.Bs + rg.stage * B_STAGE;
+          // ---- B operand: 16 x 64 chunk: lane = 16-byte segment of a row, q = row ---------
+          {
+            int bytes_row = (nt - lane * 2) * 8;
+            bytes_row = bytes_row < 0 ? 0 : (bytes_row > 16 ? 16 : bytes_row);
+            const double* src0 = Bg + (long long)k0 * sg.ldb + lane * 2;
 #pragma unroll
-          for (int q = 0; q < (BK * BN / 2) / NPROD; ++q) {  // 4
-            int sid = ptid + q * NPROD;
-            int row = sid >> 5, sgm = sid & 31;
-            int k = k0 + row;
-            int bytes = (k < K) ? (nt - sgm * 2) * 8 : 0;
-            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-            const double* src = bytes ? (Bg + (long long)k * sg.ldb + sgm * 2) : Bg;
-            cp_async16(bs + row * LDBS + sgm * 2, src, bytes);
+            for (int q = 0; q < BK; ++q) {
+              const int bytes = (k0 + q < K) ? bytes_row : 0;
+              cp_async16(bs + q * LDBS + lane * 2, bytes ? src0 + (long long)q * sg.ldb : Bg, bytes);
+            }
           }
+          const int arow = lane >> 3, aseg = lane & 7;  // A: 4 rows x 8 segments per pass
           if (sg.nsrc == 0) {
             // ---- A operand straight from one array ----------------------------------------
+            int bytes_k = (K - (k0 + aseg * 2)) * 8;
+            bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
+            const double* src0 = Ag + (long long)arow * sg.lda + k0 + aseg * 2;
 #pragma unroll
-            for (int q = 0; q < (BM * BK / 2) / NPROD; ++q) {  // 4
-              int sid = ptid + q * NPROD;
-              int row = sid >> 3, sgm = sid & 7;
-              int k = k0 + sgm * 2;
-              int bytes = (row < mt) ? (K - k) * 8 : 0;
-              bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-              const double* src = bytes ? (Ag + (long long)row * sg.lda + k) : Ag;
-              cp_async16(as + row * LDAS + sgm * 2, src, bytes);
+            for (int q = 0; q < BM / 4; ++q) {
+              const int row = q * 4 + arow;
+              const int bytes = (row < mt) ? bytes_k : 0;
+              cp_async16(as + row * LDAS + aseg * 2, bytes ? src0 + (long long)q * 4 * sg.lda : Ag, bytes);
             }
           } else {
-            // ---- A operand = sum_j coef_j * source_j (fused stage W) ------------------------
-            double2 acc2[4];
-            long long off[4];
-            bool ok[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int sid = ptid + q * NPROD;
-              int row = sid >> 3, k = k0 + (sid & 7) * 2;
-              ok[q] = row < mt && k < K;  // (k+1 may be the zero pad column when K is odd)
-              off[q] = sg.a_off + (long long)row * sg.lda + k;
-              acc2[q] = make_double2(0.0, 0.0);
-            }
+            // ---- A operand = sum_j coef_j * source_j (fused stage W, HTN_FUSE_W=1) -----------
+            const int k = k0 + aseg * 2;
             const MixSrc* sp = srcs + sg.src_begin;
-            int j = 0;
-            for (; j + 2 <= sg.nsrc; j += 2) {
-              const MixSrc s0 = sp[j], s1 = sp[j + 1];
-              const double* p0 = resolve(s0.off, s0.base, bases);
-              const double* p1 = resolve(s1.off, s1.base, bases);
-              double2 v0[4], v1[4];
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {  // two passes of 8 row groups keep the register count down
+              double2 acc2[8];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v0[q] = ok[q] ? __ldg(reinterpret_cast<const double2*>(p0 + off[q])) : make_double2(0.0, 0.0);
-                v1[q] = ok[q] ? __ldg(reinterpret_cast<const double2*>(p1 + off[q])) : make_double2(0.0, 0.0);
+              for (int q = 0; q < 8; ++q) acc2[q] = make_double2(0.0, 0.0);
+#pragma unroll 1
+              for (int j = 0; j < sg.nsrc; ++j) {
+                const MixSrc s0 = sp[j];
+                const double* p0 = resolve(s0.off, s0.base, bases) + sg.a_off + k;
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int row = (h * 8 + q) * 4 + arow;
+                  v[q] = (row < mt && k < K) ? __ldg(reinterpret_cast<const double2*>(p0 + (long long)row * sg.lda))
+                                             : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  acc2[q].x = fma(s0.coef, v[q].x, acc2[q].x);
+                  acc2[q].y = fma(s0.coef, v[q].y, acc2[q].y);
+                }
               }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                acc2[q].x = fma(s0.coef, v0[q].x, acc2[q].x);
-                acc2[q].y = fma(s0.coef, v0[q].y, acc2[q].y);
-                acc2[q].x = fma(s1.coef, v1[q].x, acc2[q].x);
-                acc2[q].y = fma(s1.coef, v1[q].y, acc2[q].y);
+              for (int q = 0; q < 8; ++q) {
+                const int row = (h * 8 + q) * 4 + arow;
+                *reinterpret_cast<double2*>(as + row * LDAS + aseg * 2) = acc2[q];
               }
-            }
-            if (j < sg.nsrc) {
-              const MixSrc s0 = sp[j];
-              const double* p0 = resolve(s0.off, s0.base, bases);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                double2 v = ok[q] ? __ldg(reinterpret_cast<const double2*>(p0 + off[q])) : make_double2(0.0, 0.0);
-                acc2[q].x = fma(s0.coef, v.x, acc2[q].x);
-                acc2[q].y = fma(s0.coef, v.y, acc2[q].y);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int sid = ptid + q * NPROD;
-              *reinterpret_cast<double2*>(as + (sid >> 3) * LDAS + (sid & 7) * 2) = acc2[q];
             }
           }
-          if (ptid == 0) {
+          if (lane == 0) {
             int krem = K - k0;
-            meta[stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
+            rg.meta[rg.stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
           }
-          cp_async_mbar_arrive(&full[stage]);
-          mbar_arrive(&full[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          cp_async_mbar_arrive(&rg.full[rg.stage]);
+          mbar_arrive(&rg.full[rg.stage]);
+          rg.advance();
         }
         sg = sg_next;
       }
@@ -273,80 +328,20 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
       item = next_item;
     }
   } else {
-    // =========================== CONSUMER ===========================================
-    const int g = lane >> 2, t = lane & 3;
+    // =========================== CONSUMERS (four warps) =============================
     int it = blockIdx.x;
     GemmItem item = items[it];
     while (true) {
       const int itn = it + gridDim.x;
       GemmItem next_item = item;
       if (itn < nitems) next_item = items[itn];
-      const int mt = item.mt, nt = item.nt;
-      const bool layb = item.layout != 0;
       // rotate the strip a warp owns from item to item so that partially filled strips do not
-      // always land on the same SM sub-partition (warp id % 4)
+      // always land on the same SM sub-partition
       const int role = (warp + it) & 3;
-      const int flex = ((layb ? nt : mt) + 7) >> 3;
-      const bool active = role * 16 < (layb ? mt : nt);  // warp-uniform: this strip holds data
-      const int a_role = layb ? role * 16 * LDAS : 0;
-      const int b_role = layb ? 0 : role * 16;
-
-      double acc[8][2][2];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-
-      const int nchunks = item.nchunks;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&full[stage], phase);
-        if (active) {
-          const int nk4 = meta[stage];
-          const double* as = As + stage * A_STAGE + g * LDAS + t + a_role;
-          const double* bs = Bs + stage * B_STAGE + t * LDBS + g + b_role;
-          if (layb)
-            mma_dispatch<true>(flex, acc, as, bs, nk4);
-          else
-            mma_dispatch<false>(flex, acc, as, bs, nk4);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-
-      // ---- epilogue -------------------------------------------------------------------
-      if (active) {
-        double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
-        const int ldc = item.ldc;
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          if (x < flex) {
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-              const int ra = layb ? (role * 2 + f) : x;  // row atom
-              const int ca = layb ? x : (role * 2 + f);  // col atom
-              const int row = ra * 8 + g, col = ca * 8 + 2 * t;
-              if (row < mt && col < nt) {
-                double* p = C + (long long)row * ldc + col;
-                if (col + 1 < nt) {
-                  double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
-                  if (item.beta) {
-                    double2 o = *reinterpret_cast<double2*>(p);
-                    v.x += o.x;
-                    v.y += o.y;
-                  }
-                  *reinterpret_cast<double2*>(p) = v;
-                } else {
-                  double v = acc[x][f][0];
-                  if (item.beta) v += *p;
-                  *p = v;
-                }
-              }
-            }
-          }
-        }
-      }
+      if (item.layout != 0)
+        consume_dispatch<true>((item.nt + 7) >> 3, item, rg, role, lane, bases);
+      else
+        consume_dispatch<false>((item.mt + 7) >> 3, item, rg, role, lane, bases);
       if (itn >= nitems) break;
       it = itn;
       item = next_item;
@@ -561,8 +556,49 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(double* out) {
   if (s == 123.456) out[0] = s;
 }
 
+// DMMA issue-rate probe with few resident warps: `nacc` independent accumulators per warp
+template <int NACC>
+__global__ void __launch_bounds__(1024) probe_dmma_warps_kernel(double* out, int iters) {
+  double c[NACC][2];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
 double probe_fp64(int which, int sm_count, cudaStream_t st) {
   constexpr int ITER = 4096;
+  if (which >= 10) {
+    // which = 10 + warps_per_sm (4, 8, 16, 32): one CTA per SM, 14 independent DMMAs per warp
+    const int warps = which - 10;
+    double* d = nullptr;
+    cudaMalloc(&d, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0, st);
+      probe_dmma_warps_kernel<14><<<sm_count, warps * 32, 0, st>>>(d, ITER);
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      double tf = (double)sm_count * warps * ITER * 14.0 * 512.0 / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+  }
   double* d = nullptr;
   cudaMalloc(&d, 8);
   cudaEvent_t e0, e1;
