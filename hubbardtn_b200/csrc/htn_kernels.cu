@@ -258,27 +258,47 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           double* as = rg.As + rg.stage * A_STAGE;
           double* bs = rg.Bs + rg.stage * B_STAGE;
           // ---- B operand: 16 x 64 chunk: lane = 16-byte segment of a row, q = row ---------
+          // (columns >= nt feed only discarded outputs: loaded only up to the tile extent)
           {
             int bytes_row = (nt - lane * 2) * 8;
             bytes_row = bytes_row < 0 ? 0 : (bytes_row > 16 ? 16 : bytes_row);
-            const double* src0 = Bg + (long long)k0 * sg.ldb + lane * 2;
+            const char* src = reinterpret_cast<const char*>(Bg + (long long)k0 * sg.ldb + lane * 2);
+            const long long step = (long long)sg.ldb * 8;
+            double* dst = bs + lane * 2;
+            if (k0 + BK <= K) {
+              if (bytes_row == 16) {
 #pragma unroll
-            for (int q = 0; q < BK; ++q) {
-              const int bytes = (k0 + q < K) ? bytes_row : 0;
-              cp_async16(bs + q * LDBS + lane * 2, bytes ? src0 + (long long)q * sg.ldb : Bg, bytes);
+                for (int q = 0; q < BK; ++q) cp_async16(dst + q * LDBS, src + q * step, 16);
+              } else if (bytes_row > 0) {
+#pragma unroll
+                for (int q = 0; q < BK; ++q) cp_async16(dst + q * LDBS, src + q * step, bytes_row);
+              }
+            } else {  // K tail: rows >= K must be zero (they meet the zero-filled A columns)
+#pragma unroll
+              for (int q = 0; q < BK; ++q) {
+                const int bytes = (k0 + q < K) ? bytes_row : 0;
+                cp_async16(dst + q * LDBS, bytes ? src + q * step : reinterpret_cast<const char*>(Bg), bytes);
+              }
             }
           }
           const int arow = lane >> 3, aseg = lane & 7;  // A: 4 rows x 8 segments per pass
           if (sg.nsrc == 0) {
-            // ---- A operand straight from one array ----------------------------------------
+            // ---- A operand straight from one array; rows >= mt feed only discarded outputs ----
             int bytes_k = (K - (k0 + aseg * 2)) * 8;
             bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
-            const double* src0 = Ag + (long long)arow * sg.lda + k0 + aseg * 2;
+            const char* src = reinterpret_cast<const char*>(Ag + (long long)arow * sg.lda + k0 + aseg * 2);
+            const long long step = (long long)sg.lda * 32;  // 4 rows
+            double* dst = as + arow * LDAS + aseg * 2;
+            const int nq = (mt - arow + 3) >> 2;  // rows q*4+arow < mt
+            if (nq == BM / 4) {
 #pragma unroll
-            for (int q = 0; q < BM / 4; ++q) {
-              const int row = q * 4 + arow;
-              const int bytes = (row < mt) ? bytes_k : 0;
-              cp_async16(as + row * LDAS + aseg * 2, bytes ? src0 + (long long)q * 4 * sg.lda : Ag, bytes);
+              for (int q = 0; q < BM / 4; ++q)
+                cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
+            } else {
+#pragma unroll
+              for (int q = 0; q < BM / 4; ++q)
+                if (q < nq)
+                  cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
             }
           } else {
             // ---- A operand = sum_j coef_j * source_j (fused stage W, HTN_FUSE_W=1) -----------

@@ -110,14 +110,20 @@ class HeffCase:
     """Device-resident synthetic H_AC problem: spaces, GL, W, GR, x, y and the plan."""
 
     def __init__(self, ctx, sym: int = S.SU2U1, D: int = 1024, chi: int = 96, nnz_per_row: int = 4,
-                 seed: int = SEED, site: int = 0):
+                 seed: int = SEED, site: int = 0, spaces=None):
+        """`spaces` = (vl_mult, vr_mult, phys, levels) overrides the SURVEY 8(d) recipe (used by
+        tools/ and tests to build special shapes, e.g. one dense sector)."""
         from . import device as dev
         self.ctx, self.sym, self.D, self.chi, self.site = ctx, sym, D, chi, site
-        self.phys = S.physical_space(sym, 1, 1)
-        # site parity picks the (left,right) bond types: A|B on even sites, B|A on odd ones
-        self.vl_mult = bond_space(sym, D, site & 1)
-        self.vr_mult = bond_space(sym, D, 1 - (site & 1))
-        self.levels = mpo_levels(sym, chi)
+        if spaces is not None:
+            self.vl_mult, self.vr_mult, self.phys, self.levels = spaces
+            chi = self.chi = len(self.levels)
+        else:
+            self.phys = S.physical_space(sym, 1, 1)
+            # site parity picks the (left,right) bond types: A|B on even sites, B|A on odd ones
+            self.vl_mult = bond_space(sym, D, site & 1)
+            self.vr_mult = bond_space(sym, D, 1 - (site & 1))
+            self.levels = mpo_levels(sym, chi)
         self.w_entries = mpo_entries(sym, self.levels, self.phys, nnz_per_row, seed + site)
         self.Vl = dev.Space(ctx, sym, self.vl_mult)
         self.Vr = dev.Space(ctx, sym, self.vr_mult)
