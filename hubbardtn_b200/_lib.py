@@ -24,7 +24,7 @@ SYM_SU2U1 = 0
 SYM_U1U1 = 1
 SIDE_LEFT = 0
 SIDE_RIGHT = 1
-T_MPS, T_BOND, T_ENVL, T_ENVR = 0, 1, 2, 3
+T_MPS, T_BOND, T_ENVL, T_ENVR, T_MPST = 0, 1, 2, 3, 4
 
 
 class HtnError(RuntimeError):
@@ -69,6 +69,8 @@ SIGNATURES = {
     "htn_tensor_create_bond": (_i32, [_p, _p, _pp]),
     "htn_tensor_create_env": (_i32, [_p, _i32, _p, _p, _i32, _pp]),
     "htn_tensor_create_like": (_i32, [_p, _pp]),
+    "htn_tensor_create_transposed": (_i32, [_p, _pp]),
+    "htn_tensor_transpose": (_i32, [_p, _p, _i32]),
     "htn_tensor_destroy": (_i32, [_p]),
     "htn_tensor_blocktable": (_i32, [_p, _pi32, _pi64, _pi32, _pi32, _pi32, _pi64]),
     "htn_tensor_upload": (_i32, [_p, _p, _i64]),
@@ -76,7 +78,19 @@ SIGNATURES = {
     "htn_mpo_create": (_i32, [_p, _p, _p, _p, _i32, _pi32, _pi32, _pd, _pp]),
     "htn_mpo_destroy": (_i32, [_p]),
     "htn_plan_heff_ac": (_i32, [_p, _p, _p, _p, _p, _pp]),
+    "htn_plan_heff_c": (_i32, [_p, _p, _p, _p, _pp]),
     "htn_plan_destroy": (_i32, [_p]),
+    "htn_plan_transfer": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _pp]),
+    "htn_transfer_apply": (_i32, [_p, _p, _p, _p, _p]),
+    "htn_eigsolve": (_i32, [_p, _p, _p, _i32, C.c_double, _i32, _pd, _pd, _pi32]),
+    "htn_qrpos": (_i32, [_p, _p, _p]),
+    "htn_lqpos": (_i32, [_p, _p, _p]),
+    "htn_regauge": (_i32, [_p, _p, _p]),
+    "htn_gauge_right": (_i32, [_p, _i32, _pp, _p, _pp, _pp, C.c_double, _i32, _pi32, _pd]),
+    "htn_environments": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, _pp, C.c_double, _i32, _i32, _pd, _pd]),
+    "htn_vumps": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, _pp, _pp, C.c_double, _i32, _i32, _pd, _pd, _pi32,
+                         _pd, _i32]),
+    "htn_expval_diag": (_i32, [_p, _pd, _i32, _pd]),
     "htn_heff_apply": (_i32, [_p, _p, _p]),
     "htn_heff_apply_host": (_i32, [_p, _p, _p, _i64]),
     "htn_plan_stats": (_i32, [_p, _pd, _i32]),

@@ -4,7 +4,7 @@
 #include <new>
 #include <numeric>
 
-#include "htn_internal.hpp"
+#include "htn_linalg.hpp"
 
 using namespace htn;
 
@@ -71,6 +71,10 @@ int32_t htn_ctx_create(int32_t device, htn_ctx** out) {
     return HTN_ERR_NO_DEVICE;
   }
   cudaMallocHost(&c->red_host, 64 * sizeof(double));
+  cudaMalloc(&c->kry_scal, 512 * sizeof(double));
+  cudaMallocHost(&c->kry_scal_host, 512 * sizeof(double));
+  cudaMalloc(&c->d_status, sizeof(int));
+  cudaMemset(c->d_status, 0, sizeof(int));
   *out = c;
   return HTN_OK;
 }
@@ -82,6 +86,11 @@ int32_t htn_ctx_destroy(htn_ctx* ctx) {
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->red) cudaFree(ctx->red);
   if (ctx->red_host) cudaFreeHost(ctx->red_host);
+  if (ctx->kry_V) cudaFree(ctx->kry_V);
+  if (ctx->kry_scal) cudaFree(ctx->kry_scal);
+  if (ctx->kry_scal_host) cudaFreeHost(ctx->kry_scal_host);
+  if (ctx->kry_partial) cudaFree(ctx->kry_partial);
+  if (ctx->d_status) cudaFree(ctx->d_status);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HTN_OK;
@@ -165,16 +174,24 @@ int32_t htn_legs_destroy(htn_legs* l) {
 // ---- tensors --------------------------------------------------------------------------
 static int32_t finalize_tensor(htn_tensor* t) {
   htn_ctx* ctx = t->ctx;
+  // Blocks of one coupled sector (MPS: same r; transposed MPS: same l) are laid out back to back
+  // so that they form ONE row-major panel -- the matrix TensorKit stores per coupled sector and
+  // the unit the QR / LQ gauge kernels work on in place.  Panels start 128-byte aligned.
   int64_t off = 0, hoff = 0;
+  int prev_group = -1;
   for (size_t i = 0; i < t->blocks.size(); ++i) {
     Block& b = t->blocks[i];
     b.ld = even_up(b.cols);
+    const int group = t->kind == HTN_T_MPS ? b.lab[2] : (t->kind == HTN_T_MPST ? b.lab[0] : -2 - (int)i);
+    if (group != prev_group) off = align_up(off, 16);
+    prev_group = group;
     b.off = off;
     b.hoff = hoff;
-    off = align_up(off + (int64_t)b.rows * b.ld, 16);
+    off += (int64_t)b.rows * b.ld;
     hoff += (int64_t)b.rows * b.cols;
     t->index[std::make_tuple(b.lab[0], b.lab[1], b.lab[2])] = (int)i;
   }
+  off = align_up(off, 16);
   t->dsize = std::max<int64_t>(off, 16);
   t->hsize = hoff;
   CU(ctx, cudaSetDevice(ctx->device));
@@ -205,8 +222,10 @@ static int32_t finalize_tensor(htn_tensor* t) {
 }
 
 static htn_tensor* new_tensor(htn_ctx* ctx, int kind, int sym) {
+  static uint64_t next_uid = 0;
   htn_tensor* t = new htn_tensor();
   t->ctx = ctx;
+  t->uid = ++next_uid;
   t->kind = kind;
   t->sym = sym;
   t->s0.ctx = t->s1.ctx = ctx;
@@ -220,7 +239,7 @@ int32_t htn_tensor_create_mps(htn_ctx* ctx, const htn_space* Vl, const htn_legs*
                               htn_tensor** out) {
   if (!ctx || !Vl || !P || !Vr || !out) return HTN_ERR_INVALID;
   if (Vl->sym != P->sym || Vr->sym != P->sym) return ctx->fail(HTN_ERR_INVALID, "symmetry kinds differ");
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   HTN_TRY
   htn_tensor* t = new_tensor(ctx, HTN_T_MPS, P->sym);
   t->s0 = *Vl;
@@ -252,7 +271,7 @@ int32_t htn_tensor_create_mps(htn_ctx* ctx, const htn_space* Vl, const htn_legs*
 
 int32_t htn_tensor_create_bond(htn_ctx* ctx, const htn_space* V, htn_tensor** out) {
   if (!ctx || !V || !out) return HTN_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   HTN_TRY
   htn_tensor* t = new_tensor(ctx, HTN_T_BOND, V->sym);
   t->s0 = *V;
@@ -284,7 +303,7 @@ int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, co
     Sector s = M->sec[identity_level];
     if (s.p != 0 || s.q != 0 || s.n != 0) return ctx->fail(HTN_ERR_INVALID, "identity level must carry the trivial sector");
   }
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   HTN_TRY
   htn_tensor* t = new_tensor(ctx, side == HTN_SIDE_LEFT ? HTN_T_ENVL : HTN_T_ENVR, V->sym);
   t->s0 = *V;
@@ -322,7 +341,7 @@ int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, co
 int32_t htn_tensor_create_like(const htn_tensor* src, htn_tensor** out) {
   if (!src || !out) return HTN_ERR_INVALID;
   htn_ctx* ctx = src->ctx;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   HTN_TRY
   htn_tensor* t = new_tensor(ctx, src->kind, src->sym);
   t->s0 = src->s0;
@@ -340,6 +359,43 @@ int32_t htn_tensor_create_like(const htn_tensor* src, htn_tensor** out) {
   HTN_CATCH(ctx)
 }
 
+// blockwise transposed companion of an MPS tensor: blocks (l,s,r) stored as [n_r x n_l], ordered and
+// laid out by LEFT sector (one row-major panel per l) -- the operand layout of the transfer GEMMs
+// and the panel layout of the LQ gauge step
+int32_t htn_tensor_create_transposed(const htn_tensor* src, htn_tensor** out) {
+  if (!src || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = src->ctx;
+  if (src->kind != HTN_T_MPS) return ctx->fail(HTN_ERR_INVALID, "create_transposed: source must be an MPS tensor");
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, HTN_T_MPST, src->sym);
+  t->s0 = src->s0;
+  t->s1 = src->s1;
+  t->legs = src->legs;
+  const int nl = (int)src->s0.sec.size(), ns = (int)src->legs.sec.size(), nr = (int)src->s1.sec.size();
+  for (int l = 0; l < nl; ++l)
+    for (int s = 0; s < ns; ++s)
+      for (int r = 0; r < nr; ++r)
+        if (allowed(t->sym, src->s0.sec[l], src->legs.sec[s], src->s1.sec[r])) {
+          Block b{};
+          b.lab[0] = l;
+          b.lab[1] = s;
+          b.lab[2] = r;
+          b.rows = src->s1.mult[r];
+          b.cols = src->s0.mult[l];
+          b.weight = sdim(t->sym, src->s1.sec[r]);
+          t->blocks.push_back(b);
+        }
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
 int32_t htn_tensor_destroy(htn_tensor* t) {
   if (!t) return HTN_OK;
   cudaSetDevice(t->ctx->device);
@@ -347,6 +403,7 @@ int32_t htn_tensor_destroy(htn_tensor* t) {
   if (t->d) cudaFree(t->d);
   if (t->dblocks) cudaFree(t->dblocks);
   if (t->dchunks) cudaFree(t->dchunks);
+  for (auto& kv : t->devtables) cudaFree(kv.second.first);
   delete t;
   return HTN_OK;
 }
@@ -413,7 +470,7 @@ int32_t htn_download_locked(const htn_tensor* t, double* host, int64_t nelem) {
 
 int32_t htn_tensor_upload(htn_tensor* t, const double* host, int64_t nelem) {
   if (!t || (!host && nelem > 0)) return HTN_ERR_INVALID;
-  std::lock_guard<std::mutex> g(t->ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(t->ctx->mu);
   int32_t rc = htn_upload_locked(t, host, nelem);
   if (rc) return rc;
   // the host buffer belongs to the caller: do not return before the copy has read it
@@ -423,7 +480,7 @@ int32_t htn_tensor_upload(htn_tensor* t, const double* host, int64_t nelem) {
 
 int32_t htn_tensor_download(const htn_tensor* t, double* host, int64_t nelem) {
   if (!t || (!host && nelem > 0)) return HTN_ERR_INVALID;
-  std::lock_guard<std::mutex> g(t->ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(t->ctx->mu);
   return htn_download_locked(t, host, nelem);
 }
 
@@ -481,7 +538,7 @@ bool htn_same_structure(const htn_tensor* x, const htn_tensor* y) { return same_
 int32_t htn_tensor_dot(const htn_tensor* x, const htn_tensor* y, double* out) {
   if (!x || !y || !out) return HTN_ERR_INVALID;
   htn_ctx* ctx = x->ctx;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!same_structure(x, y)) return ctx->fail(HTN_ERR_SHAPE, "dot: tensors differ in structure");
   CU(ctx, cudaSetDevice(ctx->device));
   if (x->nchunks == 0) {
@@ -504,12 +561,21 @@ int32_t htn_tensor_dot(const htn_tensor* x, const htn_tensor* y, double* out) {
 int32_t htn_tensor_axpby(double alpha, const htn_tensor* x, double beta, htn_tensor* y) {
   if (!x || !y) return HTN_ERR_INVALID;
   htn_ctx* ctx = x->ctx;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!same_structure(x, y)) return ctx->fail(HTN_ERR_SHAPE, "axpby: tensors differ in structure");
   CU(ctx, cudaSetDevice(ctx->device));
   launch_axpby(alpha, x->d, beta, y->d, x->dsize, ctx->stream);
   CU(ctx, cudaGetLastError());
   return HTN_OK;
+}
+
+int32_t htn_tensor_transpose(const htn_tensor* src, htn_tensor* dst, int32_t weighted) {
+  if (!src || !dst) return HTN_ERR_INVALID;
+  htn_ctx* ctx = src->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int mode = !weighted ? 0 : (src->kind == HTN_T_MPS ? 1 : 2);
+  return htn::t_transpose(src, dst, mode);
 }
 
 // ---- test hooks -----------------------------------------------------------------------
@@ -522,7 +588,7 @@ int32_t htn_network_coefficient(int32_t sym, const int32_t* L, double* out) {
 
 int32_t htn_probe_fp64_peak(htn_ctx* ctx, int32_t which, double* tflops) {
   if (!ctx || !tflops) return HTN_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   *tflops = probe_fp64(which, ctx->sm_count, ctx->stream);
   CU(ctx, cudaGetLastError());

@@ -53,13 +53,21 @@ struct DevBlock {
 struct htn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  std::mutex mu;
+  std::recursive_mutex mu;  // public entry points may nest (drivers call the primitives)
   std::string err;
   double* stage = nullptr;  // device staging buffer for packed host <-> padded device copies
   int64_t stage_cap = 0;
   double* red = nullptr;  // reduction scratch
   int64_t red_cap = 0;
   double* red_host = nullptr;  // pinned
+  // Krylov workspace: basis vectors, device scalars (+ pinned mirror), multidot partials
+  double* kry_V = nullptr;
+  int64_t kry_cap = 0;
+  double* kry_scal = nullptr;       // 512 doubles on the device
+  double* kry_scal_host = nullptr;  // pinned mirror
+  double* kry_partial = nullptr;
+  int64_t kry_partial_cap = 0;
+  int* d_status = nullptr;  // device-side failure flags (QR rank deficiency, ...)
   int sm_count = 148;
   int32_t fail(int32_t code, const std::string& msg) {
     err = msg;
@@ -82,6 +90,7 @@ struct htn_legs {
 
 struct htn_tensor {
   htn_ctx* ctx;
+  uint64_t uid = 0;  // unique per created tensor (keys of cached device tables)
   int kind;
   int sym;
   htn_space s0, s1;  // MPS: Vl, Vr; BOND: V,V; ENV: V,V
@@ -96,6 +105,8 @@ struct htn_tensor {
   // row-chunk table for pack/unpack/dot kernels: (block, row0, nrows)
   int* dchunks = nullptr;
   int nchunks = 0;
+  // cached device tables (transpose tiles, level fills, QR panels) keyed by (partner, mode)
+  std::map<std::pair<const void*, int>, std::pair<void*, int>> devtables;
   int find(int a, int b, int c) const {
     auto it = index.find(std::make_tuple(a, b, c));
     return it == index.end() ? -1 : it->second;
@@ -118,30 +129,24 @@ struct htn_mpo {
 // ---- device work tables (shared between planner and kernels) ---------------------------
 namespace htn {
 
-enum Base { B_GL = 0, B_GR = 1, B_X = 2, B_Y = 3, B_T = 4, B_U = 5, B_P = 6, B_COUNT = 7 };
-
-// References in the device tables are resolved by a post-pass of the planner: arrays that
-// live as long as the plan (GL, GR, T, U) become absolute pointers (REF_ABS); the apply's
-// input / output vectors stay relative (REF_X / REF_Y) and are passed per launch.
-enum Ref { REF_ABS = 0, REF_X = 1, REF_Y = 2 };
+// A contraction program addresses memory through "references": base 0 = absolute device
+// pointer (program workspace, resolved when the program is finalised), base k>0 = offset into
+// the k-th tensor bound at launch time (slot k-1).  The same program therefore serves any set
+// of tensors with the planned block structure (x/y of a Krylov iteration, AL or AR, ...).
+constexpr int MAX_SLOTS = 6;
 struct Bases {
-  const double* x;
-  double* y;
+  const double* p[MAX_SLOTS];
 };
 __host__ __device__ inline const double* resolve(long long v, int base, const Bases& b) {
-  return base == REF_ABS ? reinterpret_cast<const double*>(v) : (base == REF_X ? b.x + v : b.y + v);
+  return base == 0 ? reinterpret_cast<const double*>(v) : b.p[base - 1] + v;
 }
 
-// one K-segment of a grouped GEMM work item:  C_tile += coef * A_seg[mt x K] * B_seg[K x nt]
-// If nsrc > 0 the A operand is not read from one array but assembled on the fly as
-// sum_j srcs[src_begin + j].coef * (source block j) -- the stage-W recoupling mix fused into the
-// operand load of stage R (all sources share the shape and leading dimension lda).
+// one K-segment of a grouped GEMM work item:  C_tile += A_seg[mt x K] * B_seg[K x nt]
 struct GemmSeg {
-  long long a_off, b_off;  // element offsets from the bases (or absolute pointers, see Ref)
+  long long a_off, b_off;
   int a_base, b_base;
   int lda, ldb;
   int K;
-  int nsrc, src_begin;
   int pad_;
 };
 
@@ -173,9 +178,9 @@ struct MixChunk {
   int target, elem0, nelem, pad_;
 };
 
-void launch_gemm(const GemmItem* items, const GemmSeg* segs, const MixSrc* srcs, int nitems, Bases bases,
-                 int grid, cudaStream_t st);
-void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, Bases bases,
+void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const Bases& bases, int grid,
+                 cudaStream_t st);
+void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, const Bases& bases,
                 cudaStream_t st);
 void launch_pack(const DevBlock* blocks, const int* chunks, int nchunks, const double* packed, double* padded,
                  cudaStream_t st);
@@ -184,37 +189,37 @@ void launch_unpack(const DevBlock* blocks, const int* chunks, int nchunks, const
 void launch_dot(const DevBlock* blocks, const int* chunks, int nchunks, const double* x, const double* y,
                 double* partial, double* out, cudaStream_t st);
 void launch_axpby(double alpha, const double* x, double beta, double* y, long long n, cudaStream_t st);
+// out[j] = <V_j, w> (weighted) for j < nvec, V_j = V + j * stride; deterministic two-pass
+void launch_multidot(const DevBlock* blocks, const int* chunks, int nchunks, const double* V, long long stride,
+                     int nvec, const double* w, double* partial, double* out, cudaStream_t st);
+// w += sum_j sign * h[j] V_j   (h on the device)
+void launch_multiaxpy(const double* V, long long stride, int nvec, const double* h, double sign, double* w,
+                      long long n, cudaStream_t st);
+// y = x * (*scal) or x / (*scal) with the scalar on the device
+void launch_scale_dev(const double* x, const double* scal, int invert, double* y, long long n, cudaStream_t st);
+// blockwise transposes: dst block = scale[b] * (src block)^T ; tables give (src off, dst off, rows, cols, lds, ldd)
+struct TrBlock {
+  long long soff, doff;
+  int rows, cols, lds, ldd;
+  double scale;
+};
+void launch_transpose(const TrBlock* blocks, int nblocks, const double* src, double* dst, cudaStream_t st);
+// set blocks to 0 (mode 0) or to the unit matrix (mode 1): table entries (off, rows, cols, ld)
+struct FillBlock {
+  long long off;
+  int rows, cols, ld, mode;
+};
+void launch_fill(const FillBlock* blocks, int nblocks, double* dst, cudaStream_t st);
+// in-place QR with positive diagonal (iterated classical Gram-Schmidt) of row-major [m x n] panels:
+// panel p: Q overwrites A (off_a, m, n, lda); R (n x n upper, row-major ldr) written at off_r
+struct QrPanel {
+  long long off_a, off_r;
+  int m, n, lda, ldr;
+};
+void launch_qr(const QrPanel* panels, int npanels, double* A, double* R, int* status, cudaStream_t st);
 int gemm_max_ctas_per_sm();
 double probe_fp64(int which, int sm_count, cudaStream_t st);
 
 constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = 16;
 
 }  // namespace htn
-
-struct htn_plan {
-  htn_ctx* ctx;
-  const htn_tensor* GL;
-  const htn_tensor* GR;
-  htn_tensor* like;  // private structural copy (no data use)
-  double* T = nullptr;
-  htn::MixSrc* gsrcs = nullptr;  // fused stage-W sources of the stage-R A operand (HTN_FUSE_W=1)
-  double* U = nullptr;
-  double* Pp = nullptr;  // split-K partial outputs of stage R: nsplit_max copies of the y layout
-  int64_t t_elems = 0, u_elems = 0, p_elems = 0;  // u_elems: size U would have (never materialised)
-  // device tables
-  htn::GemmItem* itemsL = nullptr;
-  htn::GemmSeg* segsL = nullptr;
-  int nitemsL = 0, nsegsL = 0;
-  htn::GemmItem* itemsR = nullptr;
-  htn::GemmSeg* segsR = nullptr;
-  int nitemsR = 0, nsegsR = 0;
-  htn::MixTarget* mixT = nullptr;
-  htn::MixSrc* mixS = nullptr;
-  htn::MixChunk* mixC = nullptr;   // chunks [0, nmixCU) -> U targets, [nmixCU, nmixC) -> y targets
-  int nmixT = 0, nmixS = 0, nmixC = 0, nmixCU = 0;
-  int gridL = 0, gridR = 0;
-  double stats[12] = {0};
-  // host staging tensors for htn_heff_apply_host
-  htn_tensor* hx = nullptr;
-  htn_tensor* hy = nullptr;
-};

@@ -13,6 +13,7 @@
 //    with the TensorKit inner product (weights = quantum dimension of the coupled sector).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "htn_internal.hpp"
@@ -213,8 +214,8 @@ __device__ __forceinline__ void consume_dispatch(int flex, const GemmItem& item,
 }
 
 __global__ void __launch_bounds__(NTHREADS, 3)
-grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs,
-                    const MixSrc* __restrict__ srcs, int nitems, Bases bases) {
+grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
+                    const __grid_constant__ Bases bases) {
   extern __shared__ __align__(16) double smem[];
   Ring rg;
   rg.As = smem;
@@ -246,13 +247,14 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
       GemmItem next_item = item;
       if (itn < nitems) next_item = items[itn];  // prefetch: consumed at the next iteration
       const int mt = item.mt, nt = item.nt;
-      GemmSeg sg = segs[item.seg_begin];
+      GemmSeg sg{};
+      if (item.seg_begin < item.seg_end) sg = segs[item.seg_begin];
       for (int si = item.seg_begin; si < item.seg_end; ++si) {
         GemmSeg sg_next = sg;
         if (si + 1 < item.seg_end) sg_next = segs[si + 1];
         const int K = sg.K;
         const double* Bg = resolve(sg.b_off, sg.b_base, bases);
-        const double* Ag = sg.nsrc ? nullptr : resolve(sg.a_off, sg.a_base, bases);
+        const double* Ag = resolve(sg.a_off, sg.a_base, bases);
         for (int k0 = 0; k0 < K; k0 += BK) {
           mbar_wait(&rg.empty[rg.stage], rg.phase ^ 1u);
           double* as = rg.As + rg.stage * A_STAGE;
@@ -282,56 +284,24 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
             }
           }
           const int arow = lane >> 3, aseg = lane & 7;  // A: 4 rows x 8 segments per pass
-          if (sg.nsrc == 0) {
-            // ---- A operand straight from one array; rows >= mt feed only discarded outputs ----
-            int bytes_k = (K - (k0 + aseg * 2)) * 8;
-            bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
-            const char* src = reinterpret_cast<const char*>(Ag + (long long)arow * sg.lda + k0 + aseg * 2);
-            const long long step = (long long)sg.lda * 32;  // 4 rows
-            double* dst = as + arow * LDAS + aseg * 2;
-            const int nq = (mt - arow + 3) >> 2;  // rows q*4+arow < mt
-            if (nq == BM / 4) {
+          {
+          // ---- A operand straight from one array; rows >= mt feed only discarded outputs ----
+          int bytes_k = (K - (k0 + aseg * 2)) * 8;
+          bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
+          const char* src = reinterpret_cast<const char*>(Ag + (long long)arow * sg.lda + k0 + aseg * 2);
+          const long long step = (long long)sg.lda * 32;  // 4 rows
+          double* dst = as + arow * LDAS + aseg * 2;
+          const int nq = (mt - arow + 3) >> 2;  // rows q*4+arow < mt
+          if (nq == BM / 4) {
 #pragma unroll
-              for (int q = 0; q < BM / 4; ++q)
-                cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
-            } else {
-#pragma unroll
-              for (int q = 0; q < BM / 4; ++q)
-                if (q < nq)
-                  cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
-            }
+            for (int q = 0; q < BM / 4; ++q)
+              cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
           } else {
-            // ---- A operand = sum_j coef_j * source_j (fused stage W, HTN_FUSE_W=1) -----------
-            const int k = k0 + aseg * 2;
-            const MixSrc* sp = srcs + sg.src_begin;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {  // two passes of 8 row groups keep the register count down
-              double2 acc2[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) acc2[q] = make_double2(0.0, 0.0);
-#pragma unroll 1
-              for (int j = 0; j < sg.nsrc; ++j) {
-                const MixSrc s0 = sp[j];
-                const double* p0 = resolve(s0.off, s0.base, bases) + sg.a_off + k;
-                double2 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const int row = (h * 8 + q) * 4 + arow;
-                  v[q] = (row < mt && k < K) ? __ldg(reinterpret_cast<const double2*>(p0 + (long long)row * sg.lda))
-                                             : make_double2(0.0, 0.0);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  acc2[q].x = fma(s0.coef, v[q].x, acc2[q].x);
-                  acc2[q].y = fma(s0.coef, v[q].y, acc2[q].y);
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int row = (h * 8 + q) * 4 + arow;
-                *reinterpret_cast<double2*>(as + row * LDAS + aseg * 2) = acc2[q];
-              }
-            }
+            for (int q = 0; q < BM / 4; ++q)
+              if (q < nq)
+                cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
+          }
           }
           if (lane == 0) {
             int krem = K - k0;
@@ -379,15 +349,15 @@ int gemm_max_ctas_per_sm() {
   return cached;
 }
 
-void launch_gemm(const GemmItem* items, const GemmSeg* segs, const MixSrc* srcs, int nitems, Bases bases,
-                 int grid, cudaStream_t st) {
+void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const Bases& bases, int grid,
+                 cudaStream_t st) {
   if (nitems <= 0) return;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
     attr = true;
   }
-  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, srcs, nitems, bases);
+  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases);
 }
 
 // ------------------------------------------------------------------------------------
@@ -398,7 +368,8 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, const MixSrc* srcs,
 constexpr int MIX_MAX_SRC_SMEM = 128;
 
 __global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ tg, const MixSrc* __restrict__ src,
-                                                  const MixChunk* __restrict__ chunks, Bases bases) {
+                                                  const MixChunk* __restrict__ chunks,
+                                                  const __grid_constant__ Bases bases) {
   __shared__ const double* sptr[MIX_MAX_SRC_SMEM];
   __shared__ double scoef[MIX_MAX_SRC_SMEM];
   const MixChunk ch = chunks[blockIdx.x];
@@ -444,7 +415,7 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ 
   }
 }
 
-void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, Bases bases,
+void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, const Bases& bases,
                 cudaStream_t st) {
   if (nchunks <= 0) return;
   mix_kernel<<<nchunks, 256, 0, st>>>(tg, src, chunks, bases);
@@ -539,6 +510,212 @@ void launch_axpby(double alpha, const double* x, double beta, double* y, long lo
   int grid = (int)((n + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   axpby_kernel<<<grid, 256, 0, st>>>(alpha, x, beta, y, n);
+}
+
+// ------------------------------------------------------------------------------------
+// Krylov vector kernels (KrylovKit orthogonalisation): all inner products of
+// one vector against the whole basis in ONE pass over the vector (classical Gram-Schmidt step),
+// the matching rank-k update, and scaling by a device-resident scalar -- no host round trip
+// between them.  Deterministic: per-chunk partials, then an ordered tree sum.
+// ------------------------------------------------------------------------------------
+constexpr int MD_MAXVEC = 64;
+
+__global__ void __launch_bounds__(256)
+multidot_partial_kernel(const DevBlock* __restrict__ blocks, const int* __restrict__ chunks,
+                        const double* __restrict__ V, long long stride, int nvec, const double* __restrict__ w,
+                        double* __restrict__ partial) {
+  const int b = chunks[3 * blockIdx.x], r0 = chunks[3 * blockIdx.x + 1], nr = chunks[3 * blockIdx.x + 2];
+  const DevBlock B = blocks[b];
+  const long long base = B.off + (long long)r0 * B.ld;
+  const int n = nr * B.ld;  // pads are zero in every vector
+  __shared__ double sh[MD_MAXVEC][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = 0; j < nvec; ++j) {
+    const double* vj = V + (long long)j * stride + base;
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) acc = fma(vj[e], w[base + e], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) sh[j][warp] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < nvec) {
+    double s = 0.0;
+    for (int wv = 0; wv < 8; ++wv) s += sh[threadIdx.x][wv];
+    partial[(long long)blockIdx.x * nvec + threadIdx.x] = s * B.weight;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+multidot_final_kernel(const double* __restrict__ partial, int nchunks, int nvec, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int j = blockIdx.x;
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < nchunks; c += blockDim.x) acc += partial[(long long)c * nvec + j];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[j] = sh[0];
+}
+
+void launch_multidot(const DevBlock* blocks, const int* chunks, int nchunks, const double* V, long long stride,
+                     int nvec, const double* w, double* partial, double* out, cudaStream_t st) {
+  if (nvec <= 0) return;
+  if (nchunks <= 0) {
+    cudaMemsetAsync(out, 0, nvec * sizeof(double), st);
+    return;
+  }
+  multidot_partial_kernel<<<nchunks, 256, 0, st>>>(blocks, chunks, V, stride, nvec, w, partial);
+  multidot_final_kernel<<<nvec, 256, 0, st>>>(partial, nchunks, nvec, out);
+}
+
+__global__ void __launch_bounds__(256)
+multiaxpy_kernel(const double* __restrict__ V, long long stride, int nvec, const double* __restrict__ h, double sign,
+                 double* __restrict__ w, long long n) {
+  __shared__ double hs[MD_MAXVEC];
+  if (threadIdx.x < nvec) hs[threadIdx.x] = sign * h[threadIdx.x];
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gs = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += gs) {
+    double acc = w[i];
+    for (int j = 0; j < nvec; ++j) acc = fma(hs[j], V[(long long)j * stride + i], acc);
+    w[i] = acc;
+  }
+}
+
+void launch_multiaxpy(const double* V, long long stride, int nvec, const double* h, double sign, double* w,
+                      long long n, cudaStream_t st) {
+  if (n <= 0 || nvec <= 0) return;
+  int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  multiaxpy_kernel<<<grid, 256, 0, st>>>(V, stride, nvec, h, sign, w, n);
+}
+
+// mode 0: y = x * s ; 1: y = x / s ; 2: y = x / sqrt(s)
+__global__ void scale_dev_kernel(const double* __restrict__ x, const double* __restrict__ scal, int mode,
+                                 double* __restrict__ y, long long n) {
+  double s = *scal;
+  if (mode == 1) s = 1.0 / s;
+  if (mode == 2) s = 1.0 / sqrt(s);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gs = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += gs) y[i] = x[i] * s;
+}
+
+void launch_scale_dev(const double* x, const double* scal, int mode, double* y, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  scale_dev_kernel<<<grid, 256, 0, st>>>(x, scal, mode, y, n);
+}
+
+// ------------------------------------------------------------------------------------
+// blockwise transpose with a per-block scale (tiles of <= 32 x 32 listed by the host)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const TrBlock* __restrict__ tiles, const double* __restrict__ src,
+                                                        double* __restrict__ dst) {
+  __shared__ double t[32][33];
+  const TrBlock T = tiles[blockIdx.x];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < T.rows; r += 8)
+    if (tx < T.cols) t[r][tx] = src[T.soff + (long long)r * T.lds + tx];
+  __syncthreads();
+  for (int c = ty; c < T.cols; c += 8)
+    if (tx < T.rows) dst[T.doff + (long long)c * T.ldd + tx] = T.scale * t[tx][c];
+}
+
+void launch_transpose(const TrBlock* tiles, int ntiles, const double* src, double* dst, cudaStream_t st) {
+  if (ntiles > 0) transpose_kernel<<<ntiles, 256, 0, st>>>(tiles, src, dst);
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const FillBlock* __restrict__ blocks, double* __restrict__ dst) {
+  const FillBlock B = blocks[blockIdx.x];
+  const int n = B.rows * B.ld;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int r = e / B.ld, c = e % B.ld;
+    dst[B.off + e] = (B.mode == 1 && r == c && c < B.cols) ? 1.0 : 0.0;
+  }
+}
+
+void launch_fill(const FillBlock* blocks, int nblocks, double* dst, cudaStream_t st) {
+  if (nblocks > 0) fill_kernel<<<nblocks, 256, 0, st>>>(blocks, dst);
+}
+
+// ------------------------------------------------------------------------------------
+// Positive QR of tall row-major panels, one CTA per panel (replaces LAPACK geqrf/orgqr behind
+// TensorKit `leftorth!(.., QRpos())`).  Column-by-column classical
+// Gram-Schmidt with one re-orthogonalisation pass (CGS2): orthogonality at machine precision for
+// numerically full-rank panels, and diag(R) > 0 by construction.  Q overwrites A.
+// Thread layout: 32 x 16; tx runs over already-orthogonalised columns (coalesced along a row).
+// ------------------------------------------------------------------------------------
+constexpr int QR_TY = 16;
+
+__global__ void __launch_bounds__(32 * QR_TY) qr_cgs2_kernel(const QrPanel* __restrict__ panels, double* __restrict__ Abase,
+                                                             double* __restrict__ Rbase, int* __restrict__ status) {
+  const QrPanel P = panels[blockIdx.x];
+  double* A = Abase + P.off_a;
+  double* R = Rbase + P.off_r;
+  const int m = P.m, n = P.n, lda = P.lda, ldr = P.ldr;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ double red[QR_TY][33];
+  __shared__ double hs[512];  // projection coefficients of the current column (n <= 512)
+  __shared__ double snorm;
+  for (int e = threadIdx.x; e < n * ldr; e += blockDim.x) R[e] = 0.0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    for (int pass = 0; pass < 2; ++pass) {
+      // h[c] = sum_i Q[i][c] * v[i],  c < j
+      for (int c0 = 0; c0 < j; c0 += 32) {
+        const int c = c0 + tx;
+        double acc = 0.0;
+        if (c < j)
+          for (int i = ty; i < m; i += QR_TY) acc = fma(A[(long long)i * lda + c], A[(long long)i * lda + j], acc);
+        red[ty][tx] = acc;
+        __syncthreads();
+        if (ty == 0 && c < j) {
+          double s = 0.0;
+#pragma unroll
+          for (int q = 0; q < QR_TY; ++q) s += red[q][tx];
+          hs[c] = s;
+        }
+        __syncthreads();
+      }
+      // v[i] -= sum_c Q[i][c] h[c]   (one warp per row)
+      for (int i = ty; i < m; i += QR_TY) {
+        double acc = 0.0;
+        for (int c = tx; c < j; c += 32) acc = fma(A[(long long)i * lda + c], hs[c], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (tx == 0) A[(long long)i * lda + j] -= acc;
+      }
+      for (int c = threadIdx.x; c < j; c += blockDim.x) R[(long long)c * ldr + j] += hs[c];
+      __syncthreads();
+    }
+    // norm of the remainder
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const double v = A[(long long)i * lda + j];
+      acc = fma(v, v, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (tx == 0) red[ty][0] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int q = 0; q < QR_TY; ++q) s += red[q][0];
+      snorm = sqrt(s);
+      R[(long long)j * ldr + j] = snorm;
+      if (!(snorm > 0.0)) atomicOr(status, 1);
+    }
+    __syncthreads();
+    const double inv = snorm > 0.0 ? 1.0 / snorm : 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) A[(long long)i * lda + j] *= inv;
+    __syncthreads();
+  }
+}
+
+void launch_qr(const QrPanel* panels, int npanels, double* A, double* R, int* status, cudaStream_t st) {
+  if (npanels > 0) qr_cgs2_kernel<<<npanels, 32 * QR_TY, 0, st>>>(panels, A, R, status);
 }
 
 // ------------------------------------------------------------------------------------

@@ -1,0 +1,446 @@
+// Tensor-level linear algebra of the gauge and Krylov steps: blockwise transposes, level fills,
+// positive QR / LQ per coupled sector, Lanczos and GMRES over device-resident vectors.
+//
+// Replaces: TensorKit `leftorth!(.., QRpos())` / `rightorth!(.., LQpos())`
+// (LAPACK geqrf under MKL_jll 2025.0.1, Manifest.toml:716) and KrylovKit 0.9.5 `eigsolve`
+// (Lanczos) / `linsolve` (GMRES) (Manifest.toml:548).  The Krylov recurrences are driven from the
+// host, but every vector stays in HBM: per iteration one fused "all inner products" kernel pair, one
+// rank-k update, and a single readback of <= 130 scalars.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "htn_linalg.hpp"
+
+using namespace htn;
+
+extern "C" bool htn_same_structure(const htn_tensor* x, const htn_tensor* y);
+
+namespace htn {
+
+static int32_t cuda_rc(htn_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return HTN_OK;
+}
+
+template <class T>
+static int32_t cached_table(htn_tensor* owner, const void* partner, int mode, const std::vector<T>& host, T** dev,
+                            int* n) {
+  htn_ctx* ctx = owner->ctx;
+  auto key = std::make_pair(partner, mode);
+  auto it = owner->devtables.find(key);
+  if (it != owner->devtables.end()) {
+    *dev = static_cast<T*>(it->second.first);
+    *n = it->second.second;
+    return HTN_OK;
+  }
+  T* d = nullptr;
+  if (!host.empty()) {
+    if (cudaMalloc(&d, host.size() * sizeof(T)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "device table allocation failed");
+    cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  owner->devtables[key] = {d, (int)host.size()};
+  *dev = d;
+  *n = (int)host.size();
+  return HTN_OK;
+}
+
+int32_t t_copy(const htn_tensor* src, htn_tensor* dst) {
+  htn_ctx* ctx = src->ctx;
+  if (src->dsize != dst->dsize) return ctx->fail(HTN_ERR_SHAPE, "copy: tensors differ in structure");
+  if (src->d == dst->d) return HTN_OK;
+  cudaMemcpyAsync(dst->d, src->d, src->dsize * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+  return cuda_rc(ctx, "copy");
+}
+
+// mode 0: plain; 1: scale sqrt(d_r/d_l); 2: scale 1/sqrt(d_r/d_l)   (MPS <-> MPST only)
+int32_t t_transpose(const htn_tensor* src, htn_tensor* dst, int mode) {
+  htn_ctx* ctx = src->ctx;
+  const bool ok = (src->kind == HTN_T_MPS && dst->kind == HTN_T_MPST) || (src->kind == HTN_T_MPST && dst->kind == HTN_T_MPS) ||
+                  (src->kind == HTN_T_BOND && dst->kind == HTN_T_BOND);
+  if (!ok || src->blocks.size() != dst->blocks.size() || src->d == dst->d)
+    return ctx->fail(HTN_ERR_INVALID, "transpose: incompatible tensors");
+  htn_tensor* owner = const_cast<htn_tensor*>(src);
+  TrBlock* dt = nullptr;
+  int nt = 0;
+  const void* pk = reinterpret_cast<const void*>(static_cast<uintptr_t>(dst->uid));
+  auto key = std::make_pair(pk, mode);
+  if (owner->devtables.find(key) == owner->devtables.end()) {
+    std::vector<TrBlock> tiles;
+    for (const Block& sb : src->blocks) {
+      const int di = dst->find(sb.lab[0], sb.lab[1], sb.lab[2]);
+      if (di < 0) return ctx->fail(HTN_ERR_SHAPE, "transpose: block structures differ");
+      const Block& db = dst->blocks[di];
+      if (db.rows != sb.cols || db.cols != sb.rows) return ctx->fail(HTN_ERR_SHAPE, "transpose: block shapes differ");
+      double scale = 1.0;
+      if (mode != 0 && src->kind != HTN_T_BOND) {
+        const double w = std::sqrt((double)sdim(src->sym, src->s1.sec[sb.lab[2]]) / sdim(src->sym, src->s0.sec[sb.lab[0]]));
+        scale = mode == 1 ? w : 1.0 / w;
+      }
+      for (int r0 = 0; r0 < sb.rows; r0 += 32)
+        for (int c0 = 0; c0 < sb.cols; c0 += 32)
+          tiles.push_back(TrBlock{sb.off + (int64_t)r0 * sb.ld + c0, db.off + (int64_t)c0 * db.ld + r0,
+                                  std::min(32, sb.rows - r0), std::min(32, sb.cols - c0), sb.ld, db.ld, scale});
+    }
+    int32_t rc = cached_table(owner, pk, mode, tiles, &dt, &nt);
+    if (rc) return rc;
+  } else {
+    dt = static_cast<TrBlock*>(owner->devtables[key].first);
+    nt = owner->devtables[key].second;
+  }
+  launch_transpose(dt, nt, src->d, dst->d, ctx->stream);
+  return cuda_rc(ctx, "transpose");
+}
+
+// set all blocks of one MPO level of an environment to zero (mode 0) or the unit matrix (mode 1)
+int32_t t_fill_level(htn_tensor* env, int level, int mode) {
+  htn_ctx* ctx = env->ctx;
+  FillBlock* d = nullptr;
+  int n = 0;
+  auto key = std::make_pair((const void*)nullptr, 1000 + 2 * level + mode);
+  if (env->devtables.find(key) == env->devtables.end()) {
+    std::vector<FillBlock> fb;
+    for (const Block& b : env->blocks) {
+      const bool hit = env->kind == HTN_T_BOND ? level == 0 : b.lab[0] == level;
+      if (!hit) continue;
+      if (mode == 1 && b.lab[1] != b.lab[2]) return ctx->fail(HTN_ERR_INVALID, "fill_level: identity on an off-diagonal block");
+      fb.push_back(FillBlock{b.off, b.rows, b.cols, b.ld, mode});
+    }
+    int32_t rc = cached_table(env, nullptr, 1000 + 2 * level + mode, fb, &d, &n);
+    if (rc) return rc;
+  } else {
+    d = static_cast<FillBlock*>(env->devtables[key].first);
+    n = env->devtables[key].second;
+  }
+  launch_fill(d, n, env->d, ctx->stream);
+  return cuda_rc(ctx, "fill_level");
+}
+
+// A = Q R in place (Q overwrites A), one panel per coupled sector; R is a BOND tensor on the
+// column space.  MPS: panels = right sectors; MPST: panels = left sectors; BOND: every block.
+int32_t t_qr_inplace(htn_tensor* A, htn_tensor* R) {
+  htn_ctx* ctx = A->ctx;
+  if (R->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "qr: R must be a bond tensor");
+  const htn_space& Vc = A->kind == HTN_T_MPS ? A->s1 : A->s0;
+  if (R->s0.sec != Vc.sec || R->s0.mult != Vc.mult) return ctx->fail(HTN_ERR_SHAPE, "qr: R space does not match the column space of A");
+  QrPanel* d = nullptr;
+  int n = 0;
+  const void* pk = reinterpret_cast<const void*>(static_cast<uintptr_t>(R->uid));
+  auto key = std::make_pair(pk, 2000);
+  if (A->devtables.find(key) == A->devtables.end()) {
+    std::vector<QrPanel> panels;
+    const int gidx = A->kind == HTN_T_MPS ? 2 : 0;
+    size_t i = 0;
+    while (i < A->blocks.size()) {
+      const Block& b0 = A->blocks[i];
+      size_t j = i;
+      int m = 0;
+      if (A->kind == HTN_T_BOND) {
+        m = b0.rows;
+        j = i + 1;
+      } else {
+        while (j < A->blocks.size() && A->blocks[j].lab[gidx] == b0.lab[gidx]) {
+          m += A->blocks[j].rows;
+          ++j;
+        }
+      }
+      const int g = A->kind == HTN_T_BOND ? b0.lab[0] : b0.lab[gidx];
+      const Block& rb = R->blocks[g];
+      if (b0.cols > 512) return ctx->fail(HTN_ERR_SHAPE, "qr: sector multiplicity above 512 is not supported by the panel kernel");
+      if (m < b0.cols) return ctx->fail(HTN_ERR_SHAPE, "qr: a coupled-sector panel has fewer rows than columns (spaces not full rank)");
+      panels.push_back(QrPanel{b0.off, rb.off, m, b0.cols, b0.ld, rb.ld});
+      i = j;
+    }
+    int32_t rc = cached_table(A, pk, 2000, panels, &d, &n);
+    if (rc) return rc;
+  } else {
+    d = static_cast<QrPanel*>(A->devtables[key].first);
+    n = A->devtables[key].second;
+  }
+  cudaMemsetAsync(R->d, 0, R->dsize * sizeof(double), ctx->stream);
+  launch_qr(d, n, A->d, R->d, ctx->d_status, ctx->stream);
+  return cuda_rc(ctx, "qr");
+}
+
+int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunks) {
+  const int64_t need = nvec * stride;
+  if (ctx->kry_cap < need) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->kry_V) cudaFree(ctx->kry_V);
+    ctx->kry_V = nullptr;
+    ctx->kry_cap = 0;
+    if (cudaMalloc(&ctx->kry_V, need * sizeof(double)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "Krylov basis allocation failed");
+    ctx->kry_cap = need;
+  }
+  const int64_t pneed = (nchunks + 1) * MD_MAXVEC_HOST;
+  if (ctx->kry_partial_cap < pneed) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->kry_partial) cudaFree(ctx->kry_partial);
+    ctx->kry_partial = nullptr;
+    ctx->kry_partial_cap = 0;
+    if (cudaMalloc(&ctx->kry_partial, pneed * sizeof(double)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "Krylov scratch allocation failed");
+    ctx->kry_partial_cap = pneed;
+  }
+  return HTN_OK;
+}
+
+// device scalar slots inside ctx->kry_scal
+enum { S_H = 0, S_H2 = 64, S_BETA = 128, S_NRM = 129, S_Y = 192, S_TMP = 300 };
+
+int32_t t_dot_dev(const htn_tensor* like, const double* x, const double* y, double* out_dev) {
+  htn_ctx* ctx = like->ctx;
+  int32_t rc = ensure_krylov(ctx, 0, 0, like->nchunks);
+  if (rc) return rc;
+  if (like->nchunks == 0) {
+    cudaMemsetAsync(out_dev, 0, sizeof(double), ctx->stream);
+    return HTN_OK;
+  }
+  launch_multidot(like->dblocks, like->dchunks, like->nchunks, x, 0, 1, y, ctx->kry_partial, out_dev, ctx->stream);
+  return cuda_rc(ctx, "dot");
+}
+
+int32_t t_dot_host(const htn_tensor* like, const double* x, const double* y, double* out) {
+  htn_ctx* ctx = like->ctx;
+  int32_t rc = t_dot_dev(like, x, y, ctx->kry_scal + S_TMP);
+  if (rc) return rc;
+  cudaMemcpyAsync(ctx->kry_scal_host + S_TMP, ctx->kry_scal + S_TMP, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return cuda_rc(ctx, "dot readback");
+  *out = ctx->kry_scal_host[S_TMP];
+  return HTN_OK;
+}
+
+// x <- x / ||x||   (norm stays on the device)
+int32_t t_normalize(const htn_tensor* like, double* x) {
+  htn_ctx* ctx = like->ctx;
+  int32_t rc = t_dot_dev(like, x, x, ctx->kry_scal + S_NRM);
+  if (rc) return rc;
+  launch_scale_dev(x, ctx->kry_scal + S_NRM, 2, x, like->dsize, ctx->stream);
+  return cuda_rc(ctx, "normalize");
+}
+
+// ---- small dense symmetric eigenproblem (cyclic Jacobi) on the host ----------------------
+static void jacobi_eigh(int n, std::vector<double>& A, std::vector<double>& V, std::vector<double>& w) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) off += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[(size_t)p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
+        const double tau = (aqq - app) / (2.0 * apq);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * akp - s * akq;
+          A[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)p * n + k] = c * apk - s * aqk;
+          A[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+          V[(size_t)k * n + p] = c * vkp - s * vkq;
+          V[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; ++i) w[i] = A[(size_t)i * n + i];
+}
+
+// Lowest eigenpair of the symmetric operator `apply` (Lanczos, full CGS2 re-orthogonalisation,
+// explicit restart from the Ritz vector -- same recurrence as oracle/krylov.py:lanczos_lowest).
+// x0: start vector; x_out: eigenvector (unit norm, <x0, x_out> >= 0).  x0 may alias x_out.
+int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const double* x0, double* x_out, int krylovdim,
+                       double tol, int maxiter, KrylovInfo* info) {
+  htn_ctx* ctx = like->ctx;
+  krylovdim = std::max(2, std::min(krylovdim, 60));
+  const int64_t n = like->dsize;
+  int32_t rc = ensure_krylov(ctx, krylovdim + 2, n, like->nchunks);
+  if (rc) return rc;
+  double* V = ctx->kry_V;
+  double* xsave = V + (int64_t)(krylovdim + 1) * n;  // copy of x0 for the final sign convention
+  double* sc = ctx->kry_scal;
+  double* sh = ctx->kry_scal_host;
+  cudaStream_t st = ctx->stream;
+  cudaMemcpyAsync(xsave, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(V, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if ((rc = t_normalize(like, V))) return rc;
+  int applies = 0;
+  double theta = 0.0, res = 1e300;
+  bool converged = false;
+  std::vector<double> alphas, betas, Tm, Z, ev;
+  for (int restart = 0; restart < maxiter && !converged; ++restart) {
+    alphas.clear();
+    betas.clear();
+    int m = 0;
+    std::vector<double> y;
+    for (int j = 0; j < krylovdim; ++j) {
+      double* w = V + (int64_t)(j + 1) * n;
+      if ((rc = apply(V + (int64_t)j * n, w))) return rc;
+      ++applies;
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
+      cudaMemcpyAsync(sh, sc, 130 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "lanczos");
+      const double a = sh[S_H + j] + sh[S_H2 + j];
+      const double b = std::sqrt(std::max(sh[S_BETA], 0.0));
+      alphas.push_back(a);
+      m = j + 1;
+      Tm.assign((size_t)m * m, 0.0);
+      for (int i = 0; i < m; ++i) {
+        Tm[(size_t)i * m + i] = alphas[i];
+        if (i + 1 < m) Tm[(size_t)i * m + i + 1] = Tm[(size_t)(i + 1) * m + i] = betas[i];
+      }
+      jacobi_eigh(m, Tm, Z, ev);
+      int lo = 0;
+      for (int i = 1; i < m; ++i)
+        if (ev[i] < ev[lo]) lo = i;
+      theta = ev[lo];
+      y.assign(m, 0.0);
+      for (int i = 0; i < m; ++i) y[i] = Z[(size_t)i * m + lo];
+      res = std::fabs(b * y[m - 1]);
+      if (res < tol || b < 1e-14 || j == krylovdim - 1) break;
+      betas.push_back(b);
+      launch_scale_dev(w, sc + S_BETA, 2, w, n, st);
+    }
+    // Ritz vector -> V[0]  (built in the spare slot, then copied)
+    for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
+    cudaMemcpyAsync(sc + S_Y, sh + S_Y, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    // slot m (the un-normalised remainder) is dead now; use it as the accumulator
+    double* acc = V + (int64_t)m * n;
+    cudaMemsetAsync(acc, 0, n * sizeof(double), st);
+    launch_multiaxpy(V, n, m, sc + S_Y, 1.0, acc, n, st);
+    if ((rc = t_normalize(like, acc))) return rc;
+    cudaMemcpyAsync(V, acc, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaStreamSynchronize(st);  // the pinned y buffer is reused next round
+    converged = res < tol;
+  }
+  // sign convention: positive overlap with the start vector
+  double ov = 0.0;
+  if ((rc = t_dot_host(like, xsave, V, &ov))) return rc;
+  launch_axpby(ov < 0 ? -1.0 : 1.0, V, 0.0, x_out, n, st);
+  if ((rc = cuda_rc(ctx, "lanczos"))) return rc;
+  if (info) {
+    info->value = theta;
+    info->residual = res;
+    info->applies = applies;
+    info->converged = converged ? 1 : 0;
+  }
+  return converged ? HTN_OK : HTN_NOT_CONVERGED;
+}
+
+// Restarted GMRES for apply(x) = b, x0 = 0 (same recurrence as oracle/krylov.py:gmres).
+int32_t gmres_solve(const htn_tensor* like, const ApplyFn& apply, const double* b, double* x, int krylovdim, double tol,
+                    int maxiter, KrylovInfo* info) {
+  htn_ctx* ctx = like->ctx;
+  krylovdim = std::max(2, std::min(krylovdim, 60));
+  const int64_t n = like->dsize;
+  int32_t rc = ensure_krylov(ctx, krylovdim + 2, n, like->nchunks);
+  if (rc) return rc;
+  double* V = ctx->kry_V;
+  double* tmp = V + (int64_t)(krylovdim + 1) * n;
+  double* sc = ctx->kry_scal;
+  double* sh = ctx->kry_scal_host;
+  cudaStream_t st = ctx->stream;
+  cudaMemsetAsync(x, 0, n * sizeof(double), st);
+  double bnorm2 = 0.0;
+  if ((rc = t_dot_host(like, b, b, &bnorm2))) return rc;
+  const double bnorm = std::sqrt(std::max(bnorm2, 0.0));
+  int applies = 0;
+  double res = 0.0;
+  bool converged = bnorm == 0.0;
+  for (int restart = 0; restart < maxiter && !converged; ++restart) {
+    // r = b - A x
+    if (restart == 0) {
+      cudaMemcpyAsync(V, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    } else {
+      if ((rc = apply(x, tmp))) return rc;
+      ++applies;
+      cudaMemcpyAsync(V, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      launch_axpby(-1.0, tmp, 1.0, V, n, st);
+    }
+    double beta2 = 0.0;
+    if ((rc = t_dot_host(like, V, V, &beta2))) return rc;
+    const double beta = std::sqrt(std::max(beta2, 0.0));
+    res = beta / bnorm;
+    if (res < tol) {
+      converged = true;
+      break;
+    }
+    launch_axpby(1.0 / beta, V, 0.0, V, n, st);
+    // Arnoldi with CGS2; least squares by Givens rotations
+    std::vector<double> H((size_t)(krylovdim + 1) * krylovdim, 0.0), cs(krylovdim), sn(krylovdim), gvec(krylovdim + 1, 0.0);
+    gvec[0] = beta;
+    int m = 0;
+    for (int j = 0; j < krylovdim; ++j) {
+      double* w = V + (int64_t)(j + 1) * n;
+      if ((rc = apply(V + (int64_t)j * n, w))) return rc;
+      ++applies;
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
+      cudaMemcpyAsync(sh, sc, 130 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "gmres");
+      const int ldh = krylovdim;
+      for (int i = 0; i <= j; ++i) H[(size_t)i * ldh + j] = sh[S_H + i] + sh[S_H2 + i];
+      const double hn = std::sqrt(std::max(sh[S_BETA], 0.0));
+      H[(size_t)(j + 1) * ldh + j] = hn;
+      // apply previous rotations to the new column
+      for (int i = 0; i < j; ++i) {
+        const double t0 = cs[i] * H[(size_t)i * ldh + j] + sn[i] * H[(size_t)(i + 1) * ldh + j];
+        H[(size_t)(i + 1) * ldh + j] = -sn[i] * H[(size_t)i * ldh + j] + cs[i] * H[(size_t)(i + 1) * ldh + j];
+        H[(size_t)i * ldh + j] = t0;
+      }
+      const double h0 = H[(size_t)j * ldh + j], h1 = H[(size_t)(j + 1) * ldh + j];
+      const double rr = std::hypot(h0, h1);
+      cs[j] = rr > 0 ? h0 / rr : 1.0;
+      sn[j] = rr > 0 ? h1 / rr : 0.0;
+      H[(size_t)j * ldh + j] = rr;
+      H[(size_t)(j + 1) * ldh + j] = 0.0;
+      gvec[j + 1] = -sn[j] * gvec[j];
+      gvec[j] = cs[j] * gvec[j];
+      m = j + 1;
+      res = std::fabs(gvec[j + 1]) / bnorm;
+      if (res < tol || hn < 1e-14) break;
+      launch_scale_dev(w, sc + S_BETA, 2, w, n, st);
+    }
+    // back substitution, x += V y
+    std::vector<double> y(m, 0.0);
+    for (int i = m - 1; i >= 0; --i) {
+      double s = gvec[i];
+      for (int k = i + 1; k < m; ++k) s -= H[(size_t)i * krylovdim + k] * y[k];
+      y[i] = s / H[(size_t)i * krylovdim + i];
+    }
+    for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
+    cudaMemcpyAsync(sc + S_Y, sh + S_Y, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    launch_multiaxpy(V, n, m, sc + S_Y, 1.0, x, n, st);
+    cudaStreamSynchronize(st);
+    if (res < tol) converged = true;
+  }
+  if ((rc = cuda_rc(ctx, "gmres"))) return rc;
+  if (info) {
+    info->value = 0.0;
+    info->residual = res;
+    info->applies = applies;
+    info->converged = converged ? 1 : 0;
+  }
+  return converged ? HTN_OK : HTN_NOT_CONVERGED;
+}
+
+}  // namespace htn

@@ -1,0 +1,733 @@
+// Uniform-MPS drivers on the device: positive QR/LQ, regauge, uniform right-orthonormalisation,
+// Jordan-MPO environments and the VUMPS ground-state search.
+//
+// Replaces the MPSKit 0.13.1 routines HubbardTN reaches through `find_groundstate(psi, H, VUMPS(..))`
+// (/root/reference/src/HubbardFunctions.jl:1012,1017,1025-1027) and `InfiniteMPS(..)` (HF:958,990):
+// `leftorth!/rightorth!`, `regauge!`, `uniform_rightorth!`, `environments`/`recalculate!`,
+// `calc_galerkin`.  Algorithm and conventions are exactly those of
+// oracle/mps.py (the CPU restatement these drivers are parity-tested against); every tensor stays
+// in HBM, the host only steers the iteration with a few scalars per step.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "htn_linalg.hpp"
+
+using namespace htn;
+
+extern "C" {
+bool htn_same_structure(const htn_tensor* x, const htn_tensor* y);
+int32_t htn_heff_run(htn_plan* p, const double* x, double* y, int mask);
+int32_t htn_plan_transfer(htn_ctx* ctx, int32_t side, const htn_mpo* W, const htn_tensor* A, const htn_tensor* At,
+                          const htn_tensor* env_in, const htn_tensor* env_out, htn_plan** out);
+}
+
+namespace htn {
+
+static int32_t cuda_rc(htn_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return HTN_OK;
+}
+
+#define RC(call)                 \
+  do {                           \
+    int32_t rc_ = (call);        \
+    if (rc_ < 0) return rc_;     \
+  } while (0)
+
+// ---- small block-product programs -------------------------------------------------------
+// out[l,s,r] = A[l,s,r] . B[r]      slots {A, B(bond on Vr), out}
+static int32_t build_mul_right(htn_ctx* ctx, const htn_tensor* A, const htn_tensor* B, Program* pg) {
+  std::vector<GemmTaskH> tasks;
+  for (const Block& b : A->blocks) {
+    const Block& c = B->blocks[b.lab[2]];
+    GemmTaskH t;
+    t.C = Opnd{2, b.off};
+    t.ldc = b.ld;
+    t.M = b.rows;
+    t.N = b.cols;
+    t.segs.push_back(GemmSegH{Opnd{0, b.off}, b.ld, Opnd{1, c.off}, c.ld, b.cols});
+    tasks.push_back(std::move(t));
+  }
+  pg->add_gemm(tasks, TAG_L);
+  return pg->finalize(ctx, 3);
+}
+
+// out[r] = sum_{l,s} At[l,s,r] . Y[l,s,r]    slots {At (MPST), Y (MPS), out (bond on Vr)}
+static int32_t build_project(htn_ctx* ctx, const htn_tensor* At, const htn_tensor* Y, const htn_tensor* B, Program* pg) {
+  std::vector<GemmTaskH> tasks(B->blocks.size());
+  std::vector<std::vector<MixSrcH>> extra(B->blocks.size());
+  for (size_t c = 0; c < B->blocks.size(); ++c) {
+    const Block& b = B->blocks[c];
+    tasks[c].C = Opnd{2, b.off};
+    tasks[c].ldc = b.ld;
+    tasks[c].M = b.rows;
+    tasks[c].N = b.cols;
+  }
+  for (const Block& y : Y->blocks) {
+    const Block& at = At->blocks[At->find(y.lab[0], y.lab[1], y.lab[2])];
+    tasks[y.lab[2]].segs.push_back(GemmSegH{Opnd{0, at.off}, at.ld, Opnd{1, y.off}, y.ld, at.cols});
+  }
+  pg->add_gemm_reduce(tasks, extra, TAG_R, TAG_Y);
+  return pg->finalize(ctx, 3);
+}
+
+// out[c] = X[c] . Y[c]    slots {X, Y, out}  (all bond tensors on one space)
+static int32_t build_bond_mul(htn_ctx* ctx, const htn_tensor* B, Program* pg) {
+  std::vector<GemmTaskH> tasks;
+  for (const Block& b : B->blocks) {
+    GemmTaskH t;
+    t.C = Opnd{2, b.off};
+    t.ldc = b.ld;
+    t.M = b.rows;
+    t.N = b.cols;
+    t.segs.push_back(GemmSegH{Opnd{0, b.off}, b.ld, Opnd{1, b.off}, b.ld, b.cols});
+    tasks.push_back(std::move(t));
+  }
+  pg->add_gemm(tasks, TAG_L);
+  return pg->finalize(ctx, 3);
+}
+
+// copy one MPO level between an environment and a bond tensor (to_env = false: bond <- env level)
+static int32_t build_level_copy(htn_ctx* ctx, const htn_tensor* env, const htn_tensor* B, int level, bool to_env, Program* pg) {
+  std::vector<MixTaskH> tasks;
+  for (size_t c = 0; c < B->blocks.size(); ++c) {
+    const int ei = env->find(level, (int)c, (int)c);
+    if (ei < 0) continue;
+    const Block& eb = env->blocks[ei];
+    const Block& bb = B->blocks[c];
+    MixTaskH t;
+    t.nelem = bb.rows * bb.ld;
+    if (to_env) {
+      t.dst = Opnd{1, eb.off};
+      t.srcs.push_back(MixSrcH{Opnd{0, bb.off}, 1.0});
+    } else {
+      t.dst = Opnd{1, bb.off};
+      t.srcs.push_back(MixSrcH{Opnd{0, eb.off}, 1.0});
+    }
+    tasks.push_back(std::move(t));
+  }
+  pg->add_mix(tasks, TAG_W);
+  return pg->finalize(ctx, 2);
+}
+
+// out[l,s,r] = values[s] * A[l,s,r]     slots {A, out}
+static int32_t build_diag_op(htn_ctx* ctx, const htn_tensor* A, const double* values, Program* pg) {
+  std::vector<MixTaskH> tasks;
+  for (const Block& b : A->blocks) {
+    MixTaskH t;
+    t.dst = Opnd{1, b.off};
+    t.nelem = b.rows * b.ld;
+    t.srcs.push_back(MixSrcH{Opnd{0, b.off}, values[b.lab[1]]});
+    tasks.push_back(std::move(t));
+  }
+  pg->add_mix(tasks, TAG_W);
+  return pg->finalize(ctx, 2);
+}
+
+struct TensorOwner {  // RAII for driver-internal tensors / plans
+  std::vector<htn_tensor*> tensors;
+  std::vector<htn_plan*> plans;
+  std::vector<Program*> programs;
+  ~TensorOwner() {
+    for (htn_plan* p : plans) htn_plan_destroy(p);
+    for (Program* p : programs) {
+      p->destroy();
+      delete p;
+    }
+    for (htn_tensor* t : tensors) htn_tensor_destroy(t);
+  }
+  htn_tensor* like(const htn_tensor* t) {
+    htn_tensor* o = nullptr;
+    if (htn_tensor_create_like(t, &o) != HTN_OK) return nullptr;
+    tensors.push_back(o);
+    return o;
+  }
+  htn_tensor* transposed(const htn_tensor* t) {
+    htn_tensor* o = nullptr;
+    if (htn_tensor_create_transposed(t, &o) != HTN_OK) return nullptr;
+    tensors.push_back(o);
+    return o;
+  }
+  htn_tensor* bond(htn_ctx* ctx, const htn_space* V) {
+    htn_tensor* o = nullptr;
+    if (htn_tensor_create_bond(ctx, V, &o) != HTN_OK) return nullptr;
+    tensors.push_back(o);
+    return o;
+  }
+  Program* program() {
+    Program* p = new Program();
+    programs.push_back(p);
+    return p;
+  }
+};
+
+static int32_t run3(Program* pg, const double* a, const double* b, double* c) {
+  const double* slots[3] = {a, b, c};
+  return pg->run(slots);
+}
+static int32_t run2(Program* pg, const double* a, double* b) {
+  const double* slots[2] = {a, b};
+  return pg->run(slots);
+}
+
+static int32_t check_qr_status(htn_ctx* ctx) {
+  int st = 0;
+  cudaMemcpyAsync(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (st) {
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream);
+    return ctx->fail(HTN_ERR_INVALID, "QR: rank-deficient coupled-sector panel");
+  }
+  return HTN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// The uniform-MPS work space: everything the gauge / environment / VUMPS drivers need per site
+// ------------------------------------------------------------------------------------------
+struct Uniform {
+  htn_ctx* ctx = nullptr;
+  int L = 0, chi = 0, depth = 0;
+  std::vector<htn_tensor*> AL, AR, C, AC, GL, GR;  // caller-owned
+  std::vector<const htn_mpo*> W;
+  TensorOwner own;
+  std::vector<htn_tensor*> ALt, ARt, tA, tA2, tAt, tB, tB2, tB3, nAC, nC, tGL, tGR, one;
+  std::vector<Program*> mulR, proj, bmul, getL, putL, getR, putR;
+  std::vector<htn_plan*> hac, hc, TL, TR, tl1, tr1;
+  std::vector<std::unique_ptr<htn_mpo>> idmpo;
+  std::vector<std::unique_ptr<htn_space>> spaces;
+
+  int prev(int i) const { return (i + L - 1) % L; }
+  int next(int i) const { return (i + 1) % L; }
+
+  int32_t init_gauge(htn_ctx* c, int n, htn_tensor* const* al, htn_tensor* const* ar, htn_tensor* const* cc,
+                     htn_tensor* const* ac) {
+    ctx = c;
+    L = n;
+    for (int i = 0; i < L; ++i) {
+      AL.push_back(al[i]);
+      AR.push_back(ar ? ar[i] : nullptr);
+      C.push_back(cc[i]);
+      AC.push_back(ac ? ac[i] : nullptr);
+    }
+    for (int i = 0; i < L; ++i) {
+      if (AL[i]->kind != HTN_T_MPS || C[i]->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "uniform MPS: wrong tensor kinds");
+      if (AL[i]->s1.sec != C[i]->s0.sec || AL[i]->s1.mult != C[i]->s0.mult || AL[i]->s0.sec != C[prev(i)]->s0.sec ||
+          AL[i]->s0.mult != C[prev(i)]->s0.mult)
+        return ctx->fail(HTN_ERR_SHAPE, "uniform MPS: bond spaces of A and C do not chain");
+      if (AR[i] && !htn_same_structure(AL[i], AR[i])) return ctx->fail(HTN_ERR_SHAPE, "uniform MPS: AL / AR structures differ");
+      if (AC[i] && !htn_same_structure(AL[i], AC[i])) return ctx->fail(HTN_ERR_SHAPE, "uniform MPS: AL / AC structures differ");
+    }
+    for (int i = 0; i < L; ++i) {
+      tA.push_back(own.like(AL[i]));
+      tA2.push_back(own.like(AL[i]));
+      tAt.push_back(own.transposed(AL[i]));
+      ALt.push_back(own.transposed(AL[i]));
+      ARt.push_back(own.transposed(AL[i]));
+      tB.push_back(own.like(C[i]));
+      tB2.push_back(own.like(C[i]));
+      tB3.push_back(own.like(C[i]));
+      one.push_back(own.like(C[i]));
+      nAC.push_back(own.like(AL[i]));
+      nC.push_back(own.like(C[i]));
+      if (!tA[i] || !tA2[i] || !tAt[i] || !ALt[i] || !ARt[i] || !tB[i] || !tB2[i] || !tB3[i] || !one[i] || !nAC[i] || !nC[i])
+        return ctx->fail(HTN_ERR_OOM, "uniform MPS: work tensor allocation failed");
+      RC(t_fill_level(one[i], 0, 1));
+      Program* p = own.program();
+      RC(build_mul_right(ctx, AL[i], C[i], p));
+      mulR.push_back(p);
+      p = own.program();
+      RC(build_project(ctx, ALt[i], AL[i], C[i], p));
+      proj.push_back(p);
+      p = own.program();
+      RC(build_bond_mul(ctx, C[i], p));
+      bmul.push_back(p);
+    }
+    return HTN_OK;
+  }
+
+  // AL -> (AR, C): iterated LQ through the unit cell (oracle/mps.py:uniform_rightorth)
+  int32_t rightorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
+    cudaStream_t st = ctx->stream;
+    RC(t_copy(C_guess, C[L - 1]));
+    RC(t_normalize(C[L - 1], C[L - 1]->d));
+    double delta = 1e300;
+    int it = 0;
+    for (it = 1; it <= maxiter; ++it) {
+      RC(t_copy(C[L - 1], tB3[L - 1]));  // C_old
+      for (int i = L - 1; i >= 0; --i) {
+        const int pb = prev(i);
+        RC(run3(mulR[i], AL[i]->d, C[i]->d, tA[i]->d));          // AL C
+        RC(t_transpose(tA[i], tAt[i], 1));                         // weighted transpose: panels per left sector
+        RC(t_qr_inplace(tAt[i], tB[pb]));                          // At = Qt Rt
+        RC(t_transpose(tB[pb], C[pb], 0));                         // L = Rt^T
+        RC(t_normalize(C[pb], C[pb]->d));
+        RC(t_transpose(tAt[i], AR[i], 2));                         // AR = Qt^T with the inverse weights
+      }
+      launch_axpby(-1.0, C[L - 1]->d, 1.0, tB3[L - 1]->d, C[L - 1]->dsize, st);
+      double d2 = 0.0;
+      RC(t_dot_host(C[L - 1], tB3[L - 1]->d, tB3[L - 1]->d, &d2));
+      delta = std::sqrt(std::max(d2, 0.0));
+      if (delta < tol) break;
+    }
+    RC(check_qr_status(ctx));
+    if (iters) *iters = std::min(it, maxiter);
+    if (delta_out) *delta_out = delta;
+    return delta < tol ? HTN_OK : HTN_NOT_CONVERGED;
+  }
+
+  // AL = Q(AC) Q(C)^T  (oracle/mps.py:regauge)
+  int32_t regauge(int i, const htn_tensor* ac, const htn_tensor* c, htn_tensor* al_out) {
+    RC(t_copy(ac, tA[i]));
+    RC(t_qr_inplace(tA[i], tB[i]));
+    RC(t_copy(c, tB2[i]));
+    RC(t_qr_inplace(tB2[i], tB[i]));
+    RC(t_transpose(tB2[i], tB3[i], 0));
+    RC(run3(mulR[i], tA[i]->d, tB3[i]->d, al_out->d));
+    return HTN_OK;
+  }
+
+  int32_t refresh_ac_and_transposes() {
+    for (int i = 0; i < L; ++i) {
+      if (AC[i]) RC(run3(mulR[i], AL[i]->d, C[i]->d, AC[i]->d));
+      RC(t_transpose(AL[i], ALt[i], 0));
+      if (AR[i]) RC(t_transpose(AR[i], ARt[i], 0));
+    }
+    return HTN_OK;
+  }
+
+  // ---------------- environments ----------------
+  int32_t init_envs(const htn_mpo* const* w, htn_tensor* const* gl, htn_tensor* const* gr) {
+    for (int i = 0; i < L; ++i) {
+      W.push_back(w[i]);
+      GL.push_back(gl[i]);
+      GR.push_back(gr[i]);
+    }
+    chi = (int)W[0]->Ml.sec.size();
+    for (int i = 0; i < L; ++i) {
+      if ((int)W[i]->Ml.sec.size() != chi || (int)W[i]->Mr.sec.size() != chi)
+        return ctx->fail(HTN_ERR_SHAPE, "environments: every site must carry the same MPO levels");
+      if (GL[i]->kind != HTN_T_ENVL || GR[i]->kind != HTN_T_ENVR || GL[i]->identity_level != 0 || GR[i]->identity_level != chi - 1)
+        return ctx->fail(HTN_ERR_INVALID, "environments: GL needs identity level 0, GR identity level chi-1");
+    }
+    // depth of the strictly upper-triangular level graph (oracle/mps.py:mpo_depth)
+    std::vector<int> d(chi, 0);
+    for (int sweep = 0; sweep < chi; ++sweep) {
+      bool changed = false;
+      for (int i = 0; i < L; ++i)
+        for (const MpoEntry& e : W[i]->entries)
+          if (e.a != e.b && d[e.b] < d[e.a] + 1) {
+            d[e.b] = d[e.a] + 1;
+            changed = true;
+          }
+      if (!changed) break;
+    }
+    depth = *std::max_element(d.begin(), d.end());
+    for (int i = 0; i < L; ++i) {
+      tGL.push_back(own.like(GL[i]));
+      tGR.push_back(own.like(GR[i]));
+      if (!tGL[i] || !tGR[i]) return ctx->fail(HTN_ERR_OOM, "environments: work tensor allocation failed");
+    }
+    for (int i = 0; i < L; ++i) {
+      htn_plan* p = nullptr;
+      // GL[i] (bond i-1) -> GL[i+1] (bond i) through AL[i];  GR[i] (bond i) -> GR[i-1] (bond i-1) through AR[i]
+      RC(htn_plan_transfer(ctx, HTN_SIDE_LEFT, W[i], AL[i], ALt[i], GL[i], GL[next(i)], &p));
+      own.plans.push_back(p);
+      TL.push_back(p);
+      RC(htn_plan_transfer(ctx, HTN_SIDE_RIGHT, W[i], AR[i], ARt[i], GR[i], GR[prev(i)], &p));
+      own.plans.push_back(p);
+      TR.push_back(p);
+      // MPO-free transfers on bond tensors
+      std::unique_ptr<htn_mpo> id(new htn_mpo());
+      id->ctx = ctx;
+      id->sym = AL[i]->sym;
+      id->Ml.ctx = id->Mr.ctx = ctx;
+      id->Ml.sym = id->Mr.sym = AL[i]->sym;
+      id->Ml.sec.push_back(Sector{0, 0, 0});
+      id->Mr.sec.push_back(Sector{0, 0, 0});
+      id->P = AL[i]->legs;
+      for (int s = 0; s < (int)id->P.sec.size(); ++s) id->entries.push_back(MpoEntry{0, s, s, 0, id->P.sec[s], 1.0});
+      RC(htn_plan_transfer(ctx, HTN_SIDE_LEFT, id.get(), AL[i], ALt[i], C[prev(i)], C[i], &p));
+      own.plans.push_back(p);
+      tl1.push_back(p);
+      RC(htn_plan_transfer(ctx, HTN_SIDE_RIGHT, id.get(), AR[i], ARt[i], C[i], C[prev(i)], &p));
+      own.plans.push_back(p);
+      tr1.push_back(p);
+      idmpo.push_back(std::move(id));
+    }
+    // level copies: last level of GL[0] <-> bond L-1 ; first level of GR[L-1] <-> bond L-1
+    Program* q = own.program();
+    RC(build_level_copy(ctx, GL[0], C[L - 1], chi - 1, false, q));
+    getL.push_back(q);
+    q = own.program();
+    RC(build_level_copy(ctx, GL[0], C[L - 1], chi - 1, true, q));
+    putL.push_back(q);
+    q = own.program();
+    RC(build_level_copy(ctx, GR[L - 1], C[L - 1], 0, false, q));
+    getR.push_back(q);
+    q = own.program();
+    RC(build_level_copy(ctx, GR[L - 1], C[L - 1], 0, true, q));
+    putR.push_back(q);
+    return HTN_OK;
+  }
+
+  int32_t transfer(htn_plan* p, const htn_tensor* A, const htn_tensor* At, const htn_tensor* in, htn_tensor* out) {
+    const double* slots[4] = {A->d, At->d, in->d, out->d};
+    return p->prog.run(slots);
+  }
+
+  // oracle/mps.py:Environments.  tol: GMRES tolerance.
+  int32_t environments(double tol, int krylovdim, int maxiter, double* e_left, double* e_right, int* applies) {
+    cudaStream_t st = ctx->stream;
+    const int last = chi - 1, bL = L - 1;
+    const int steps = std::max(depth + L - 1, L);
+    int napp = 0;
+    // ---------------- left ----------------
+    for (int i = 0; i < L; ++i) {
+      cudaMemsetAsync(GL[i]->d, 0, GL[i]->dsize * sizeof(double), st);
+      RC(t_fill_level(GL[i], 0, 1));
+    }
+    int i = 0;
+    for (int s = 0; s < steps; ++s) {
+      const int nx = next(i);
+      RC(transfer(TL[i], AL[i], ALt[i], GL[i], tGL[nx]));
+      RC(t_copy(tGL[nx], GL[nx]));
+      RC(t_fill_level(GL[nx], last, 0));
+      RC(t_fill_level(GL[nx], 0, 1));
+      i = nx;
+    }
+    for (i = 0; i < L; ++i) {
+      const int nx = next(i);
+      RC(transfer(TL[i], AL[i], ALt[i], GL[i], tGL[nx]));
+      if (nx != 0) RC(t_copy(tGL[nx], GL[nx]));
+    }
+    htn_tensor* Y = tB[bL];
+    RC(run2(getL[0], tGL[0]->d, Y->d));
+    // rho = C C^T on bond L-1
+    htn_tensor* rho = tB2[bL];
+    RC(t_transpose(C[bL], tB3[bL], 0));
+    RC(run3(bmul[bL], C[bL]->d, tB3[bL]->d, rho->d));
+    double eL = 0.0;
+    RC(t_dot_host(Y, Y->d, rho->d, &eL));
+    {
+      htn_tensor* like = C[bL];
+      const int64_t n = like->dsize;
+      double* sc = ctx->kry_scal + 400;
+      ApplyFn op = [&](const double* X, double* out) -> int32_t {
+        // out = X - T_cell(X) + (X|rho) 1
+        const double* cur = X;
+        for (int k = 0; k < L; ++k) {
+          const double* slots[4] = {AL[k]->d, ALt[k]->d, cur, nC[k]->d};
+          RC(tl1[k]->prog.run(slots));
+          cur = nC[k]->d;
+        }
+        cudaMemcpyAsync(out, X, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        launch_axpby(-1.0, cur, 1.0, out, n, st);
+        RC(t_dot_dev(like, X, rho->d, sc));
+        launch_multiaxpy(one[bL]->d, 0, 1, sc, 1.0, out, n, st);
+        return cuda_rc(ctx, "env operator");
+      };
+      launch_axpby(-eL, one[bL]->d, 1.0, Y->d, n, st);  // rhs = Y - eL 1
+      KrylovInfo info;
+      int32_t rc = gmres_solve(like, op, Y->d, tB3[bL]->d, krylovdim, tol, maxiter, &info);
+      if (rc < 0) return rc;
+      napp += info.applies;
+      RC(run2(putL[0], tB3[bL]->d, GL[0]->d));
+    }
+    for (i = 0; i + 1 < L; ++i) {
+      RC(transfer(TL[i], AL[i], ALt[i], GL[i], tGL[i + 1]));
+      RC(t_copy(tGL[i + 1], GL[i + 1]));
+    }
+    // ---------------- right ----------------
+    for (i = 0; i < L; ++i) {
+      cudaMemsetAsync(GR[i]->d, 0, GR[i]->dsize * sizeof(double), st);
+      RC(t_fill_level(GR[i], last, 1));
+    }
+    i = L - 1;
+    for (int s = 0; s < steps; ++s) {
+      const int pv = prev(i);
+      RC(transfer(TR[i], AR[i], ARt[i], GR[i], tGR[pv]));
+      RC(t_copy(tGR[pv], GR[pv]));
+      RC(t_fill_level(GR[pv], 0, 0));
+      RC(t_fill_level(GR[pv], last, 1));
+      i = pv;
+    }
+    for (i = L - 1; i >= 0; --i) {
+      const int pv = prev(i);
+      RC(transfer(TR[i], AR[i], ARt[i], GR[i], tGR[pv]));
+      if (pv != L - 1) RC(t_copy(tGR[pv], GR[pv]));
+    }
+    RC(run2(getR[0], tGR[bL]->d, Y->d));
+    // rho = C^T C on bond L-1
+    RC(t_transpose(C[bL], tB3[bL], 0));
+    RC(run3(bmul[bL], tB3[bL]->d, C[bL]->d, rho->d));
+    double eR = 0.0;
+    RC(t_dot_host(Y, Y->d, rho->d, &eR));
+    {
+      htn_tensor* like = C[bL];
+      const int64_t n = like->dsize;
+      double* sc = ctx->kry_scal + 400;
+      ApplyFn op = [&](const double* X, double* out) -> int32_t {
+        const double* cur = X;
+        for (int k = L - 1; k >= 0; --k) {
+          const int pv = prev(k);
+          const double* slots[4] = {AR[k]->d, ARt[k]->d, cur, nC[pv]->d};
+          RC(tr1[k]->prog.run(slots));
+          cur = nC[pv]->d;
+        }
+        cudaMemcpyAsync(out, X, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        launch_axpby(-1.0, cur, 1.0, out, n, st);
+        RC(t_dot_dev(like, X, rho->d, sc));
+        launch_multiaxpy(one[bL]->d, 0, 1, sc, 1.0, out, n, st);
+        return cuda_rc(ctx, "env operator");
+      };
+      launch_axpby(-eR, one[bL]->d, 1.0, Y->d, n, st);
+      KrylovInfo info;
+      int32_t rc = gmres_solve(like, op, Y->d, tB3[bL]->d, krylovdim, tol, maxiter, &info);
+      if (rc < 0) return rc;
+      napp += info.applies;
+      RC(run2(putR[0], tB3[bL]->d, GR[bL]->d));
+    }
+    for (i = L - 1; i > 0; --i) {
+      RC(transfer(TR[i], AR[i], ARt[i], GR[i], tGR[i - 1]));
+      RC(t_copy(tGR[i - 1], GR[i - 1]));
+    }
+    if (e_left) *e_left = eL;
+    if (e_right) *e_right = eR;
+    if (applies) *applies = napp;
+    return cuda_rc(ctx, "environments");
+  }
+
+  int32_t init_heff() {
+    for (int i = 0; i < L; ++i) {
+      htn_plan* p = nullptr;
+      RC(htn_plan_heff_ac(ctx, GL[i], W[i], GR[i], AL[i], &p));
+      own.plans.push_back(p);
+      hac.push_back(p);
+      RC(htn_plan_heff_c(ctx, GL[next(i)], GR[i], C[i], &p));
+      own.plans.push_back(p);
+      hc.push_back(p);
+    }
+    return HTN_OK;
+  }
+
+  // max_i || H_AC AC_i - AL_i (AL_i^T H_AC AC_i) ||   (oracle/mps.py:galerkin)
+  int32_t galerkin(double* eps_out) {
+    double eps = 0.0;
+    for (int i = 0; i < L; ++i) {
+      RC(htn_heff_run(hac[i], AC[i]->d, tA[i]->d, 0xF));
+      RC(run3(proj[i], ALt[i]->d, tA[i]->d, tB[i]->d));
+      RC(run3(mulR[i], AL[i]->d, tB[i]->d, tA2[i]->d));
+      launch_axpby(-1.0, tA2[i]->d, 1.0, tA[i]->d, tA[i]->dsize, ctx->stream);
+      double n2 = 0.0;
+      RC(t_dot_host(tA[i], tA[i]->d, tA[i]->d, &n2));
+      eps = std::max(eps, std::sqrt(std::max(n2, 0.0)));
+    }
+    *eps_out = eps;
+    return HTN_OK;
+  }
+};
+
+}  // namespace htn
+
+extern "C" {
+
+// ---- QR / LQ / regauge primitives ----------------------------------------------------------
+int32_t htn_qrpos(const htn_tensor* A, htn_tensor* Q, htn_tensor* R) {
+  if (!A || !Q || !R) return HTN_ERR_INVALID;
+  htn_ctx* ctx = A->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (A->kind != HTN_T_MPS && A->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "qrpos: A must be an MPS or bond tensor");
+  if (!htn_same_structure(A, Q)) return ctx->fail(HTN_ERR_SHAPE, "qrpos: Q must have the structure of A");
+  cudaSetDevice(ctx->device);
+  RC(t_copy(A, Q));
+  RC(t_qr_inplace(Q, R));
+  return check_qr_status(ctx);
+}
+
+int32_t htn_lqpos(const htn_tensor* A, htn_tensor* Lm, htn_tensor* Q) {
+  if (!A || !Q || !Lm) return HTN_ERR_INVALID;
+  htn_ctx* ctx = A->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (A->kind != HTN_T_MPS) return ctx->fail(HTN_ERR_INVALID, "lqpos: A must be an MPS tensor");
+  if (!htn_same_structure(A, Q) || Lm->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_SHAPE, "lqpos: Q / L structure");
+  cudaSetDevice(ctx->device);
+  TensorOwner own;
+  htn_tensor* At = own.transposed(A);
+  htn_tensor* Rt = own.like(Lm);
+  if (!At || !Rt) return ctx->fail(HTN_ERR_OOM, "lqpos: work tensor allocation failed");
+  RC(t_transpose(A, At, 1));
+  RC(t_qr_inplace(At, Rt));
+  RC(t_transpose(Rt, Lm, 0));
+  RC(t_transpose(At, Q, 2));
+  return check_qr_status(ctx);
+}
+
+int32_t htn_regauge(const htn_tensor* AC, const htn_tensor* C, htn_tensor* AL) {
+  if (!AC || !C || !AL) return HTN_ERR_INVALID;
+  htn_ctx* ctx = AC->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  htn_tensor* al[1] = {AL};
+  htn_tensor* cc[1] = {const_cast<htn_tensor*>(C)};
+  if (AC->kind != HTN_T_MPS || C->kind != HTN_T_BOND || !htn_same_structure(AC, AL) || AC->s1.sec != C->s0.sec ||
+      AC->s1.mult != C->s0.mult)
+    return ctx->fail(HTN_ERR_SHAPE, "regauge: structures do not match");
+  // a one-site workspace is enough (the bond chaining check needs Vl == Vr only for L = 1; bypass it)
+  U.ctx = ctx;
+  U.L = 1;
+  U.AL.push_back(al[0]);
+  U.C.push_back(cc[0]);
+  U.tA.push_back(U.own.like(AC));
+  U.tB.push_back(U.own.like(C));
+  U.tB2.push_back(U.own.like(C));
+  U.tB3.push_back(U.own.like(C));
+  if (!U.tA[0] || !U.tB[0] || !U.tB2[0] || !U.tB3[0]) return ctx->fail(HTN_ERR_OOM, "regauge: work tensor allocation failed");
+  Program* p = U.own.program();
+  RC(build_mul_right(ctx, AC, C, p));
+  U.mulR.push_back(p);
+  RC(U.regauge(0, AC, C, AL));
+  return check_qr_status(ctx);
+}
+
+// AL[0..n) (left-orthonormal) + guess for C[n-1]  ->  AR[i], C[i] with AL[i] C[i] = C[i-1] AR[i]
+int32_t htn_gauge_right(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
+                        htn_tensor* const* AR, htn_tensor* const* C, double tol, int32_t maxiter, int32_t* iterations,
+                        double* delta) {
+  if (!ctx || nsites <= 0 || !AL || !C_guess || !AR || !C) return HTN_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  RC(U.init_gauge(ctx, nsites, AL, AR, C, nullptr));
+  int it = 0;
+  double d = 0;
+  int32_t rc = U.rightorth(C_guess, tol, maxiter, &it, &d);
+  if (iterations) *iterations = it;
+  if (delta) *delta = d;
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+// GL[i], GR[i] of a Jordan-form MPO Hamiltonian and the energy per unit cell (left / right estimate)
+int32_t htn_environments(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR,
+                         htn_tensor* const* C, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
+                         double tol, int32_t krylovdim, int32_t maxiter, double* energy_left, double* energy_right) {
+  if (!ctx || nsites <= 0 || !AL || !AR || !C || !W || !GL || !GR) return HTN_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  RC(U.init_gauge(ctx, nsites, AL, AR, C, nullptr));
+  RC(U.refresh_ac_and_transposes());
+  RC(U.init_envs(W, GL, GR));
+  int32_t rc = U.environments(tol, krylovdim, maxiter, energy_left, energy_right, nullptr);
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+int32_t htn_eigsolve(htn_plan* p, const htn_tensor* x0, htn_tensor* x, int32_t krylovdim, double tol, int32_t maxiter,
+                     double* eigenvalue, double* residual, int32_t* applies) {
+  if (!p || !x0 || !x) return HTN_ERR_INVALID;
+  htn_ctx* ctx = p->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (p->kind != HTN_PLAN_HEFF_AC && p->kind != HTN_PLAN_HEFF_C && p->kind != HTN_PLAN_HEFF_AC2)
+    return ctx->fail(HTN_ERR_INVALID, "eigsolve: not an effective-Hamiltonian plan");
+  if (!htn_same_structure(p->like_in, x0) || !htn_same_structure(p->like_in, x))
+    return ctx->fail(HTN_ERR_SHAPE, "eigsolve: vectors do not have the plan's block structure");
+  cudaSetDevice(ctx->device);
+  ApplyFn op = [&](const double* a, double* b) -> int32_t { return htn_heff_run(p, a, b, 0xF); };
+  KrylovInfo info;
+  int32_t rc = lanczos_lowest(p->like_in, op, x0->d, x->d, krylovdim, tol, maxiter, &info);
+  if (eigenvalue) *eigenvalue = info.value;
+  if (residual) *residual = info.residual;
+  if (applies) *applies = info.applies;
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+// VUMPS on fixed bond spaces (oracle/mps.py:vumps).  log: per iteration 4 doubles
+// (galerkin error, energy per site, gauge iterations, H_eff applies); at most log_cap rows.
+int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR, htn_tensor* const* C,
+                  htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
+                  double tol, int32_t maxiter, int32_t krylovdim, double* delta, double* energy_per_site,
+                  int32_t* iterations, double* log, int32_t log_cap) {
+  if (!ctx || nsites <= 0 || !AL || !AR || !C || !AC || !W || !GL || !GR) return HTN_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  RC(U.init_gauge(ctx, nsites, AL, AR, C, AC));
+  RC(U.refresh_ac_and_transposes());
+  RC(U.init_envs(W, GL, GR));
+  RC(U.init_heff());
+  const int L = nsites;
+  double eps = 1.0, eL = 0, eR = 0;
+  RC(U.environments(1e-10, krylovdim, 200, &eL, &eR, nullptr));
+  int it = 0;
+  for (it = 1; it <= maxiter; ++it) {
+    const double tol_eig = std::min(1e-4, std::max(eps * 1e-3, 1e-14));
+    const double tol_env = std::min(1e-6, std::max(eps * 1e-4, 1e-14));
+    const double tol_gauge = std::min(1e-8, std::max(eps * 1e-6, 1e-14));
+    int napp = 0;
+    for (int i = 0; i < L; ++i) {
+      KrylovInfo info;
+      ApplyFn hac = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hac[i], a, b, 0xF); };
+      int32_t rc = lanczos_lowest(U.AC[i], hac, U.AC[i]->d, U.nAC[i]->d, krylovdim, tol_eig, 5, &info);
+      if (rc < 0) return rc;
+      napp += info.applies;
+      ApplyFn hc = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hc[i], a, b, 0xF); };
+      rc = lanczos_lowest(U.C[i], hc, U.C[i]->d, U.nC[i]->d, krylovdim, tol_eig, 5, &info);
+      if (rc < 0) return rc;
+      napp += info.applies;
+    }
+    for (int i = 0; i < L; ++i) RC(U.regauge(i, U.nAC[i], U.nC[i], U.AL[i]));
+    int git = 0;
+    {
+      int32_t rc = U.rightorth(U.nC[L - 1], tol_gauge, 10000, &git, nullptr);
+      if (rc < 0) return rc;
+    }
+    RC(U.refresh_ac_and_transposes());
+    {
+      int32_t rc = U.environments(tol_env, krylovdim, 200, &eL, &eR, nullptr);
+      if (rc < 0) return rc;
+    }
+    RC(U.galerkin(&eps));
+    if (log && it <= log_cap) {
+      double* row = log + 4 * (it - 1);
+      row[0] = eps;
+      row[1] = 0.5 * (eL + eR) / L;
+      row[2] = git;
+      row[3] = napp;
+    }
+    if (eps < tol) break;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  if (delta) *delta = eps;
+  if (energy_per_site) *energy_per_site = 0.5 * (eL + eR) / L;
+  if (iterations) *iterations = std::min(it, maxiter);
+  return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
+}
+
+// <op> for a one-site operator that is the scalar values[s] on physical multiplet s
+// (number operator of HubbardFunctions.jl:316-323 evaluated as at HF:1507)
+int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out) {
+  if (!AC || !values || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = AC->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (AC->kind != HTN_T_MPS || nvalues != (int)AC->legs.sec.size()) return ctx->fail(HTN_ERR_SHAPE, "expval_diag: one value per physical multiplet");
+  cudaSetDevice(ctx->device);
+  TensorOwner own;
+  htn_tensor* t = own.like(AC);
+  if (!t) return ctx->fail(HTN_ERR_OOM, "expval_diag: allocation failed");
+  Program* p = own.program();
+  RC(build_diag_op(ctx, AC, values, p));
+  RC(run2(p, AC->d, t->d));
+  double num = 0, den = 0;
+  RC(t_dot_host(AC, AC->d, t->d, &num));
+  RC(t_dot_host(AC, AC->d, AC->d, &den));
+  *out = num / den;
+  return HTN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// Contraction-program builder and executor (see htn_program.hpp).
+#include "htn_program.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace htn {
+
+namespace {
+
+struct TileSpec {
+  int mo, mn, no, nn, layout;
+};
+
+// near-equal split of an extent into pieces of at most 64, each a multiple of the DMMA atom (8)
+std::vector<std::pair<int, int>> split_flex(int n) {
+  std::vector<std::pair<int, int>> out;
+  int atoms = (n + 7) / 8, nt = (atoms + 7) / 8;
+  int base = atoms / nt, rem = atoms % nt, o = 0;
+  for (int i = 0; i < nt; ++i) {
+    int len = std::min(8 * (base + (i < rem ? 1 : 0)), n - o);
+    out.push_back({o, len});
+    o += len;
+  }
+  return out;
+}
+
+// pipe cost (executed DMMA atoms, 2 per active strip and flex atom) + a small charge for idle strips
+double tile_cost(int flex_ext, int fixed_ext) {
+  int flex = (flex_ext + 7) / 8, strips = (fixed_ext + 15) / 16;
+  return flex * 2.0 * strips + 0.25 * flex * 2.0 * (4 - strips);
+}
+
+// Cover an M x N block with CTA tiles (see the layout comment in htn_kernels.cu).  Variant 0:
+// full 64-column tiles in layout A (rows split flexibly) + the remaining columns as layout-B
+// tiles (64-row strips, flex = remaining columns).  Variant 1: the transpose.  Cheapest wins.
+std::vector<TileSpec> tile_block(int M, int N) {
+  std::vector<TileSpec> best;
+  double best_cost = 1e300;
+  if (M <= 0 || N <= 0) return best;
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<TileSpec> v;
+    double cost = 0;
+    if (variant == 0) {
+      int nfull = N / 64, rn = N % 64;
+      for (int j = 0; j < nfull; ++j)
+        for (auto& pm : split_flex(M)) {
+          v.push_back({pm.first, pm.second, j * 64, 64, 0});
+          cost += tile_cost(pm.second, 64);
+        }
+      if (rn)
+        for (int mo = 0; mo < M; mo += 64) {
+          int mn = std::min(64, M - mo);
+          v.push_back({mo, mn, nfull * 64, rn, 1});
+          cost += tile_cost(rn, mn);
+        }
+    } else {
+      int mfull = M / 64, rm = M % 64;
+      for (int i = 0; i < mfull; ++i)
+        for (auto& pn : split_flex(N)) {
+          v.push_back({i * 64, 64, pn.first, pn.second, 1});
+          cost += tile_cost(pn.second, 64);
+        }
+      if (rm)
+        for (int no = 0; no < N; no += 64) {
+          int nn = std::min(64, N - no);
+          v.push_back({mfull * 64, rm, no, nn, 0});
+          cost += tile_cost(rm, nn);
+        }
+    }
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = v;
+    }
+  }
+  return best;
+}
+
+inline void enc(const Opnd& o, long long& off, int& base) {
+  // workspace references stay offsets until finalize() turns them into absolute pointers
+  off = o.off;
+  base = o.slot == SLOT_WS ? -1 : o.slot + 1;
+}
+
+double padded_tile_flops(int mn, int nn, int K) {
+  return 2.0 * ((mn + 7) / 8 * 8) * ((nn + 7) / 8 * 8) * ((K + 3) / 4 * 4.0);
+}
+
+template <class T>
+int32_t to_device(htn_ctx* ctx, const std::vector<T>& v, T** out) {
+  *out = nullptr;
+  if (v.empty()) return HTN_OK;
+  cudaError_t e = cudaMalloc(out, v.size() * sizeof(T));
+  if (e != cudaSuccess) return ctx->fail(HTN_ERR_OOM, std::string("cudaMalloc(program table): ") + cudaGetErrorString(e));
+  e = cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("cudaMemcpy(program table): ") + cudaGetErrorString(e));
+  return HTN_OK;
+}
+
+}  // namespace
+
+int64_t Program::ws_alloc(int64_t elems) {
+  int64_t off = ws_elems;
+  ws_elems = align_up(ws_elems + std::max<int64_t>(elems, 0), 16);
+  return off;
+}
+
+static void emit_seg(Stage& st, const GemmSegH& s, const TileSpec& ts) {
+  GemmSeg sg{};
+  enc(s.A, sg.a_off, sg.a_base);
+  sg.a_off += (int64_t)ts.mo * s.lda;
+  sg.lda = s.lda;
+  enc(s.B, sg.b_off, sg.b_base);
+  sg.b_off += ts.no;
+  sg.ldb = s.ldb;
+  sg.K = s.K;
+  st.segs.push_back(sg);
+}
+
+void Program::add_gemm(std::vector<GemmTaskH>& tasks, int tag) {
+  Stage st;
+  st.kind = 0;
+  st.tag = tag;
+  for (const GemmTaskH& t : tasks) {
+    for (const GemmSegH& s : t.segs) {
+      flops += 2.0 * t.M * t.N * s.K;
+      flops_tag[tag & 15] += 2.0 * t.M * t.N * s.K;
+    }
+    for (const TileSpec& ts : tile_block(t.M, t.N)) {
+      GemmItem it{};
+      enc(t.C, it.c_off, it.c_base);
+      it.c_off += (int64_t)ts.mo * t.ldc + ts.no;
+      it.ldc = t.ldc;
+      it.mt = ts.mn;
+      it.nt = ts.nn;
+      it.layout = ts.layout;
+      it.beta = 0;
+      it.seg_begin = (int)st.segs.size();
+      it.nchunks = 0;
+      for (const GemmSegH& s : t.segs) {
+        if (s.K <= 0) continue;
+        emit_seg(st, s, ts);
+        it.nchunks += (s.K + GEMM_BK - 1) / GEMM_BK;
+        padded_flops += padded_tile_flops(ts.mn, ts.nn, s.K);
+      }
+      it.seg_end = (int)st.segs.size();
+      st.items.push_back(it);
+    }
+  }
+  auto cost = [](const GemmItem& it) { return (double)it.mt * it.nt * it.nchunks; };
+  std::stable_sort(st.items.begin(), st.items.end(), [&](const GemmItem& a, const GemmItem& b) { return cost(a) > cost(b); });
+  n_gemm_tiles_tag[tag & 15] += (int)st.items.size();
+  if (!st.items.empty()) stages.push_back(std::move(st));
+}
+
+void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::vector<MixSrcH>>& extra, int tag_gemm,
+                              int tag_mix) {
+  // split-K: a reduce task has few tiles but a K loop over every (level, sector) pair; cut the
+  // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy of
+  // the output block (summed in fixed order by the mix => deterministic, no atomics)
+  const int SPLIT_CHUNKS = 40, SPLIT_MAX = 32;
+  Stage st;
+  st.kind = 0;
+  st.tag = tag_gemm;
+  std::vector<MixTaskH> mixes;
+  for (size_t ti = 0; ti < tasks.size(); ++ti) {
+    const GemmTaskH& t = tasks[ti];
+    MixTaskH mx;
+    mx.dst = t.C;
+    mx.nelem = t.M * t.ldc;
+    if (ti < extra.size()) mx.srcs = extra[ti];
+    std::vector<const GemmSegH*> segs;
+    int total_chunks = 0;
+    for (const GemmSegH& s : t.segs)
+      if (s.K > 0) {
+        segs.push_back(&s);
+        total_chunks += (s.K + GEMM_BK - 1) / GEMM_BK;
+        flops += 2.0 * t.M * t.N * s.K;
+        flops_tag[tag_gemm & 15] += 2.0 * t.M * t.N * s.K;
+      }
+    if (!segs.empty() && t.M > 0 && t.N > 0) {
+      int nsplit = std::max(1, std::min({SPLIT_MAX, (total_chunks + SPLIT_CHUNKS / 2) / SPLIT_CHUNKS, (int)segs.size()}));
+      std::vector<int> cut(nsplit + 1, 0);
+      {
+        int acc = 0, sidx = 1;
+        for (size_t q = 0; q < segs.size(); ++q) {
+          acc += (segs[q]->K + GEMM_BK - 1) / GEMM_BK;
+          while (sidx < nsplit && acc >= (long long)total_chunks * sidx / nsplit) cut[sidx++] = (int)q + 1;
+        }
+        for (; sidx <= nsplit; ++sidx) cut[sidx] = (int)segs.size();
+        for (int q = 1; q <= nsplit; ++q) cut[q] = std::max(cut[q], cut[q - 1]);
+      }
+      const int64_t blk = (int64_t)t.M * t.ldc;
+      std::vector<int64_t> poff(nsplit, -1);
+      for (int sp = 0; sp < nsplit; ++sp)
+        if (cut[sp + 1] > cut[sp]) {
+          poff[sp] = ws_alloc(blk);
+          mx.srcs.push_back(MixSrcH{Opnd{SLOT_WS, poff[sp]}, 1.0});
+        }
+      for (const TileSpec& ts : tile_block(t.M, t.N))
+        for (int sp = 0; sp < nsplit; ++sp) {
+          if (poff[sp] < 0) continue;
+          GemmItem it{};
+          it.c_base = -1;
+          it.c_off = poff[sp] + (int64_t)ts.mo * t.ldc + ts.no;
+          it.ldc = t.ldc;
+          it.mt = ts.mn;
+          it.nt = ts.nn;
+          it.layout = ts.layout;
+          it.beta = 0;
+          it.seg_begin = (int)st.segs.size();
+          it.nchunks = 0;
+          for (int q = cut[sp]; q < cut[sp + 1]; ++q) {
+            emit_seg(st, *segs[q], ts);
+            it.nchunks += (segs[q]->K + GEMM_BK - 1) / GEMM_BK;
+            padded_flops += padded_tile_flops(ts.mn, ts.nn, segs[q]->K);
+          }
+          it.seg_end = (int)st.segs.size();
+          st.items.push_back(it);
+        }
+    }
+    if (mx.nelem > 0) mixes.push_back(std::move(mx));
+  }
+  auto cost = [](const GemmItem& it) { return (double)it.mt * it.nt * it.nchunks; };
+  std::stable_sort(st.items.begin(), st.items.end(), [&](const GemmItem& a, const GemmItem& b) { return cost(a) > cost(b); });
+  n_gemm_tiles_tag[tag_gemm & 15] += (int)st.items.size();
+  if (!st.items.empty()) stages.push_back(std::move(st));
+  add_mix(mixes, tag_mix);
+}
+
+void Program::add_mix(std::vector<MixTaskH>& tasks, int tag) {
+  Stage st;
+  st.kind = 1;
+  st.tag = tag;
+  for (const MixTaskH& t : tasks) {
+    if (t.nelem <= 0) continue;
+    MixTarget mt{};
+    enc(t.dst, mt.off, mt.base);
+    mt.nelem = t.nelem;
+    mt.src_begin = (int)st.ms.size();
+    for (const MixSrcH& s : t.srcs) {
+      MixSrc ms{};
+      enc(s.src, ms.off, ms.base);
+      ms.coef = s.coef;
+      st.ms.push_back(ms);
+    }
+    mt.src_end = (int)st.ms.size();
+    int ti = (int)st.mt.size();
+    st.mt.push_back(mt);
+    // ~16k element-sources per CTA, chunk a multiple of 512 elements (256 threads x double2)
+    int per = 16384 / std::max<int>(1, (int)t.srcs.size());
+    per = std::max(512, std::min(8192, per / 512 * 512));
+    for (int e = 0; e < t.nelem; e += per) st.mc.push_back(MixChunk{ti, e, std::min(per, t.nelem - e), 0});
+  }
+  if (!st.mc.empty()) stages.push_back(std::move(st));
+}
+
+int32_t Program::finalize(htn_ctx* c, int nslots_) {
+  ctx = c;
+  nslots = nslots_;
+  cudaSetDevice(ctx->device);
+  ws_elems = std::max<int64_t>(ws_elems, 16);
+  if (cudaMalloc(&ws, ws_elems * sizeof(double)) != cudaSuccess) {
+    ws = nullptr;
+    return ctx->fail(HTN_ERR_OOM, "program workspace allocation failed");
+  }
+  cudaMemset(ws, 0, ws_elems * sizeof(double));
+  auto fix = [&](long long& off, int& base) {
+    if (base == -1) {
+      off = reinterpret_cast<long long>(ws + off);
+      base = 0;
+    }
+  };
+  const int cap = ctx->sm_count * gemm_max_ctas_per_sm();
+  int32_t rc;
+  for (Stage& st : stages) {
+    if (st.kind == 0) {
+      for (GemmSeg& sg : st.segs) {
+        fix(sg.a_off, sg.a_base);
+        fix(sg.b_off, sg.b_base);
+      }
+      for (GemmItem& it : st.items) fix(it.c_off, it.c_base);
+      if (st.segs.empty()) st.segs.push_back(GemmSeg{});  // keep the table pointer valid
+      if ((rc = to_device(ctx, st.items, &st.d_items)) || (rc = to_device(ctx, st.segs, &st.d_segs))) return rc;
+      st.n = (int)st.items.size();
+      st.grid = std::max(1, std::min(st.n, cap));
+    } else {
+      for (MixTarget& t : st.mt) fix(t.off, t.base);
+      for (MixSrc& s : st.ms) fix(s.off, s.base);
+      if (st.ms.empty()) st.ms.push_back(MixSrc{});
+      if ((rc = to_device(ctx, st.mt, &st.d_mt)) || (rc = to_device(ctx, st.ms, &st.d_ms)) ||
+          (rc = to_device(ctx, st.mc, &st.d_mc)))
+        return rc;
+      st.n = (int)st.mc.size();
+    }
+    // host tables are no longer needed
+    std::vector<GemmItem>().swap(st.items);
+    std::vector<GemmSeg>().swap(st.segs);
+    std::vector<MixTarget>().swap(st.mt);
+    std::vector<MixSrc>().swap(st.ms);
+    std::vector<MixChunk>().swap(st.mc);
+  }
+  finalized = true;
+  return HTN_OK;
+}
+
+int32_t Program::run(const double* const* slots, int mask) const {
+  Bases bs;
+  for (int i = 0; i < MAX_SLOTS; ++i) bs.p[i] = i < nslots ? slots[i] : nullptr;
+  for (const Stage& st : stages) {
+    if (!(st.tag & mask)) continue;
+    if (st.kind == 0)
+      launch_gemm(st.d_items, st.d_segs, st.n, bs, st.grid, ctx->stream);
+    else
+      launch_mix(st.d_mt, st.d_ms, st.d_mc, st.n, bs, ctx->stream);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("program launch: ") + cudaGetErrorString(e));
+  return HTN_OK;
+}
+
+int Program::launches(int mask) const {
+  int n = 0;
+  for (const Stage& st : stages)
+    if (st.tag & mask) ++n;
+  return n;
+}
+
+void Program::destroy() {
+  for (Stage& st : stages) {
+    cudaFree(st.d_items);
+    cudaFree(st.d_segs);
+    cudaFree(st.d_mt);
+    cudaFree(st.d_ms);
+    cudaFree(st.d_mc);
+  }
+  stages.clear();
+  cudaFree(ws);
+  ws = nullptr;
+}
+
+}  // namespace htn

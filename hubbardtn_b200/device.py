@@ -149,6 +149,16 @@ class Tensor:
         L.check(lib.htn_tensor_create_like(self.h, C.byref(h)), self.ctx.h)
         return Tensor(self.ctx, h)
 
+    def transposed(self) -> "Tensor":
+        """Blockwise-transposed companion (kind MPST) of an MPS tensor (structure only)."""
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_transposed(self.h, C.byref(h)), self.ctx.h)
+        return Tensor(self.ctx, h)
+
+    def transpose_into(self, dst: "Tensor", weighted: bool = False) -> "Tensor":
+        L.check(lib.htn_tensor_transpose(self.h, dst.h, 1 if weighted else 0), self.ctx.h)
+        return dst
+
     # -- data movement -------------------------------------------------------------------
     def upload(self, packed: np.ndarray):
         packed = np.ascontiguousarray(packed, dtype=np.float64)
@@ -219,7 +229,24 @@ PLAN_STAT_NAMES = ["flops", "flops_L", "flops_R", "n_gemm_L", "n_gemm_R", "n_mix
                    "launches_per_apply"]
 
 
-class HeffAC:
+class _Heff:
+    """Common part of the effective-Hamiltonian plans (apply, eigsolve, timing)."""
+
+    def _finish(self, like):
+        st = (C.c_double * 12)()
+        L.check(lib.htn_plan_stats(self.h, st, 12), self.ctx.h)
+        self.stats = dict(zip(PLAN_STAT_NAMES, [float(v) for v in st]))
+        self.nelem = like.nelem
+
+    def eigsolve(self, x0: Tensor, x: Tensor, krylovdim: int = 30, tol: float = 1e-10, maxiter: int = 100):
+        """Lowest eigenpair (KrylovKit `eigsolve(.., :SR, Lanczos)`): returns (eigenvalue, info)."""
+        ev, res, napp = C.c_double(), C.c_double(), C.c_int32()
+        rc = L.check(lib.htn_eigsolve(self.h, x0.h, x.h, krylovdim, tol, maxiter, C.byref(ev), C.byref(res),
+                                      C.byref(napp)), self.ctx.h)
+        return ev.value, dict(converged=rc == 0, residual=res.value, applies=napp.value)
+
+
+class HeffAC(_Heff):
     """y = H_AC x  (MPSKit `AC_hamiltonian`): plan over fixed GL, W, GR."""
 
     def __init__(self, ctx: Context, GL: Tensor, W: Mpo, GR: Tensor, like: Tensor):
@@ -227,10 +254,7 @@ class HeffAC:
         h = C.c_void_p()
         L.check(lib.htn_plan_heff_ac(ctx.h, GL.h, W.h, GR.h, like.h, C.byref(h)), ctx.h)
         self.h = h
-        st = (C.c_double * 12)()
-        L.check(lib.htn_plan_stats(h, st, 12), ctx.h)
-        self.stats = dict(zip(PLAN_STAT_NAMES, [float(v) for v in st]))
-        self.nelem = like.nelem
+        self._finish(like)
 
     def apply(self, x: Tensor, y: Tensor):
         L.check(lib.htn_heff_apply(self.h, x.h, y.h), self.ctx.h)
@@ -264,6 +288,103 @@ class HeffAC:
             self.h = None
         except Exception:
             pass
+
+
+class HeffC(_Heff):
+    """y = H_C x  (MPSKit `C_hamiltonian`): GL on the bond of C (left env of the next site), GR of this site."""
+
+    def __init__(self, ctx: Context, GL: Tensor, GR: Tensor, like: Tensor):
+        self.ctx, self.GL, self.GR = ctx, GL, GR
+        h = C.c_void_p()
+        L.check(lib.htn_plan_heff_c(ctx.h, GL.h, GR.h, like.h, C.byref(h)), ctx.h)
+        self.h = h
+        self._finish(like)
+
+    def apply(self, x: Tensor, y: Tensor):
+        L.check(lib.htn_heff_apply(self.h, x.h, y.h), self.ctx.h)
+        return y
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                lib.htn_plan_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
+class Transfer:
+    """Environment transfer through one site (MPSKit `TransferMatrix`): side 0 = left, 1 = right."""
+
+    def __init__(self, ctx: Context, side: int, W: Mpo, A: Tensor, At: Tensor, env_in: Tensor, env_out: Tensor):
+        self.ctx, self.side, self.W = ctx, side, W
+        h = C.c_void_p()
+        L.check(lib.htn_plan_transfer(ctx.h, side, W.h, A.h, At.h, env_in.h, env_out.h, C.byref(h)), ctx.h)
+        self.h = h
+        st = (C.c_double * 12)()
+        L.check(lib.htn_plan_stats(h, st, 12), ctx.h)
+        self.stats = dict(zip(PLAN_STAT_NAMES, [float(v) for v in st]))
+
+    def apply(self, A: Tensor, At: Tensor, env_in: Tensor, env_out: Tensor):
+        L.check(lib.htn_transfer_apply(self.h, A.h, At.h, env_in.h, env_out.h), self.ctx.h)
+        return env_out
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                lib.htn_plan_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
+def _harr(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.h for t in tensors])
+    return arr
+
+
+def qrpos(A: Tensor, Q: Tensor, R: Tensor):
+    L.check(lib.htn_qrpos(A.h, Q.h, R.h), A.ctx.h)
+
+
+def lqpos(A: Tensor, Lm: Tensor, Q: Tensor):
+    L.check(lib.htn_lqpos(A.h, Lm.h, Q.h), A.ctx.h)
+
+
+def regauge(AC: Tensor, Cb: Tensor, AL: Tensor):
+    L.check(lib.htn_regauge(AC.h, Cb.h, AL.h), AC.ctx.h)
+
+
+def gauge_right(ctx: Context, AL, C_guess: Tensor, AR, Cs, tol=1e-13, maxiter=10000):
+    it, delta = C.c_int32(), C.c_double()
+    rc = L.check(lib.htn_gauge_right(ctx.h, len(AL), _harr(AL), C_guess.h, _harr(AR), _harr(Cs), tol, maxiter,
+                                     C.byref(it), C.byref(delta)), ctx.h)
+    return dict(converged=rc == 0, iterations=it.value, delta=delta.value)
+
+
+def environments(ctx: Context, AL, AR, Cs, Ws, GL, GR, tol=1e-12, krylovdim=30, maxiter=200):
+    el, er = C.c_double(), C.c_double()
+    rc = L.check(lib.htn_environments(ctx.h, len(AL), _harr(AL), _harr(AR), _harr(Cs), _harr(Ws), _harr(GL), _harr(GR),
+                                      tol, krylovdim, maxiter, C.byref(el), C.byref(er)), ctx.h)
+    return dict(converged=rc == 0, energy_cell_left=el.value, energy_cell_right=er.value)
+
+
+def vumps(ctx: Context, AL, AR, Cs, AC, Ws, GL, GR, tol=1e-10, maxiter=100, krylovdim=30):
+    """`find_groundstate(psi, H, VUMPS(; tol, maxiter))` on fixed bond spaces (in/out tensors)."""
+    delta, e, it = C.c_double(), C.c_double(), C.c_int32()
+    log = np.zeros((maxiter, 4))
+    rc = L.check(lib.htn_vumps(ctx.h, len(AL), _harr(AL), _harr(AR), _harr(Cs), _harr(AC), _harr(Ws), _harr(GL),
+                               _harr(GR), tol, maxiter, krylovdim, C.byref(delta), C.byref(e), C.byref(it),
+                               log.ctypes.data_as(C.POINTER(C.c_double)), maxiter), ctx.h)
+    return dict(converged=rc == 0, delta=delta.value, energy_per_site=e.value, iterations=it.value,
+                log=log[:it.value])
+
+
+def expval_diag(AC: Tensor, values) -> float:
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    out = C.c_double()
+    L.check(lib.htn_expval_diag(AC.h, v.ctypes.data_as(C.POINTER(C.c_double)), v.size, C.byref(out)), AC.ctx.h)
+    return out.value
 
 
 def network_coefficient(sym: int, nine_labels) -> float:

@@ -50,6 +50,7 @@ extern "C" {
 #define HTN_T_BOND 1 /* C      : V <- V               labels (c, c, c)   block [n_c , n_c ] */
 #define HTN_T_ENVL 2 /* GL     : (bra, level, ket)    labels (a, l', l)  block [n_l', n_l ] */
 #define HTN_T_ENVR 3 /* GR     : (ket, level, bra)    labels (b, r, r')  block [n_r , n_r'] */
+#define HTN_T_MPST 4 /* A^T    : blockwise transpose  labels (l, s, r)   block [n_r , n_l ], grouped by l */
 
 typedef struct htn_ctx htn_ctx;
 typedef struct htn_space htn_space;   /* graded bond space  (TensorKit GradedSpace)          */
@@ -91,6 +92,12 @@ int32_t htn_tensor_create_bond(htn_ctx* ctx, const htn_space* V, htn_tensor** ou
 int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, const htn_legs* M,
                               int32_t identity_level, htn_tensor** out);
 int32_t htn_tensor_create_like(const htn_tensor* t, htn_tensor** out);
+/* blockwise-transposed companion (kind HTN_T_MPST) of an MPS tensor; filled by htn_tensor_transpose */
+int32_t htn_tensor_create_transposed(const htn_tensor* t, htn_tensor** out);
+/* dst = blockwise transpose of src (MPS <-> MPST, or bond -> bond); weighted != 0 multiplies block
+ * (l,s,r) by sqrt(dim r / dim l) (MPS -> MPST) or its inverse (MPST -> MPS): the isometric weights
+ * of the right-orthonormal form */
+int32_t htn_tensor_transpose(const htn_tensor* src, htn_tensor* dst, int32_t weighted);
 int32_t htn_tensor_destroy(htn_tensor* t);
 /* Block table: nblocks rows of (label0,label1,label2) POSITIONS into the spaces, rows, cols,
  * packed host offset (elements, row-major blocks back to back, no padding).  Pass NULL
@@ -116,6 +123,11 @@ int32_t htn_mpo_destroy(htn_mpo* w);
  * copied; they must outlive the plan) and copies W. `like` fixes the block structure of x,y. */
 int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
                          const htn_tensor* like, htn_plan** out);
+/* Replaces: MPSKit `C_hamiltonian` / `∂C` (zero-site effective Hamiltonian, same call sites).
+ * GL = left environment on the bond of C (i.e. of the NEXT site), GR = right environment of
+ * this site; `like` is a bond tensor. */
+int32_t htn_plan_heff_c(htn_ctx* ctx, const htn_tensor* GL, const htn_tensor* GR, const htn_tensor* like,
+                        htn_plan** out);
 int32_t htn_plan_destroy(htn_plan* p);
 /* y = H_AC x on the device (x, y created with the plan's `like` structure; x != y) */
 int32_t htn_heff_apply(htn_plan* p, const htn_tensor* x, htn_tensor* y);
@@ -133,6 +145,61 @@ int32_t htn_plan_profile(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_
 /* `reps` back-to-back applies bracketed by two CUDA events on the library stream (device time
  * of the whole timed region, ms) — what bench.py reports as ms_per_step * steps */
 int32_t htn_heff_time(htn_plan* p, const htn_tensor* x, htn_tensor* y, int32_t reps, float* ms_total);
+
+/* ---- environment transfers ---------------------------------------------------------- */
+/* Replaces: MPSKit `TransferMatrix` application / `left_cyclethrough` used by `environments`
+ * (reached from find_groundstate, HubbardFunctions.jl:1010-1027).
+ *   side LEFT : GL'[b,r',r] = sum_a  A^T[l',s',r'] GL[a,l',l] W[a,b] A[l,s,r]   (env on the left bond -> right bond)
+ *   side RIGHT: GR'[a,l,l'] = sum_b  A[l,s,r] W[a,b] GR[b,r,r'] A^T[l',s',r']   (right bond -> left bond)
+ * At = htn_tensor_transpose(A) (kind HTN_T_MPST).  env_in/env_out fix the block structure; bond
+ * tensors are accepted as one-level environments (MPO-free transfer matrix, W = one trivial level). */
+int32_t htn_plan_transfer(htn_ctx* ctx, int32_t side, const htn_mpo* W, const htn_tensor* A, const htn_tensor* At,
+                          const htn_tensor* env_in, const htn_tensor* env_out, htn_plan** out);
+int32_t htn_transfer_apply(htn_plan* p, const htn_tensor* A, const htn_tensor* At, const htn_tensor* env_in,
+                           htn_tensor* env_out);
+
+/* ---- Krylov eigensolver --------------------------------------------------------------- */
+/* Replaces: KrylovKit `eigsolve(H_eff, x0, 1, :SR, Lanczos(krylovdim, tol, maxiter))` as called by
+ * MPSKit's VUMPS / IDMRG.  x: unit-norm eigenvector with <x0,x> >= 0.
+ * Returns HTN_NOT_CONVERGED (>0) with the last Ritz pair when maxiter restarts did not reach tol. */
+int32_t htn_eigsolve(htn_plan* p, const htn_tensor* x0, htn_tensor* x, int32_t krylovdim, double tol, int32_t maxiter,
+                     double* eigenvalue, double* residual, int32_t* applies);
+
+/* ---- gauge fixing --------------------------------------------------------------------- */
+/* Replaces: TensorKit `leftorth!(A, alg = QRpos())`: A = Q R per coupled (right) sector, diag R > 0.
+ * A: MPS tensor (Q same structure, R bond tensor on the right space) or bond tensor. */
+int32_t htn_qrpos(const htn_tensor* A, htn_tensor* Q, htn_tensor* R);
+/* Replaces: TensorKit `rightorth!(A, alg = LQpos())`: A = L Q per left sector, diag L > 0. */
+int32_t htn_lqpos(const htn_tensor* A, htn_tensor* L, htn_tensor* Q);
+/* Replaces: MPSKit `regauge!`: AL = Q(AC) Q(C)^T. */
+int32_t htn_regauge(const htn_tensor* AC, const htn_tensor* C, htn_tensor* AL);
+/* Replaces: MPSKit `uniform_rightorth!` (entered through InfiniteMPS(...), HubbardFunctions.jl:958,990
+ * and VUMPS's gauge step): from left-orthonormal AL[0..n) and a guess for C[n-1] compute AR[i], C[i]
+ * (C[i] on the bond right of site i, unit norm) with AL[i] C[i] = C[i-1] AR[i]. */
+int32_t htn_gauge_right(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
+                        htn_tensor* const* AR, htn_tensor* const* C, double tol, int32_t maxiter, int32_t* iterations,
+                        double* delta);
+
+/* ---- environments and ground-state driver ------------------------------------------------ */
+/* Replaces: MPSKit `environments(psi, H)` / `recalculate!` for an InfiniteMPOHamiltonian in Jordan
+ * form (level 0 and level chi-1 carry the identity): GL[i] on the bond left of site i (created with
+ * identity_level 0), GR[i] on the bond right of site i (identity_level chi-1); the identity-diagonal
+ * level is solved by GMRES.  energy_left/right = energy per UNIT CELL seen by either side. */
+int32_t htn_environments(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR,
+                         htn_tensor* const* C, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
+                         double tol, int32_t krylovdim, int32_t maxiter, double* energy_left, double* energy_right);
+/* Replaces: `find_groundstate(psi, H, VUMPS(; tol, maxiter))` (HubbardFunctions.jl:1012,1017,1025-1027)
+ * on fixed bond spaces.  In/out: AL, AR, C, AC (mixed gauge), GL, GR.  delta = final Galerkin error
+ * (the `δ` MPSKit returns, HF:1027).  log (may be NULL): rows of 4 doubles per iteration
+ * (galerkin error, energy per site, gauge iterations, H_eff applies). Returns HTN_NOT_CONVERGED when
+ * maxiter is reached (state usable, as MPSKit does). */
+int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR, htn_tensor* const* C,
+                  htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
+                  double tol, int32_t maxiter, int32_t krylovdim, double* delta, double* energy_per_site,
+                  int32_t* iterations, double* log, int32_t log_cap);
+/* Replaces: `expectation_value(psi, i => op)` (HubbardFunctions.jl:1448-1449,1507,1533) for one-site
+ * operators that are scalars on every physical multiplet (n, n_up, n_dn): values[s] per multiplet s. */
+int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out);
 
 /* ---- vector algebra on tensors of identical structure (KrylovKit inner products) ------ */
 /* <x,y> = sum_blocks dim(coupled sector) tr(x^T y)   (TensorKit inner product) */
