@@ -24,7 +24,7 @@ SYM_SU2U1 = 0
 SYM_U1U1 = 1
 SIDE_LEFT = 0
 SIDE_RIGHT = 1
-T_MPS, T_BOND, T_ENVL, T_ENVR, T_MPST = 0, 1, 2, 3, 4
+T_MPS, T_BOND, T_ENVL, T_ENVR, T_MPST, T_MPS2 = 0, 1, 2, 3, 4, 5
 
 
 class HtnError(RuntimeError):
@@ -70,6 +70,13 @@ SIGNATURES = {
     "htn_tensor_create_env": (_i32, [_p, _i32, _p, _p, _i32, _pp]),
     "htn_tensor_create_like": (_i32, [_p, _pp]),
     "htn_tensor_create_transposed": (_i32, [_p, _pp]),
+    "htn_tensor_create_mps2": (_i32, [_p, _p, _p, _p, _p, _pp]),
+    "htn_tensor_mid_sectors": (_i32, [_p, _pi32, _pi32]),
+    "htn_tensor_blocktable5": (_i32, [_p, _pi32, _pi64, _pi32, _pi32, _pi32, _pi64]),
+    "htn_tensor_kind": (_i32, [_p]),
+    "htn_plan_heff_ac2": (_i32, [_p, _p, _p, _p, _p, _p, _pp]),
+    "htn_contract_two_site": (_i32, [_p, _p, _p]),
+    "htn_tsvd": (_i32, [_p, C.c_double, _i32, _pp, _pp, _pp, _pp, _pd, _pi32]),
     "htn_tensor_transpose": (_i32, [_p, _p, _i32]),
     "htn_tensor_destroy": (_i32, [_p]),
     "htn_tensor_blocktable": (_i32, [_p, _pi32, _pi64, _pi32, _pi32, _pi32, _pi64]),

@@ -189,7 +189,10 @@ static int32_t finalize_tensor(htn_tensor* t) {
     b.hoff = hoff;
     off += (int64_t)b.rows * b.ld;
     hoff += (int64_t)b.rows * b.cols;
-    t->index[std::make_tuple(b.lab[0], b.lab[1], b.lab[2])] = (int)i;
+    if (t->kind == HTN_T_MPS2)
+      t->index5[std::array<int, 5>{b.lab[0], b.lab[1], b.lab[2], b.lab[3], b.lab[4]}] = (int)i;
+    else
+      t->index[std::make_tuple(b.lab[0], b.lab[1], b.lab[2])] = (int)i;
   }
   off = align_up(off, 16);
   t->dsize = std::max<int64_t>(off, 16);
@@ -347,6 +350,8 @@ int32_t htn_tensor_create_like(const htn_tensor* src, htn_tensor** out) {
   t->s0 = src->s0;
   t->s1 = src->s1;
   t->legs = src->legs;
+  t->legs2 = src->legs2;
+  t->mid = src->mid;
   t->identity_level = src->identity_level;
   t->blocks = src->blocks;
   int32_t rc = finalize_tensor(t);
@@ -357,6 +362,100 @@ int32_t htn_tensor_create_like(const htn_tensor* src, htn_tensor** out) {
   *out = t;
   return HTN_OK;
   HTN_CATCH(ctx)
+}
+
+// two-site tensor in the fusion-tree basis (l,s1 -> m), (m,s2 -> r); block order = oracle/twosite.py:
+// coupled sector r, then s2, then m (canonical sector order), then s1, then l
+int32_t htn_tensor_create_mps2(htn_ctx* ctx, const htn_space* Vl, const htn_legs* P1, const htn_legs* P2,
+                               const htn_space* Vr, htn_tensor** out) {
+  if (!ctx || !Vl || !P1 || !P2 || !Vr || !out) return HTN_ERR_INVALID;
+  if (Vl->sym != P1->sym || Vr->sym != P1->sym || P2->sym != P1->sym) return ctx->fail(HTN_ERR_INVALID, "symmetry kinds differ");
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  HTN_TRY
+  htn_tensor* t = new_tensor(ctx, HTN_T_MPS2, P1->sym);
+  const int sym = t->sym;
+  t->s0 = *Vl;
+  t->s1 = *Vr;
+  t->legs = *P1;
+  t->legs2 = *P2;
+  t->legs2.ctx = ctx;
+  const int nl = (int)Vl->sec.size(), n1 = (int)P1->sec.size(), n2 = (int)P2->sec.size(), nr = (int)Vr->sec.size();
+  auto fuse = [&](Sector a, Sector b) {
+    std::vector<Sector> out;
+    const int p = (a.p + b.p) & 1, n = a.n + b.n;
+    if (sym == HTN_SYM_SU2U1)
+      for (int q = std::abs(a.q - b.q); q <= a.q + b.q; q += 2) out.push_back(Sector{p, q, n});
+    else
+      out.push_back(Sector{p, a.q + b.q, n});
+    return out;
+  };
+  // all intermediate sectors that occur in some block
+  std::vector<Sector> mids;
+  for (int l = 0; l < nl; ++l)
+    for (int s1 = 0; s1 < n1; ++s1)
+      for (Sector m : fuse(Vl->sec[l], P1->sec[s1])) {
+        bool used = false;
+        for (int s2 = 0; s2 < n2 && !used; ++s2)
+          for (int r = 0; r < nr && !used; ++r) used = allowed(sym, m, P2->sec[s2], Vr->sec[r]);
+        if (used && std::find(mids.begin(), mids.end(), m) == mids.end()) mids.push_back(m);
+      }
+  std::sort(mids.begin(), mids.end(), [sym](Sector a, Sector b) { return canonical_less(sym, a, b); });
+  t->mid = mids;
+  for (int r = 0; r < nr; ++r)
+    for (int s2 = 0; s2 < n2; ++s2)
+      for (int m = 0; m < (int)mids.size(); ++m) {
+        if (!allowed(sym, mids[m], P2->sec[s2], Vr->sec[r])) continue;
+        for (int s1 = 0; s1 < n1; ++s1)
+          for (int l = 0; l < nl; ++l)
+            if (allowed(sym, Vl->sec[l], P1->sec[s1], mids[m])) {
+              Block b{};
+              b.lab[0] = l;
+              b.lab[1] = s1;
+              b.lab[2] = m;
+              b.lab[3] = s2;
+              b.lab[4] = r;
+              b.rows = Vl->mult[l];
+              b.cols = Vr->mult[r];
+              b.weight = sdim(sym, Vr->sec[r]);
+              t->blocks.push_back(b);
+            }
+      }
+  int32_t rc = finalize_tensor(t);
+  if (rc != HTN_OK) {
+    htn_tensor_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_tensor_mid_sectors(const htn_tensor* t, int32_t* n, int32_t* labels) {
+  if (!t) return HTN_ERR_INVALID;
+  if (n) *n = (int32_t)t->mid.size();
+  if (labels)
+    for (size_t i = 0; i < t->mid.size(); ++i) {
+      labels[3 * i] = t->mid[i].p;
+      labels[3 * i + 1] = t->mid[i].q;
+      labels[3 * i + 2] = t->mid[i].n;
+    }
+  return HTN_OK;
+}
+
+int32_t htn_tensor_blocktable5(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels, int32_t* rows,
+                               int32_t* cols, int64_t* offsets) {
+  if (!t) return HTN_ERR_INVALID;
+  if (nblocks) *nblocks = (int32_t)t->blocks.size();
+  if (nelem) *nelem = t->hsize;
+  for (size_t i = 0; i < t->blocks.size(); ++i) {
+    const Block& b = t->blocks[i];
+    if (labels)
+      for (int k = 0; k < 5; ++k) labels[5 * i + k] = b.lab[k];
+    if (rows) rows[i] = b.rows;
+    if (cols) cols[i] = b.cols;
+    if (offsets) offsets[i] = b.hoff;
+  }
+  return HTN_OK;
 }
 
 // blockwise transposed companion of an MPS tensor: blocks (l,s,r) stored as [n_r x n_l], ordered and
@@ -407,6 +506,8 @@ int32_t htn_tensor_destroy(htn_tensor* t) {
   delete t;
   return HTN_OK;
 }
+
+int32_t htn_tensor_kind(const htn_tensor* t) { return t ? t->kind : HTN_ERR_INVALID; }
 
 int32_t htn_tensor_blocktable(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels,
                               int32_t* rows, int32_t* cols, int64_t* offsets) {
@@ -527,7 +628,8 @@ static bool same_structure(const htn_tensor* x, const htn_tensor* y) {
     return false;
   for (size_t i = 0; i < x->blocks.size(); ++i) {
     const Block &a = x->blocks[i], &b = y->blocks[i];
-    if (a.lab[0] != b.lab[0] || a.lab[1] != b.lab[1] || a.lab[2] != b.lab[2] || a.rows != b.rows || a.cols != b.cols)
+    if (a.lab[0] != b.lab[0] || a.lab[1] != b.lab[1] || a.lab[2] != b.lab[2] || a.lab[3] != b.lab[3] ||
+        a.lab[4] != b.lab[4] || a.rows != b.rows || a.cols != b.cols)
       return false;
   }
   return true;

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstdint>
 #include <map>
 #include <mutex>
@@ -35,7 +36,7 @@ inline int even_up(int x) { return (x + 1) & ~1; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Block {
-  int32_t lab[3];
+  int32_t lab[5];  // kinds with 3 labels leave lab[3], lab[4] = 0
   int32_t rows, cols, ld;
   int64_t off;   // device offset (elements) inside the tensor's arena slice
   int64_t hoff;  // packed host offset (elements)
@@ -94,7 +95,10 @@ struct htn_tensor {
   int kind;
   int sym;
   htn_space s0, s1;  // MPS: Vl, Vr; BOND: V,V; ENV: V,V
-  htn_legs legs;     // MPS: P; ENV: M
+  htn_legs legs;     // MPS: P; ENV: M; MPS2: P of the first site
+  htn_legs legs2;    // MPS2: P of the second site
+  std::vector<htn::Sector> mid;  // MPS2: intermediate sectors m (canonical order); lab[2] indexes this list
+  std::map<std::array<int, 5>, int> index5;
   int identity_level = -1;
   std::vector<htn::Block> blocks;
   std::map<std::tuple<int, int, int>, int> index;
@@ -107,6 +111,10 @@ struct htn_tensor {
   int nchunks = 0;
   // cached device tables (transpose tiles, level fills, QR panels) keyed by (partner, mode)
   std::map<std::pair<const void*, int>, std::pair<void*, int>> devtables;
+  int find5(int l, int s1, int m, int s2, int r) const {
+    auto it = index5.find(std::array<int, 5>{l, s1, m, s2, r});
+    return it == index5.end() ? -1 : it->second;
+  }
   int find(int a, int b, int c) const {
     auto it = index.find(std::make_tuple(a, b, c));
     return it == index.end() ? -1 : it->second;
@@ -204,6 +212,14 @@ struct TrBlock {
   double scale;
 };
 void launch_transpose(const TrBlock* blocks, int nblocks, const double* src, double* dst, cudaStream_t st);
+void launch_copy2d(const TrBlock* blocks, int nblocks, const double* src, double* dst, cudaStream_t st);
+// one-sided Jacobi SVD of row panels: G [k x len] (ldg), Q [k x k] (ldq); k <= 1024
+struct SvdPanel {
+  long long offG, offQ, offS;
+  int k, len, ldg, ldq, u_in_g, pad_;
+};
+void launch_svd(const SvdPanel* panels, int npanels, double* G, double* Q, double* G2, double* Q2, double* sig,
+                int* status, cudaStream_t st);
 // set blocks to 0 (mode 0) or to the unit matrix (mode 1): table entries (off, rows, cols, ld)
 struct FillBlock {
   long long off;

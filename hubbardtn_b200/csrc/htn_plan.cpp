@@ -53,24 +53,91 @@ struct Src {
   double coef;
 };
 
-// Common front end of H_AC and T_L: enumerate the terms of
-//   sum coef * GL[a,l',l] . X[l,s,r] (x) (b; l',s',r' <- r)
-// and build stage L (T blocks) + the mix sources of every U block (b,l',s',r',r).
+// One term of an effective-Hamiltonian-like contraction:
+//   Y[yi] += coef * GL[a,lp,l] . X[xi] . (right object of level b mapping r -> rp)
+// X / Y blocks are referred to by their index in `like` (so the same back end serves one-site
+// tensors (l,s,r) and two-site tensors (l,s1,m,s2,r)).
+struct HTerm {
+  int yi, xi, a, lp, l, b, r, rp;
+  bool operator<(const HTerm& o) const {
+    return std::tie(yi, a, l, xi, b, r) < std::tie(o.yi, o.a, o.l, o.xi, o.b, o.r);
+  }
+};
+
+// Front end shared by H_AC, H_AC2 and T_L: stage L (T = GL . X, once per (a,lp,l,xi)) and the mix
+// sources of every U block (b, yi, r).
 struct LeftFront {
-  std::vector<std::tuple<int, int, int, int, int>> ukeys;  // (b,lp,sp,rp,r)
+  std::vector<std::tuple<int, int, int>> ukeys;  // (b, yi, r)
   std::vector<WsBlock> ub;
   std::vector<std::vector<Src>> usrc;
   int n_t = 0;
 };
 
-static LeftFront build_left_front(Program& pg, int sym, const htn_tensor* like, const EnvView& GL, const htn_mpo* W,
-                                  const std::function<bool(int, int, int)>& has_right /*(b,r,rp)*/, int slot_x,
-                                  int slot_gl) {
+static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView& GL,
+                             const std::map<HTerm, double>& terms, int slot_x, int slot_gl) {
+  LeftFront F;
+  const int idL = GL.identity_level();
+  std::map<std::tuple<int, int, int, int>, int> tindex;  // (a,lp,l,xi)
+  std::map<std::tuple<int, int, int>, int> uindex;
+  std::vector<GemmTaskH> tasksL;
+  std::vector<WsBlock> tb;
+  for (auto& kv : terms) {
+    if (kv.second == 0.0) continue;
+    const HTerm& t = kv.first;
+    const Block& xb = like->blocks[t.xi];
+    const Block& yb = like->blocks[t.yi];
+    Src src;
+    src.coef = kv.second;
+    if (t.a == idL) {
+      if (t.lp != t.l) continue;  // identity level is trivial
+      src.o = Opnd{slot_x, xb.off};
+    } else {
+      auto key = std::make_tuple(t.a, t.lp, t.l, t.xi);
+      auto it = tindex.find(key);
+      int ti;
+      if (it == tindex.end()) {
+        ti = (int)tb.size();
+        tindex[key] = ti;
+        WsBlock w{yb.rows, xb.cols, even_up(xb.cols), 0};
+        w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
+        tb.push_back(w);
+        const Block& gl = GL.t->blocks[GL.find(t.a, t.lp, t.l)];
+        GemmTaskH g;
+        g.C = Opnd{SLOT_WS, w.off};
+        g.ldc = w.ld;
+        g.M = w.rows;
+        g.N = w.cols;
+        g.segs.push_back(GemmSegH{Opnd{slot_gl, gl.off}, gl.ld, Opnd{slot_x, xb.off}, xb.ld, gl.cols});
+        tasksL.push_back(std::move(g));
+      } else
+        ti = it->second;
+      src.o = Opnd{SLOT_WS, tb[ti].off};
+    }
+    auto key = std::make_tuple(t.b, t.yi, t.r);
+    auto it = uindex.find(key);
+    int ui;
+    if (it == uindex.end()) {
+      ui = (int)F.ub.size();
+      uindex[key] = ui;
+      F.ukeys.push_back(key);
+      F.ub.push_back(WsBlock{yb.rows, xb.cols, even_up(xb.cols), -1});
+      F.usrc.emplace_back();
+    } else
+      ui = it->second;
+    F.usrc[ui].push_back(src);
+  }
+  F.n_t = (int)tb.size();
+  pg.add_gemm(tasksL, TAG_L);
+  return F;
+}
+
+// terms of the one-site network  sum w N / dim(r') : H_AC (has_right = GR block) and T_L (has_right =
+// output block)
+static std::map<HTerm, double> one_site_terms(int sym, const htn_tensor* like, const EnvView& GL, const htn_mpo* W,
+                                              const std::function<bool(int, int, int)>& has_right /*(b,r,rp)*/) {
   const auto& Vl = like->s0;
   const auto& Vr = like->s1;
   const auto& P = like->legs;
-  LeftFront F;
-  // partner tables
   std::map<std::pair<int, int>, std::vector<int>> pl;  // (a,l) -> l'
   const int nl = (int)Vl.sec.size(), nr = (int)Vr.sec.size();
   const int nlev_l = (int)W->Ml.sec.size(), nlev_r = (int)W->Mr.sec.size();
@@ -85,9 +152,7 @@ static LeftFront build_left_front(Program& pg, int sym, const htn_tensor* like, 
         if (has_right(b, r, rp)) pr[{b, r}].push_back(rp);
   std::vector<std::vector<std::pair<int, int>>> xs(P.sec.size());
   for (const Block& b : like->blocks) xs[b.lab[1]].push_back({b.lab[0], b.lab[2]});
-
-  typedef std::tuple<int, int, int, int, int, int, int, int> TermKey;  // lp,sp,rp,a,l,s,r,b
-  std::map<TermKey, double> terms;
+  std::map<HTerm, double> terms;
   for (const MpoEntry& e : W->entries) {
     for (auto& lr : xs[e.s]) {
       int l = lr.first, r = lr.second;
@@ -96,67 +161,62 @@ static LeftFront build_left_front(Program& pg, int sym, const htn_tensor* like, 
       if (itl == pl.end() || itr == pr.end()) continue;
       for (int lp : itl->second)
         for (int rp : itr->second) {
-          if (like->find(lp, e.sp, rp) < 0) continue;
+          const int yi = like->find(lp, e.sp, rp);
+          if (yi < 0) continue;
           double n = network(sym, Vl.sec[lp], P.sec[e.sp], Vr.sec[rp], Vl.sec[l], P.sec[e.s], Vr.sec[r],
                              W->Ml.sec[e.a], W->Mr.sec[e.b], e.c);
           if (n == 0.0) continue;
-          terms[TermKey(lp, e.sp, rp, e.a, l, e.s, r, e.b)] += e.w * n / sdim(sym, Vr.sec[rp]);
+          terms[HTerm{yi, like->find(l, e.s, r), e.a, lp, l, e.b, r, rp}] += e.w * n / sdim(sym, Vr.sec[rp]);
         }
     }
   }
-  const int idL = GL.identity_level();
-  std::map<std::tuple<int, int, int, int, int>, int> tindex, uindex;
-  std::vector<GemmTaskH> tasksL;
-  std::vector<WsBlock> tb;
-  for (auto& kv : terms) {
-    if (kv.second == 0.0) continue;
-    int lp, sp, rp, a, l, s, r, b;
-    std::tie(lp, sp, rp, a, l, s, r, b) = kv.first;
-    Src src;
-    src.coef = kv.second;
-    const int nlp = Vl.mult[lp], nrr = Vr.mult[r];
-    if (a == idL) {
-      if (lp != l) continue;  // identity level is trivial
-      src.o = Opnd{slot_x, like->blocks[like->find(l, s, r)].off};
-    } else {
-      auto key = std::make_tuple(a, lp, l, s, r);
-      auto it = tindex.find(key);
-      int ti;
-      if (it == tindex.end()) {
-        ti = (int)tb.size();
-        tindex[key] = ti;
-        WsBlock w{nlp, nrr, even_up(nrr), 0};
-        w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
-        tb.push_back(w);
-        const Block& gl = GL.t->blocks[GL.find(a, lp, l)];
-        const Block& xb = like->blocks[like->find(l, s, r)];
-        GemmTaskH t;
-        t.C = Opnd{SLOT_WS, w.off};
-        t.ldc = w.ld;
-        t.M = w.rows;
-        t.N = w.cols;
-        t.segs.push_back(GemmSegH{Opnd{slot_gl, gl.off}, gl.ld, Opnd{slot_x, xb.off}, xb.ld, gl.cols});
-        tasksL.push_back(std::move(t));
-      } else
-        ti = it->second;
-      src.o = Opnd{SLOT_WS, tb[ti].off};
-    }
-    auto key = std::make_tuple(b, lp, sp, rp, r);
-    auto it = uindex.find(key);
-    int ui;
-    if (it == uindex.end()) {
-      ui = (int)F.ub.size();
-      uindex[key] = ui;
-      F.ukeys.push_back(key);
-      F.ub.push_back(WsBlock{nlp, nrr, even_up(nrr), -1});
-      F.usrc.emplace_back();
-    } else
-      ui = it->second;
-    F.usrc[ui].push_back(src);
+  return terms;
+}
+
+// Back end shared by H_AC and H_AC2: U blocks (stage W), stage R with split-K, final mix into y.
+// slots: 0 = x, 1 = y, 2 = GL, 3 = GR
+static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_tensor* GR, LeftFront& F, int* n_u_out,
+                               int* n_mix_t, int* n_mix_s_out) {
+  const int idR = GR->identity_level;
+  std::vector<MixTaskH> mixU;
+  std::vector<std::vector<MixSrcH>> yextra(like->blocks.size());
+  std::vector<GemmTaskH> tasksR(like->blocks.size());
+  int n_u = 0, n_mix_s = 0;
+  for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
+    const Block& yb = like->blocks[yi];
+    tasksR[yi].C = Opnd{1, yb.off};
+    tasksR[yi].ldc = yb.ld;
+    tasksR[yi].M = yb.rows;
+    tasksR[yi].N = yb.cols;
   }
-  F.n_t = (int)tb.size();
-  pg.add_gemm(tasksL, TAG_L);
-  return F;
+  std::vector<int> order(F.ukeys.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int i, int j) { return F.ukeys[i] < F.ukeys[j]; });
+  for (int ui : order) {
+    int b, yi, r;
+    std::tie(b, yi, r) = F.ukeys[ui];
+    n_mix_s += (int)F.usrc[ui].size();
+    if (b == idR) {
+      for (const Src& s : F.usrc[ui]) yextra[yi].push_back(MixSrcH{s.o, s.coef});
+      continue;
+    }
+    WsBlock& w = F.ub[ui];
+    w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
+    MixTaskH mt;
+    mt.dst = Opnd{SLOT_WS, w.off};
+    mt.nelem = w.rows * w.ld;
+    for (const Src& s : F.usrc[ui]) mt.srcs.push_back(MixSrcH{s.o, s.coef});
+    mixU.push_back(std::move(mt));
+    const int rp = like->kind == HTN_T_MPS ? like->blocks[yi].lab[2] : like->blocks[yi].lab[4];
+    const Block& gr = GR->blocks[GR->find(b, r, rp)];
+    tasksR[yi].segs.push_back(GemmSegH{Opnd{SLOT_WS, w.off}, w.ld, Opnd{3, gr.off}, gr.ld, gr.rows});
+    ++n_u;
+  }
+  *n_mix_t = (int)(mixU.size() + like->blocks.size());
+  pg.add_mix(mixU, TAG_W);
+  pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y);
+  *n_u_out = n_u;
+  *n_mix_s_out = n_mix_s;
 }
 
 }  // namespace htn
@@ -223,51 +283,15 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     p->bound[3] = GR;
     Program& pg = p->prog;
     EnvView gl{GL};
-    LeftFront F = build_left_front(pg, sym, like, gl, W, [&](int b, int r, int rp) { return GR->find(b, r, rp) >= 0; }, 0, 2);
-    const int idR = GR->identity_level;
-    // stage W: materialise U for non-identity right levels; identity level feeds y directly
-    std::vector<MixTaskH> mixU;
-    std::vector<std::vector<MixSrcH>> yextra(like->blocks.size());
-    std::vector<GemmTaskH> tasksR(like->blocks.size());
-    int n_u = 0, n_mix_s = 0;
-    for (size_t yi = 0; yi < like->blocks.size(); ++yi) {
-      const Block& yb = like->blocks[yi];
-      tasksR[yi].C = Opnd{1, yb.off};
-      tasksR[yi].ldc = yb.ld;
-      tasksR[yi].M = yb.rows;
-      tasksR[yi].N = yb.cols;
-    }
-    // deterministic order of the K segments: sorted U keys
-    std::vector<int> order(F.ukeys.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int i, int j) { return F.ukeys[i] < F.ukeys[j]; });
-    for (int ui : order) {
-      int b, lp, sp, rp, r;
-      std::tie(b, lp, sp, rp, r) = F.ukeys[ui];
-      const int yi = like->find(lp, sp, rp);
-      n_mix_s += (int)F.usrc[ui].size();
-      if (b == idR) {
-        for (const Src& s : F.usrc[ui]) yextra[yi].push_back(MixSrcH{s.o, s.coef});
-        continue;
-      }
-      WsBlock& w = F.ub[ui];
-      w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
-      MixTaskH mt;
-      mt.dst = Opnd{SLOT_WS, w.off};
-      mt.nelem = w.rows * w.ld;
-      for (const Src& s : F.usrc[ui]) mt.srcs.push_back(MixSrcH{s.o, s.coef});
-      mixU.push_back(std::move(mt));
-      const Block& gr = GR->blocks[GR->find(b, r, rp)];
-      tasksR[yi].segs.push_back(GemmSegH{Opnd{SLOT_WS, w.off}, w.ld, Opnd{3, gr.off}, gr.ld, gr.rows});
-      ++n_u;
-    }
-    pg.add_mix(mixU, TAG_W);
-    pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y);
+    auto terms = one_site_terms(sym, like, gl, W, [&](int b, int r, int rp) { return GR->find(b, r, rp) >= 0; });
+    LeftFront F = build_front(pg, like, gl, terms, 0, 2);
+    int n_u = 0, n_mix_t = 0, n_mix_s = 0;
+    build_heff_backend(pg, like, GR, F, &n_u, &n_mix_t, &n_mix_s);
     if ((rc = pg.finalize(ctx, 4))) {
       htn_plan_destroy(p);
       return rc;
     }
-    fill_stats(p, F.n_t, n_u, (int)(mixU.size() + like->blocks.size()), n_mix_s);
+    fill_stats(p, F.n_t, n_u, n_mix_t, n_mix_s);
   } catch (const std::bad_alloc&) {
     if (p) htn_plan_destroy(p);
     return ctx->fail(HTN_ERR_OOM, "plan_heff_ac: host allocation failed");
@@ -277,6 +301,150 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
   }
   *out = p;
   return HTN_OK;
+}
+
+// Two-site effective Hamiltonian: two nested copies of the one-site recoupling network
+// (oracle/twosite.py:HeffAC2Plan).  slots: 0 = x2, 1 = y2, 2 = GL, 3 = GR
+int32_t htn_plan_heff_ac2(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W1, const htn_mpo* W2,
+                          const htn_tensor* GR, const htn_tensor* like, htn_plan** out) {
+  if (!ctx || !GL || !W1 || !W2 || !GR || !like || !out) return HTN_ERR_INVALID;
+  *out = nullptr;
+  if (GL->kind != HTN_T_ENVL || GR->kind != HTN_T_ENVR || like->kind != HTN_T_MPS2)
+    return ctx->fail(HTN_ERR_INVALID, "plan_heff_ac2: wrong tensor kinds");
+  const int sym = like->sym;
+  if (GL->s0.sec != like->s0.sec || GL->s0.mult != like->s0.mult || GR->s0.sec != like->s1.sec ||
+      GR->s0.mult != like->s1.mult)
+    return ctx->fail(HTN_ERR_SHAPE, "plan_heff_ac2: environment bond spaces do not match x2");
+  if (GL->legs.sec != W1->Ml.sec || W1->Mr.sec != W2->Ml.sec || GR->legs.sec != W2->Mr.sec ||
+      like->legs.sec != W1->P.sec || like->legs2.sec != W2->P.sec)
+    return ctx->fail(HTN_ERR_SHAPE, "plan_heff_ac2: MPO legs do not match");
+  htn_tensor* like_copy = nullptr;
+  int32_t rc = htn_tensor_create_like(like, &like_copy);
+  if (rc) return rc;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  htn_plan* p = nullptr;
+  try {
+    p = new htn_plan();
+    p->ctx = ctx;
+    p->kind = HTN_PLAN_HEFF_AC2;
+    p->like_in = like_copy;
+    p->bound[2] = GL;
+    p->bound[3] = GR;
+    Program& pg = p->prog;
+    EnvView gl{GL};
+    const auto& Vl = like->s0;
+    const auto& Vr = like->s1;
+    const auto& P1 = like->legs;
+    const auto& P2 = like->legs2;
+    std::map<std::pair<int, int>, std::vector<int>> pl, pr;
+    for (const Block& b : GL->blocks) pl[{b.lab[0], b.lab[2]}].push_back(b.lab[1]);
+    for (const Block& b : GR->blocks) pr[{b.lab[0], b.lab[1]}].push_back(b.lab[2]);
+    std::vector<std::vector<const MpoEntry*>> w1_by_s(P1.sec.size());
+    for (const MpoEntry& e : W1->entries) w1_by_s[e.s].push_back(&e);
+    std::map<std::pair<int, int>, std::vector<const MpoEntry*>> w2_by_bs;
+    for (const MpoEntry& e : W2->entries) w2_by_bs[{e.a, e.s}].push_back(&e);
+    std::map<std::tuple<int, int, int>, int> mid_index;
+    for (size_t i = 0; i < like->mid.size(); ++i) mid_index[{like->mid[i].p, like->mid[i].q, like->mid[i].n}] = (int)i;
+    std::map<HTerm, double> terms;
+    for (size_t xi = 0; xi < like->blocks.size(); ++xi) {
+      const Block& xb = like->blocks[xi];
+      const int l = xb.lab[0], s1 = xb.lab[1], m = xb.lab[2], s2 = xb.lab[3], r = xb.lab[4];
+      const Sector cm = like->mid[m];
+      for (const MpoEntry* e1 : w1_by_s[s1]) {
+        auto itl = pl.find({e1->a, l});
+        if (itl == pl.end()) continue;
+        auto it2 = w2_by_bs.find({e1->b, s2});
+        if (it2 == w2_by_bs.end()) continue;
+        for (int lp : itl->second) {
+          const Sector clp = Vl.sec[lp], csp = P1.sec[e1->sp];
+          const int p2 = (clp.p + csp.p) & 1, n2 = clp.n + csp.n;
+          const int qlo = sym == HTN_SYM_SU2U1 ? std::abs(clp.q - csp.q) : clp.q + csp.q;
+          const int qhi = clp.q + csp.q;
+          for (int q = qlo; q <= qhi; q += 2) {
+            const Sector cmp{p2, q, n2};
+            auto itm = mid_index.find({cmp.p, cmp.q, cmp.n});
+            if (itm == mid_index.end()) continue;
+            const double na = network(sym, clp, csp, cmp, Vl.sec[l], P1.sec[s1], cm, W1->Ml.sec[e1->a], W1->Mr.sec[e1->b], e1->c);
+            if (na == 0.0) continue;
+            for (const MpoEntry* e2 : it2->second) {
+              auto itr = pr.find({e2->b, r});
+              if (itr == pr.end()) continue;
+              for (int rp : itr->second) {
+                const int yi = like->find5(lp, e1->sp, itm->second, e2->sp, rp);
+                if (yi < 0) continue;
+                const double nb = network(sym, cmp, P2.sec[e2->sp], Vr.sec[rp], cm, P2.sec[s2], Vr.sec[r], W2->Ml.sec[e2->a],
+                                          W2->Mr.sec[e2->b], e2->c);
+                if (nb == 0.0) continue;
+                terms[HTerm{yi, (int)xi, e1->a, lp, l, e2->b, r, rp}] +=
+                    (e1->w * na / sdim(sym, cmp)) * (e2->w * nb / sdim(sym, Vr.sec[rp]));
+              }
+            }
+          }
+        }
+      }
+    }
+    LeftFront F = build_front(pg, like, gl, terms, 0, 2);
+    int n_u = 0, n_mix_t = 0, n_mix_s = 0;
+    build_heff_backend(pg, like, GR, F, &n_u, &n_mix_t, &n_mix_s);
+    if ((rc = pg.finalize(ctx, 4))) {
+      htn_plan_destroy(p);
+      return rc;
+    }
+    fill_stats(p, F.n_t, n_u, n_mix_t, n_mix_s);
+  } catch (const std::bad_alloc&) {
+    if (p) htn_plan_destroy(p);
+    return ctx->fail(HTN_ERR_OOM, "plan_heff_ac2: host allocation failed");
+  } catch (const std::exception& e) {
+    if (p) htn_plan_destroy(p);
+    return ctx->fail(HTN_ERR_INVALID, std::string("plan_heff_ac2: ") + e.what());
+  }
+  *out = p;
+  return HTN_OK;
+}
+
+// x2[l,s1,m,s2,r] = A1[l,s1,m] . A2[m,s2,r]
+int32_t htn_contract_two_site(const htn_tensor* A1, const htn_tensor* A2, htn_tensor* x2) {
+  if (!A1 || !A2 || !x2) return HTN_ERR_INVALID;
+  htn_ctx* ctx = A1->ctx;
+  if (A1->kind != HTN_T_MPS || A2->kind != HTN_T_MPS || x2->kind != HTN_T_MPS2)
+    return ctx->fail(HTN_ERR_INVALID, "contract_two_site: wrong tensor kinds");
+  if (A1->s1.sec != A2->s0.sec || A1->s1.mult != A2->s0.mult || A1->s0.sec != x2->s0.sec || A1->s0.mult != x2->s0.mult ||
+      A2->s1.sec != x2->s1.sec || A2->s1.mult != x2->s1.mult || A1->legs.sec != x2->legs.sec || A2->legs.sec != x2->legs2.sec)
+    return ctx->fail(HTN_ERR_SHAPE, "contract_two_site: spaces do not match");
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  try {
+    Program pg;
+    std::vector<GemmTaskH> tasks;
+    for (const Block& b : x2->blocks) {
+      GemmTaskH t;
+      t.C = Opnd{2, b.off};
+      t.ldc = b.ld;
+      t.M = b.rows;
+      t.N = b.cols;
+      const Sector cm = x2->mid[b.lab[2]];
+      int mi = -1;
+      for (size_t i = 0; i < A1->s1.sec.size(); ++i)
+        if (A1->s1.sec[i] == cm) mi = (int)i;
+      if (mi >= 0) {
+        const Block& a1 = A1->blocks[A1->find(b.lab[0], b.lab[1], mi)];
+        const Block& a2 = A2->blocks[A2->find(mi, b.lab[3], b.lab[4])];
+        t.segs.push_back(GemmSegH{Opnd{0, a1.off}, a1.ld, Opnd{1, a2.off}, a2.ld, a1.cols});
+      }
+      tasks.push_back(std::move(t));
+    }
+    pg.add_gemm(tasks, TAG_L);
+    int32_t rc = pg.finalize(ctx, 3);
+    if (rc == HTN_OK) {
+      const double* slots[3] = {A1->d, A2->d, x2->d};
+      rc = pg.run(slots);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    pg.destroy();
+    return rc;
+  } catch (const std::exception& e) {
+    return ctx->fail(HTN_ERR_INVALID, std::string("contract_two_site: ") + e.what());
+  }
 }
 
 // slots: 0 = x (C), 1 = y, 2 = GL, 3 = GR.   GL lives on the bond of C (left env of the next
@@ -406,7 +574,8 @@ int32_t htn_plan_transfer(htn_ctx* ctx, int32_t side, const htn_mpo* W, const ht
     int n_t = 0, n_u = 0, n_mix_s = 0;
     if (left) {
       // front end identical to H_AC with x = A; the "right partner" test is the output block
-      LeftFront F = build_left_front(pg, sym, A, ein, W, [&](int b, int r, int rp) { return eout.find(b, rp, r) >= 0; }, 0, 2);
+      auto terms = one_site_terms(sym, A, ein, W, [&](int b, int r, int rp) { return eout.find(b, rp, r) >= 0; });
+      LeftFront F = build_front(pg, A, ein, terms, 0, 2);
       n_t = F.n_t;
       std::vector<MixTaskH> mixU;
       std::map<int, GemmTaskH> tasks;  // by output block index
@@ -414,8 +583,9 @@ int32_t htn_plan_transfer(htn_ctx* ctx, int32_t side, const htn_mpo* W, const ht
       for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
       std::sort(order.begin(), order.end(), [&](int i, int j) { return F.ukeys[i] < F.ukeys[j]; });
       for (int ui : order) {
-        int b, lp, sp, rp, r;
-        std::tie(b, lp, sp, rp, r) = F.ukeys[ui];
+        int b, yi, r;
+        std::tie(b, yi, r) = F.ukeys[ui];
+        const int lp = A->blocks[yi].lab[0], sp = A->blocks[yi].lab[1], rp = A->blocks[yi].lab[2];
         WsBlock& w = F.ub[ui];
         w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
         MixTaskH mt;

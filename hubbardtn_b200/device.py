@@ -124,12 +124,31 @@ class Tensor:
                                           rows.ctypes.data_as(pi32), cols.ctypes.data_as(pi32),
                                           offs.ctypes.data_as(C.POINTER(C.c_int64))), ctx.h)
         self.labels, self.rows, self.cols, self.offsets = lab, rows, cols, offs
+        self.kind = lib.htn_tensor_kind(handle)
+        self.mid = None
+        if self.kind == L.T_MPS2:
+            lab5 = np.zeros((self.nblocks, 5), dtype=np.int32)
+            L.check(lib.htn_tensor_blocktable5(handle, C.byref(nb), C.byref(ne), lab5.ctypes.data_as(pi32), None, None,
+                                               None), ctx.h)
+            self.labels = lab5
+            nm = C.c_int32()
+            L.check(lib.htn_tensor_mid_sectors(handle, C.byref(nm), None), ctx.h)
+            mid = np.zeros((nm.value, 3), dtype=np.int32)
+            L.check(lib.htn_tensor_mid_sectors(handle, C.byref(nm), mid.ctypes.data_as(pi32)), ctx.h)
+            self.mid = [tuple(int(v) for v in row) for row in mid]
 
     # -- constructors --------------------------------------------------------------------
     @staticmethod
     def mps(ctx, Vl: Space, P: Legs, Vr: Space) -> "Tensor":
         h = C.c_void_p()
         L.check(lib.htn_tensor_create_mps(ctx.h, Vl.h, P.h, Vr.h, C.byref(h)), ctx.h)
+        return Tensor(ctx, h)
+
+    @staticmethod
+    def mps2(ctx, Vl: Space, P1: Legs, P2: Legs, Vr: Space) -> "Tensor":
+        """Two-site tensor (MPSKit AC2) in the fusion-tree basis; labels (l, s1, m, s2, r), m -> self.mid."""
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_create_mps2(ctx.h, Vl.h, P1.h, P2.h, Vr.h, C.byref(h)), ctx.h)
         return Tensor(ctx, h)
 
     @staticmethod
@@ -290,6 +309,29 @@ class HeffAC(_Heff):
             pass
 
 
+class HeffAC2(_Heff):
+    """y2 = H_AC2 x2  (MPSKit `AC2_hamiltonian`): GL of the first site, GR of the second site."""
+
+    def __init__(self, ctx: Context, GL: Tensor, W1: Mpo, W2: Mpo, GR: Tensor, like: Tensor):
+        self.ctx, self.GL, self.GR, self.W1, self.W2 = ctx, GL, GR, W1, W2
+        h = C.c_void_p()
+        L.check(lib.htn_plan_heff_ac2(ctx.h, GL.h, W1.h, W2.h, GR.h, like.h, C.byref(h)), ctx.h)
+        self.h = h
+        self._finish(like)
+
+    def apply(self, x: Tensor, y: Tensor):
+        L.check(lib.htn_heff_apply(self.h, x.h, y.h), self.ctx.h)
+        return y
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                lib.htn_plan_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
 class HeffC(_Heff):
     """y = H_C x  (MPSKit `C_hamiltonian`): GL on the bond of C (left env of the next site), GR of this site."""
 
@@ -341,6 +383,37 @@ class Transfer:
 def _harr(tensors):
     arr = (C.c_void_p * len(tensors))(*[t.h for t in tensors])
     return arr
+
+
+class _OwnedSpace(Space):
+    """Space created by the library (htn_tsvd); wraps an existing handle."""
+
+    def __init__(self, ctx, sym, handle):
+        self.ctx, self.sym, self.h = ctx, sym, handle
+        n = C.c_int32()
+        L.check(lib.htn_space_info(handle, C.byref(n), None, None), ctx.h)
+        lab2 = np.zeros((n.value, 3), dtype=np.int32)
+        mul2 = np.zeros(n.value, dtype=np.int32)
+        L.check(lib.htn_space_info(handle, C.byref(n), lab2.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   mul2.ctypes.data_as(C.POINTER(C.c_int32))), ctx.h)
+        self.sectors = [tuple(int(v) for v in row) for row in lab2]
+        self.mult = [int(v) for v in mul2]
+
+
+def contract_two_site(A1: Tensor, A2: Tensor, x2: Tensor) -> Tensor:
+    L.check(lib.htn_contract_two_site(A1.h, A2.h, x2.h), A1.ctx.h)
+    return x2
+
+
+def tsvd(x2: Tensor, cut: float = 0.0, maxdim: int = 0, sym: int = 0):
+    """x2 = AL . C . AR per middle sector with global truncation (TensorKit `tsvd!` + `truncbelow`)."""
+    ctx = x2.ctx
+    hv, hal, hc, har = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    disc, kept = C.c_double(), C.c_int32()
+    L.check(lib.htn_tsvd(x2.h, cut, maxdim, C.byref(hv), C.byref(hal), C.byref(hc), C.byref(har), C.byref(disc),
+                         C.byref(kept)), ctx.h)
+    return (_OwnedSpace(ctx, sym, hv), Tensor(ctx, hal), Tensor(ctx, hc), Tensor(ctx, har),
+            dict(discarded_weight=disc.value, kept=kept.value))
 
 
 def qrpos(A: Tensor, Q: Tensor, R: Tensor):

@@ -51,6 +51,8 @@ extern "C" {
 #define HTN_T_ENVL 2 /* GL     : (bra, level, ket)    labels (a, l', l)  block [n_l', n_l ] */
 #define HTN_T_ENVR 3 /* GR     : (ket, level, bra)    labels (b, r, r')  block [n_r , n_r'] */
 #define HTN_T_MPST 4 /* A^T    : blockwise transpose  labels (l, s, r)   block [n_r , n_l ], grouped by l */
+#define HTN_T_MPS2 5 /* AC2    : (V_l (x) P (x) P) <- V_r in the fusion-tree basis (l,s1->m),(m,s2->r):
+                       labels (l, s1, m, s2, r), m = position in htn_tensor_mid_sectors; block [n_l , n_r ] */
 
 typedef struct htn_ctx htn_ctx;
 typedef struct htn_space htn_space;   /* graded bond space  (TensorKit GradedSpace)          */
@@ -91,6 +93,14 @@ int32_t htn_tensor_create_bond(htn_ctx* ctx, const htn_space* V, htn_tensor** ou
 /* identity_level >= 0 flags the level that holds the unit tensor (GL[1] / GR[chi]); -1: none */
 int32_t htn_tensor_create_env(htn_ctx* ctx, int32_t side, const htn_space* V, const htn_legs* M,
                               int32_t identity_level, htn_tensor** out);
+/* two-site tensor x2 = AC (x) AR (MPSKit `AC2`, reached from IDMRG2 at HubbardFunctions.jl:1010) */
+int32_t htn_tensor_create_mps2(htn_ctx* ctx, const htn_space* Vl, const htn_legs* P1, const htn_legs* P2,
+                               const htn_space* Vr, htn_tensor** out);
+/* intermediate sectors of a two-site tensor (canonical order); labels may be NULL to query n */
+int32_t htn_tensor_mid_sectors(const htn_tensor* t, int32_t* n, int32_t* labels /*[n][3]*/);
+/* block table with 5 labels per block (kinds with 3 labels report 0 for the last two) */
+int32_t htn_tensor_blocktable5(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels /*[n][5]*/,
+                               int32_t* rows, int32_t* cols, int64_t* offsets);
 int32_t htn_tensor_create_like(const htn_tensor* t, htn_tensor** out);
 /* blockwise-transposed companion (kind HTN_T_MPST) of an MPS tensor; filled by htn_tensor_transpose */
 int32_t htn_tensor_create_transposed(const htn_tensor* t, htn_tensor** out);
@@ -99,6 +109,7 @@ int32_t htn_tensor_create_transposed(const htn_tensor* t, htn_tensor** out);
  * of the right-orthonormal form */
 int32_t htn_tensor_transpose(const htn_tensor* src, htn_tensor* dst, int32_t weighted);
 int32_t htn_tensor_destroy(htn_tensor* t);
+int32_t htn_tensor_kind(const htn_tensor* t); /* HTN_T_* */
 /* Block table: nblocks rows of (label0,label1,label2) POSITIONS into the spaces, rows, cols,
  * packed host offset (elements, row-major blocks back to back, no padding).  Pass NULL
  * arrays to query nblocks / nelem only. */
@@ -123,6 +134,13 @@ int32_t htn_mpo_destroy(htn_mpo* w);
  * copied; they must outlive the plan) and copies W. `like` fixes the block structure of x,y. */
 int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
                          const htn_tensor* like, htn_plan** out);
+/* Replaces: MPSKit `AC2_hamiltonian` / `∂∂AC2` (two-site effective Hamiltonian of IDMRG2,
+ * HubbardFunctions.jl:1010): y2 = GL . x2 . W1 . W2 . GR; GL = left environment of the first site,
+ * GR = right environment of the second site; `like` is a HTN_T_MPS2 tensor. */
+int32_t htn_plan_heff_ac2(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W1, const htn_mpo* W2,
+                          const htn_tensor* GR, const htn_tensor* like, htn_plan** out);
+/* x2[l,s1,m,s2,r] = A1[l,s1,m] . A2[m,s2,r]  (x2 created with htn_tensor_create_mps2) */
+int32_t htn_contract_two_site(const htn_tensor* A1, const htn_tensor* A2, htn_tensor* x2);
 /* Replaces: MPSKit `C_hamiltonian` / `∂C` (zero-site effective Hamiltonian, same call sites).
  * GL = left environment on the bond of C (i.e. of the NEXT site), GR = right environment of
  * this site; `like` is a bond tensor. */
@@ -179,6 +197,14 @@ int32_t htn_regauge(const htn_tensor* AC, const htn_tensor* C, htn_tensor* AL);
 int32_t htn_gauge_right(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
                         htn_tensor* const* AR, htn_tensor* const* C, double tol, int32_t maxiter, int32_t* iterations,
                         double* delta);
+
+/* ---- truncated SVD ---------------------------------------------------------------------- */
+/* Replaces: TensorKit `tsvd!(ac2; trunc = truncbelow(cut))` / `truncdim` as used by IDMRG2 and
+ * `changebonds(.., SvdCut)` (HubbardFunctions.jl:1010,1013,1018,1363-1365): x2 = AL . C . AR with C the
+ * diagonal of kept Schmidt values.  Keeps sigma >= cut * ||x2||, at most maxdim multiplets (maxdim <= 0:
+ * no cap).  Creates the new middle space and the three factors (caller destroys them). */
+int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, htn_space** Vm, htn_tensor** AL, htn_tensor** C,
+                 htn_tensor** AR, double* discarded_weight, int32_t* kept);
 
 /* ---- environments and ground-state driver ------------------------------------------------ */
 /* Replaces: MPSKit `environments(psi, H)` / `recalculate!` for an InfiniteMPOHamiltonian in Jordan
