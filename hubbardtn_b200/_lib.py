@@ -74,6 +74,7 @@ SIGNATURES = {
     "htn_tensor_mid_sectors": (_i32, [_p, _pi32, _pi32]),
     "htn_tensor_blocktable5": (_i32, [_p, _pi32, _pi64, _pi32, _pi32, _pi32, _pi64]),
     "htn_tensor_kind": (_i32, [_p]),
+    "htn_tensor_space": (_i32, [_p, _i32, _pp]),
     "htn_plan_heff_ac2": (_i32, [_p, _p, _p, _p, _p, _p, _pp]),
     "htn_contract_two_site": (_i32, [_p, _p, _p]),
     "htn_tsvd": (_i32, [_p, C.c_double, _i32, _pp, _pp, _pp, _pp, _pd, _pi32]),
@@ -98,6 +99,9 @@ SIGNATURES = {
     "htn_vumps": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, _pp, _pp, C.c_double, _i32, _i32, _pd, _pd, _pi32,
                          _pd, _i32]),
     "htn_expval_diag": (_i32, [_p, _pd, _i32, _pd]),
+    "htn_idmrg2": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, C.c_double, C.c_double, _i32, _i32, C.c_double, _i32, _pd,
+                          _pi32, _pd, _i32]),
+    "htn_mixed_gauge": (_i32, [_p, _i32, _pp, _p, _pp, _pp, _pp, C.c_double, _i32, _pi32]),
     "htn_heff_apply": (_i32, [_p, _p, _p]),
     "htn_heff_apply_host": (_i32, [_p, _p, _p, _i64]),
     "htn_plan_stats": (_i32, [_p, _pd, _i32]),

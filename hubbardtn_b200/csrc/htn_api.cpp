@@ -509,6 +509,14 @@ int32_t htn_tensor_destroy(htn_tensor* t) {
 
 int32_t htn_tensor_kind(const htn_tensor* t) { return t ? t->kind : HTN_ERR_INVALID; }
 
+int32_t htn_tensor_space(const htn_tensor* t, int32_t which, htn_space** out) {
+  if (!t || !out) return HTN_ERR_INVALID;
+  HTN_TRY
+  *out = new htn_space(which == 0 ? t->s0 : t->s1);
+  return HTN_OK;
+  HTN_CATCH(t->ctx)
+}
+
 int32_t htn_tensor_blocktable(const htn_tensor* t, int32_t* nblocks, int64_t* nelem, int32_t* labels,
                               int32_t* rows, int32_t* cols, int64_t* offsets) {
   if (!t) return HTN_ERR_INVALID;

@@ -226,6 +226,7 @@ struct FillBlock {
   int rows, cols, ld, mode;
 };
 void launch_fill(const FillBlock* blocks, int nblocks, double* dst, cudaStream_t st);
+void launch_diag_inv(const FillBlock* blocks, int nblocks, const double* src, double* dst, cudaStream_t st);
 // in-place QR with positive diagonal (iterated classical Gram-Schmidt) of row-major [m x n] panels:
 // panel p: Q overwrites A (off_a, m, n, lda); R (n x n upper, row-major ldr) written at off_r
 struct QrPanel {

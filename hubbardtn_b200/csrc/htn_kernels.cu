@@ -638,6 +638,21 @@ __global__ void __launch_bounds__(256) fill_kernel(const FillBlock* __restrict__
   }
 }
 
+// dst = inverse of the diagonal of src, off-diagonal zero (IDMRG2 edge update: inv(C) with C diagonal)
+__global__ void __launch_bounds__(256) diag_inv_kernel(const FillBlock* __restrict__ blocks, const double* __restrict__ src,
+                                                       double* __restrict__ dst) {
+  const FillBlock B = blocks[blockIdx.x];
+  const int n = B.rows * B.ld;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int r = e / B.ld, c = e % B.ld;
+    dst[B.off + e] = (r == c && c < B.cols) ? 1.0 / src[B.off + e] : 0.0;
+  }
+}
+
+void launch_diag_inv(const FillBlock* blocks, int nblocks, const double* src, double* dst, cudaStream_t st) {
+  if (nblocks > 0) diag_inv_kernel<<<nblocks, 256, 0, st>>>(blocks, src, dst);
+}
+
 void launch_fill(const FillBlock* blocks, int nblocks, double* dst, cudaStream_t st) {
   if (nblocks > 0) fill_kernel<<<nblocks, 256, 0, st>>>(blocks, dst);
 }

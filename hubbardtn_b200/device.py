@@ -168,6 +168,12 @@ class Tensor:
         L.check(lib.htn_tensor_create_like(self.h, C.byref(h)), self.ctx.h)
         return Tensor(self.ctx, h)
 
+    def space(self, which: int, sym: int = 0) -> "Space":
+        """Copy of the left (0) / right (1) bond space this tensor was built on."""
+        h = C.c_void_p()
+        L.check(lib.htn_tensor_space(self.h, which, C.byref(h)), self.ctx.h)
+        return _OwnedSpace(self.ctx, sym, h)
+
     def transposed(self) -> "Tensor":
         """Blockwise-transposed companion (kind MPST) of an MPS tensor (structure only)."""
         h = C.c_void_p()
@@ -451,6 +457,36 @@ def vumps(ctx: Context, AL, AR, Cs, AC, Ws, GL, GR, tol=1e-10, maxiter=100, kryl
                                log.ctypes.data_as(C.POINTER(C.c_double)), maxiter), ctx.h)
     return dict(converged=rc == 0, delta=delta.value, energy_per_site=e.value, iterations=it.value,
                 log=log[:it.value])
+
+
+def idmrg2(ctx: Context, AL, AR, Cs, AC, Ws, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol=1e-8, maxdim=0):
+    """`find_groundstate(psi, H, IDMRG2(trscheme=truncbelow(cut), tol))` (HF:1010).  The bond spaces
+    change, so the tensors are REPLACED: returns new (AL, AR, C, AC) lists and an info dict."""
+    lists = [list(AL), list(AR), list(Cs), list(AC)]
+    arrs = [_harr(x) for x in lists]
+    delta, it = C.c_double(), C.c_int32()
+    log = np.zeros((maxiter, 3))
+    rc = lib.htn_idmrg2(ctx.h, len(AL), arrs[0], arrs[1], arrs[2], arrs[3], _harr(Ws), cut, tol, maxiter, krylovdim,
+                        eig_tol, maxdim, C.byref(delta), C.byref(it), log.ctypes.data_as(C.POINTER(C.c_double)), maxiter)
+    out = []
+    for x, arr in zip(lists, arrs):
+        new = []
+        for i, t in enumerate(x):
+            # the old wrapper is always retired: its tensor was either destroyed by the library or is
+            # re-wrapped here (a recycled address may carry a different block structure)
+            t.h = None
+            new.append(Tensor(ctx, C.c_void_p(arr[i])))
+        out.append(new)
+    L.check(rc, ctx.h)
+    return out[0], out[1], out[2], out[3], dict(converged=rc == 0, delta=delta.value, iterations=it.value,
+                                                 log=log[:it.value])
+
+
+def mixed_gauge(ctx: Context, AL, C_guess: Tensor, AR, Cs, AC, tol=1e-12, maxiter=10000):
+    it = C.c_int32()
+    rc = L.check(lib.htn_mixed_gauge(ctx.h, len(AL), _harr(AL), C_guess.h, _harr(AR), _harr(Cs), _harr(AC), tol, maxiter,
+                                     C.byref(it)), ctx.h)
+    return dict(converged=rc == 0, iterations=it.value)
 
 
 def expval_diag(AC: Tensor, values) -> float:

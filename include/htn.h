@@ -110,6 +110,8 @@ int32_t htn_tensor_create_transposed(const htn_tensor* t, htn_tensor** out);
 int32_t htn_tensor_transpose(const htn_tensor* src, htn_tensor* dst, int32_t weighted);
 int32_t htn_tensor_destroy(htn_tensor* t);
 int32_t htn_tensor_kind(const htn_tensor* t); /* HTN_T_* */
+/* copy of the bond space a tensor was built on: which = 0 left / first, 1 right / second (caller destroys) */
+int32_t htn_tensor_space(const htn_tensor* t, int32_t which, htn_space** out);
 /* Block table: nblocks rows of (label0,label1,label2) POSITIONS into the spaces, rows, cols,
  * packed host offset (elements, row-major blocks back to back, no padding).  Pass NULL
  * arrays to query nblocks / nelem only. */
@@ -223,6 +225,21 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
                   htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
                   double tol, int32_t maxiter, int32_t krylovdim, double* delta, double* energy_per_site,
                   int32_t* iterations, double* log, int32_t log_cap);
+/* Replaces: `find_groundstate(psi, H, IDMRG2(trscheme = truncbelow(cut), tol, maxiter))`
+ * (HubbardFunctions.jl:1010): two-site infinite DMRG over a unit cell of nsites >= 2 with bond spaces
+ * re-defined by the truncated SVD (keep Schmidt values >= cut, at most maxdim multiplets if maxdim > 0).
+ * In/out handle arrays: the library destroys every tensor it replaces and stores the new handle; the
+ * caller destroys the final ones.  delta = || C_new - C_old || on the common subspace of the edge bond.
+ * log (may be NULL): rows of 3 doubles (delta, sum of D_red over the bonds, cumulative H_AC2 applies).
+ * The result is NOT yet a consistent uniform MPS: call htn_mixed_gauge (MPSKit does `InfiniteMPS(psi.AR)`). */
+int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** AR, htn_tensor** C, htn_tensor** AC,
+                   const htn_mpo* const* W, double cut, double tol, int32_t maxiter, int32_t krylovdim, double eig_tol,
+                   int32_t maxdim, double* delta, int32_t* iterations, double* log, int32_t log_cap);
+/* Replaces: `InfiniteMPS(AL...)` gauge fixing (MPSKit `uniform_leftorth!/uniform_rightorth!`): AL <- Q(AL),
+ * then AR, C (iterated LQ) and AC = AL C.  AL is modified in place. */
+int32_t htn_mixed_gauge(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
+                        htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, double tol, int32_t maxiter,
+                        int32_t* iterations);
 /* Replaces: `expectation_value(psi, i => op)` (HubbardFunctions.jl:1448-1449,1507,1533) for one-site
  * operators that are scalars on every physical multiplet (n, n_up, n_dn): values[s] per multiplet s. */
 int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out);

@@ -93,3 +93,42 @@ def test_contract_and_tsvd_match_oracle(ctx, kind):
     Ch = BondTensor(info["space"], unpack_blocks(Cb, key=lambda lab: lab[0]))
     rec = T2.contract_two_site(mul_right(ALh, Ch), ARh)
     assert max_block_err(rec.blocks, y.blocks) < 1e-12
+
+
+def test_idmrg2_then_vumps_reproduces_reference_golden(ctx):
+    """The reference's schedule (HF:1010 IDMRG2 with truncbelow(1e-2), then HF:1025-1027 VUMPS) on the
+    device, from the same random initial state as the oracle: bond spaces identical, Schmidt values
+    and energy per site equal to the oracle's, energy equal to the reference's hard-coded golden
+    (test/OB.jl:44, U=5, P/Q=1: -0.48460447) to its printed digits."""
+    import json
+    import os
+    from oracle import mps as M
+    from oracle.hubbard import OB_Sim, mpo
+    from oracle.spaces import initial_bond_spaces
+    from util import DevUniform
+    kind = S.SU2U1
+    Ws, P, _ = mpo(OB_Sim(t=[1.0], u=[5.0]))
+    sp = M.trim_spaces(kind, initial_bond_spaces(kind, [P, P], 1, 50), [P, P])
+    st0 = M.random_state(kind, sp, [P, P], np.random.default_rng(1))
+    ALo, Co, ARo, eps_o, log_o = T2.idmrg2(st0, Ws, cut=1e-2, tol=1e-6, maxiter=60)
+    du = DevUniform(ctx, kind, st0, Ws)
+    AL, AR, Cs, AC, info = dev.idmrg2(ctx, du.AL, du.AR, du.C, du.AC, du.W, cut=1e-2, tol=1e-6, maxiter=60)
+    assert info["converged"] and abs(info["iterations"] - len(log_o)) <= 1
+    for i in range(2):
+        V = Cs[i].space(0, kind)
+        assert V.sectors == Co[i].V.sectors and V.mult == Co[i].V.mult        # same truncated bond spaces
+        assert max_block_err(unpack_blocks(Cs[i], key=lambda lab: lab[0]), Co[i].blocks) < 1e-6
+    # gauge-fix and polish with VUMPS on the grown spaces, both sides
+    sto = T2.idmrg2_to_uniform(ALo, Co)
+    sto, envs, eps, _ = M.vumps(sto, Ws, tol=1e-8, maxiter=60)
+    dev.mixed_gauge(ctx, AL, Cs[1], AR, Cs, AC)
+    V = [Cs[i].space(0, kind) for i in range(2)]
+    chi = len(Ws[0].Ml)
+    GL = [dev.Tensor.env(ctx, 0, V[i - 1], du.M, identity_level=0) for i in range(2)]
+    GR = [dev.Tensor.env(ctx, 1, V[i], du.M, identity_level=chi - 1) for i in range(2)]
+    res = dev.vumps(ctx, AL, AR, Cs, AC, du.W, GL, GR, tol=1e-8, maxiter=60)
+    assert res["converged"]
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_energies.json")))
+    g = [r for r in gold["reference"] if r["u"] == [5.0]][0]
+    assert abs(res["energy_per_site"] - envs.energy_per_site) < 1e-9
+    assert abs(res["energy_per_site"] - g["E"]) < 5e-8, (res["energy_per_site"], g["E"])

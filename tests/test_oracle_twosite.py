@@ -1,0 +1,58 @@
+"""Oracle pins for the two-site path (no GPU): H_AC2 == dense expansion, truncated SVD, and the
+reference's full schedule (HF:1010 IDMRG2 truncbelow(10^-svalue) -> HF:1025-1027 VUMPS) reproducing
+the reference's hard-coded energies (tests/golden/reference_energies.json) to their printed digits."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mps as M
+from oracle import sectors as S
+from oracle import twosite as T2
+from oracle.hubbard import OB_Sim, mpo
+from oracle.spaces import initial_bond_spaces, physical_space, synthetic_bond_space
+from oracle.tensors import EnvTensor, Legs, MPOTensor
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_energies.json")))
+LEVELS = {S.SU2U1: [(0, 0, 0), (1, 1, 1), (1, 1, -1), (0, 2, 0), (0, 0, 0)],
+          S.U1U1: [(0, 0, 0), (1, 1, 1), (1, -1, -1), (0, 2, 0), (0, 0, 0)]}
+
+
+@pytest.mark.parametrize("kind", [S.SU2U1, S.U1U1])
+def test_heff_ac2_equals_dense_and_tsvd_reconstructs(kind):
+    rng = np.random.default_rng(4)
+    P = physical_space(kind, 1, 1)
+    Va, Vb = synthetic_bond_space(kind, 10, 0), synthetic_bond_space(kind, 10, 0)
+    Mleg = Legs(kind, LEVELS[kind])
+    GL = EnvTensor("L", Va, Mleg, identity_levels=[0]).randomize(rng)
+    GR = EnvTensor("R", Vb, Mleg, identity_levels=[4]).randomize(rng)
+    W1, W2 = MPOTensor(Mleg, P, Mleg).randomize(rng), MPOTensor(Mleg, P, Mleg).randomize(rng)
+    x = T2.TwoSiteTensor(Va, P, P, Vb).randomize(rng)
+    y = T2.HeffAC2Plan(GL, W1, W2, GR, x).apply(x)
+    yd = T2.heff_ac2_apply_dense(GL, W1, W2, GR, x)
+    assert np.abs(y.to_dense() - yd).max() < 1e-11 * np.abs(yd).max()
+    AL, C, AR, info = T2.tsvd(x, 0.0)
+    rec = T2.contract_two_site(M.mul_right(AL, C), AR)
+    assert max(np.abs(rec.blocks[k] - x.blocks[k]).max() for k in x.keys) < 1e-12
+    Qd, Rd = AL.to_dense(), AR.to_dense()
+    assert np.abs(np.einsum("lsr,lsq->rq", Qd, Qd) - np.eye(Qd.shape[2])).max() < 1e-12
+    assert np.abs(np.einsum("lsr,msr->lm", Rd, Rd) - np.eye(Rd.shape[0])).max() < 1e-12
+    # truncation keeps the largest Schmidt values, discarded weight is what was cut
+    AL2, C2, AR2, info2 = T2.tsvd(x, 0.0, maxdim=info["kept"] // 2)
+    assert info2["kept"] == info["kept"] // 2 and 0 < info2["discarded_weight"] < 1
+
+
+@pytest.mark.parametrize("u", [0.0, 5.0])
+def test_reference_schedule_reproduces_golden_energy(u):
+    """IDMRG2 (Schmidt cut 1e-2 = svalue 2.0 of test/OB.jl:23,46) from the HF:917-959 initial spaces,
+    then VUMPS: E/site equals the value hard-coded in the reference's tests to 1e-6 (their atol: 1e-2)."""
+    g = [r for r in GOLD["reference"] if r["u"] == [u] and not r["spin"]][0]
+    kind = S.SU2U1
+    Ws, P, _ = mpo(OB_Sim(t=[1.0], u=[u]))
+    sp = M.trim_spaces(kind, initial_bond_spaces(kind, [P, P], 1, 50), [P, P])
+    st = M.random_state(kind, sp, [P, P], np.random.default_rng(1))
+    AL, C, AR, eps, log = T2.idmrg2(st, Ws, cut=1e-2, tol=1e-6, maxiter=60)
+    assert eps < 1e-6
+    st2, envs, eps2, _ = M.vumps(T2.idmrg2_to_uniform(AL, C), Ws, tol=1e-6, maxiter=80)
+    assert abs(envs.energy_per_site - g["E"]) < 1e-6, (g["cite"], envs.energy_per_site, g["E"])
