@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "htn_internal.hpp"
 
@@ -42,12 +43,19 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // grouped GEMM
 // ------------------------------------------------------------------------------------
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int NCONS_WARPS = 4, NPROD_WARPS = 1;
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NTHREADS = (NCONS_WARPS + NPROD_WARPS) * 32;
-constexpr int LDAS = BK + 4;  // 20 doubles: (g*20 + t) mod 16 distinct over a half warp
-constexpr int LDBS = BN + 4;  // 68 doubles: (t*68 + g) mod 16 distinct over a half warp
+// Shared-memory tiles are UNPADDED and XOR-swizzled in units of 4 doubles (32 B):
+//   A chunk [64 rows][16 k]:  element (row, k)   at row * 16 + (k   ^ ((row  & 3) << 2))
+//   B chunk [16 k][64 cols]:  element (krow, c)  at krow * 64 + (c   ^ ((krow & 3) << 2))
+// so that the 16 lanes of a half warp (4 rows x 4 k, or 4 k x 4 cols) hit 16 distinct doubles of one
+// 128-byte line for every DMMA fragment load, and the 16-byte cp.async stores stay aligned.  Without
+// padding a stage is 16 KB, which lets 4 stages x 3 CTAs fit one SM (a 3-stage ring starved the
+// consumers ~22 % of the time: profiles/r1b_*).
+constexpr int LDAS = BK;
+constexpr int LDBS = BN;
 constexpr int A_STAGE = BM * LDAS;
 constexpr int B_STAGE = BK * LDBS;
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double) + 2 * STAGES * 8 + STAGES * 4 + 64;
@@ -84,15 +92,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 //   layout 0 (LAY_A): flex = M (rows), fixed = N: role w owns col atoms 2w, 2w+1
 //   layout 1 (LAY_B): flex = N (cols), fixed = M: role w owns row atoms 2w, 2w+1
 // acc[flex atom][fixed atom f][2 values of the DMMA C fragment].
+// per-lane fragment addressing (see the swizzle comment above)
+struct FragAddr {
+  int a_base;    // A: row part + t
+  int koff[4];   // A: swizzled k offset of k4-step kk
+  int b_even;    // B: krow t, swizzled column base for even 8-column atoms
+  int b_odd;     //    ... for odd atoms
+};
+
 template <int FLEX, bool LAYB>
 __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __restrict__ as,
-                                       const double* __restrict__ bs, int kk) {
+                                       const double* __restrict__ bs, const FragAddr& fa, int kk) {
   double fx[FLEX], ff[2];
+  const double* ap = as + fa.a_base + fa.koff[kk];
+  const double* bp = bs + kk * 4 * LDBS;
   if (!LAYB) {
 #pragma unroll
-    for (int i = 0; i < FLEX; ++i) fx[i] = as[i * 8 * LDAS + kk * 4];
-    ff[0] = bs[kk * 4 * LDBS];
-    ff[1] = bs[kk * 4 * LDBS + 8];
+    for (int i = 0; i < FLEX; ++i) fx[i] = ap[i * 8 * LDAS];
+    ff[0] = bp[fa.b_even];
+    ff[1] = bp[fa.b_odd + 8];
 #pragma unroll
     for (int i = 0; i < FLEX; ++i) {
       dmma884(acc[i][0][0], acc[i][0][1], fx[i], ff[0]);
@@ -100,9 +118,9 @@ __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __r
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < FLEX; ++j) fx[j] = bs[kk * 4 * LDBS + j * 8];
-    ff[0] = as[kk * 4];
-    ff[1] = as[8 * LDAS + kk * 4];
+    for (int j = 0; j < FLEX; ++j) fx[j] = bp[((j & 1) ? fa.b_odd : fa.b_even) + j * 8];
+    ff[0] = ap[0];
+    ff[1] = ap[8 * LDAS];
 #pragma unroll
     for (int j = 0; j < FLEX; ++j) {
       dmma884(acc[j][0][0], acc[j][0][1], ff[0], fx[j]);
@@ -113,13 +131,13 @@ __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __r
 
 template <int FLEX, bool LAYB>
 __device__ __forceinline__ void mma_chunk(double (&acc)[8][2][2], const double* __restrict__ as,
-                                          const double* __restrict__ bs, int nk4) {
+                                          const double* __restrict__ bs, const FragAddr& fa, int nk4) {
   if (nk4 == BK / 4) {
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, kk);
+    for (int kk = 0; kk < BK / 4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, fa, kk);
   } else {
-#pragma unroll 1
-    for (int kk = 0; kk < nk4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, kk);
+    for (int kk = 0; kk < BK / 4; ++kk)
+      if (kk < nk4) mma_k4<FLEX, LAYB>(acc, as, bs, fa, kk);
   }
 }
 
@@ -142,12 +160,20 @@ struct Ring {
 // Consumer side of one work item, fully specialised on the tile shape: waits for the staged
 // chunks, issues the DMMAs, releases the stages, then stores the accumulators.
 template <int FLEX, bool LAYB>
-__device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int role, int lane, const Bases& bases) {
+__device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int role, int lane, const Bases& bases,
+                                             int dbg) {
   const int g = lane >> 2, t = lane & 3;
   const int mt = item.mt, nt = item.nt;
   const bool active = role * 16 < (LAYB ? mt : nt);  // warp-uniform: this strip holds data
-  const int a_role = (LAYB ? role * 16 * LDAS : 0) + g * LDAS + t;
-  const int b_role = (LAYB ? 0 : role * 16) + t * LDBS + g;
+  FragAddr fa;
+  fa.a_base = (LAYB ? role * 16 * LDAS : 0) + g * LDAS + t;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) fa.koff[kk] = (kk ^ (g & 3)) << 2;
+  {
+    const int bsw = (t & 2) << 2, gsw = g ^ ((t & 1) << 2), cbase = LAYB ? 0 : role * 16;
+    fa.b_even = t * LDBS + cbase + bsw + gsw;
+    fa.b_odd = t * LDBS + cbase - bsw + gsw;
+  }
 
   double acc[8][2][2];
 #pragma unroll
@@ -157,9 +183,14 @@ __device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
     mbar_wait(&rg.full[rg.stage], rg.phase);
-    if (active) {
+    if (active && !(dbg & 1)) {  // timing experiment HTN_GEMM_DEBUG=1: no DMMA
+#ifdef HTN_FULLCHUNK
+      // K tails are zero-filled by the producer: always run the full chunk (no meta read / branch)
+      mma_chunk<FLEX, LAYB>(acc, rg.As + rg.stage * A_STAGE, rg.Bs + rg.stage * B_STAGE, fa, BK / 4);
+#else
       const int nk4 = rg.meta[rg.stage];
-      mma_chunk<FLEX, LAYB>(acc, rg.As + rg.stage * A_STAGE + a_role, rg.Bs + rg.stage * B_STAGE + b_role, nk4);
+      mma_chunk<FLEX, LAYB>(acc, rg.As + rg.stage * A_STAGE, rg.Bs + rg.stage * B_STAGE, fa, nk4);
+#endif
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rg.empty[rg.stage]);
@@ -200,22 +231,22 @@ __device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int
 
 template <bool LAYB>
 __device__ __forceinline__ void consume_dispatch(int flex, const GemmItem& item, Ring& rg, int role, int lane,
-                                                 const Bases& bases) {
+                                                 const Bases& bases, int dbg) {
   switch (flex) {
-    case 1: consume_item<1, LAYB>(item, rg, role, lane, bases); break;
-    case 2: consume_item<2, LAYB>(item, rg, role, lane, bases); break;
-    case 3: consume_item<3, LAYB>(item, rg, role, lane, bases); break;
-    case 4: consume_item<4, LAYB>(item, rg, role, lane, bases); break;
-    case 5: consume_item<5, LAYB>(item, rg, role, lane, bases); break;
-    case 6: consume_item<6, LAYB>(item, rg, role, lane, bases); break;
-    case 7: consume_item<7, LAYB>(item, rg, role, lane, bases); break;
-    default: consume_item<8, LAYB>(item, rg, role, lane, bases); break;
+    case 1: consume_item<1, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 2: consume_item<2, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 3: consume_item<3, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 4: consume_item<4, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 5: consume_item<5, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 6: consume_item<6, LAYB>(item, rg, role, lane, bases, dbg); break;
+    case 7: consume_item<7, LAYB>(item, rg, role, lane, bases, dbg); break;
+    default: consume_item<8, LAYB>(item, rg, role, lane, bases, dbg); break;
   }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 3)
 grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
-                    const __grid_constant__ Bases bases) {
+                    const __grid_constant__ Bases bases, int dbg, int nsm) {
   extern __shared__ __align__(16) double smem[];
   Ring rg;
   rg.As = smem;
@@ -237,13 +268,28 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
   }
   __syncthreads();
   if (blockIdx.x >= nitems) return;
+  // Item order of this CTA.  Items are sorted by cost and dealt round-robin, so every CTA owns a
+  // similar mix; the CTAs that share an SM (blockIdx = sm, sm + nsm, sm + 2 nsm) walk their lists in
+  // different orders (forward / backward / from the middle) so that their load, DMMA and store phases
+  // do not run in lockstep.
+  const int n_mine = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int wave = (dbg & 4) ? 0 : ((int)blockIdx.x / nsm) % 3;
+  auto item_index = [&](int j) {
+    int k = j;
+    if (wave == 1) k = n_mine - 1 - j;
+    if (wave == 2) {
+      k = j + n_mine / 2;
+      if (k >= n_mine) k -= n_mine;
+    }
+    return (int)blockIdx.x + k * (int)gridDim.x;
+  };
 
   if (warp >= NCONS_WARPS) {
     // =========================== PRODUCER (one warp) ================================
-    int it = blockIdx.x;
+    int it = item_index(0);
     GemmItem item = items[it];
-    while (true) {
-      const int itn = it + gridDim.x;
+    for (int j = 0; j < n_mine; ++j) {
+      const int itn = j + 1 < n_mine ? item_index(j + 1) : nitems;
       GemmItem next_item = item;
       if (itn < nitems) next_item = items[itn];  // prefetch: consumed at the next iteration
       const int mt = item.mt, nt = item.nt;
@@ -259,6 +305,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           mbar_wait(&rg.empty[rg.stage], rg.phase ^ 1u);
           double* as = rg.As + rg.stage * A_STAGE;
           double* bs = rg.Bs + rg.stage * B_STAGE;
+          if (!(dbg & 2)) {  // timing experiment HTN_GEMM_DEBUG=2: no operand loads
           // ---- B operand: 16 x 64 chunk: lane = 16-byte segment of a row, q = row ---------
           // (columns >= nt feed only discarded outputs: loaded only up to the tile extent)
           {
@@ -266,22 +313,28 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
             bytes_row = bytes_row < 0 ? 0 : (bytes_row > 16 ? 16 : bytes_row);
             const char* src = reinterpret_cast<const char*>(Bg + (long long)k0 * sg.ldb + lane * 2);
             const long long step = (long long)sg.ldb * 8;
-            double* dst = bs + lane * 2;
+            // swizzled destination of this lane's 16-byte segment in k-row q: (2 lane) ^ ((q & 3) << 2)
+            double* dst0 = bs + ((lane * 2) ^ 0);
+            double* dst1 = bs + ((lane * 2) ^ 4);
+            double* dst2 = bs + ((lane * 2) ^ 8);
+            double* dst3 = bs + ((lane * 2) ^ 12);
+#define HTN_BDST(q) (((q) & 3) == 0 ? dst0 : ((q) & 3) == 1 ? dst1 : ((q) & 3) == 2 ? dst2 : dst3) + (q) * LDBS
             if (k0 + BK <= K) {
               if (bytes_row == 16) {
 #pragma unroll
-                for (int q = 0; q < BK; ++q) cp_async16(dst + q * LDBS, src + q * step, 16);
+                for (int q = 0; q < BK; ++q) cp_async16(HTN_BDST(q), src + q * step, 16);
               } else if (bytes_row > 0) {
 #pragma unroll
-                for (int q = 0; q < BK; ++q) cp_async16(dst + q * LDBS, src + q * step, bytes_row);
+                for (int q = 0; q < BK; ++q) cp_async16(HTN_BDST(q), src + q * step, bytes_row);
               }
             } else {  // K tail: rows >= K must be zero (they meet the zero-filled A columns)
 #pragma unroll
               for (int q = 0; q < BK; ++q) {
                 const int bytes = (k0 + q < K) ? bytes_row : 0;
-                cp_async16(dst + q * LDBS, bytes ? src + q * step : reinterpret_cast<const char*>(Bg), bytes);
+                cp_async16(HTN_BDST(q), bytes ? src + q * step : reinterpret_cast<const char*>(Bg), bytes);
               }
             }
+#undef HTN_BDST
           }
           const int arow = lane >> 3, aseg = lane & 7;  // A: 4 rows x 8 segments per pass
           {
@@ -290,7 +343,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
           const char* src = reinterpret_cast<const char*>(Ag + (long long)arow * sg.lda + k0 + aseg * 2);
           const long long step = (long long)sg.lda * 32;  // 4 rows
-          double* dst = as + arow * LDAS + aseg * 2;
+          double* dst = as + arow * LDAS + ((aseg * 2) ^ (arow << 2));  // rows q*4+arow: (row & 3) == arow
           const int nq = (mt - arow + 3) >> 2;  // rows q*4+arow < mt
           if (nq == BM / 4) {
 #pragma unroll
@@ -303,6 +356,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
                 cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
           }
           }
+          }
           if (lane == 0) {
             int krem = K - k0;
             rg.meta[rg.stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
@@ -313,26 +367,24 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
         }
         sg = sg_next;
       }
-      if (itn >= nitems) break;
       it = itn;
       item = next_item;
     }
   } else {
     // =========================== CONSUMERS (four warps) =============================
-    int it = blockIdx.x;
+    int it = item_index(0);
     GemmItem item = items[it];
-    while (true) {
-      const int itn = it + gridDim.x;
+    for (int j = 0; j < n_mine; ++j) {
+      const int itn = j + 1 < n_mine ? item_index(j + 1) : nitems;
       GemmItem next_item = item;
       if (itn < nitems) next_item = items[itn];
       // rotate the strip a warp owns from item to item so that partially filled strips do not
       // always land on the same SM sub-partition
       const int role = (warp + it) & 3;
       if (item.layout != 0)
-        consume_dispatch<true>((item.nt + 7) >> 3, item, rg, role, lane, bases);
+        consume_dispatch<true>((item.nt + 7) >> 3, item, rg, role, lane, bases, dbg);
       else
-        consume_dispatch<false>((item.mt + 7) >> 3, item, rg, role, lane, bases);
-      if (itn >= nitems) break;
+        consume_dispatch<false>((item.mt + 7) >> 3, item, rg, role, lane, bases, dbg);
       it = itn;
       item = next_item;
     }
@@ -357,7 +409,19 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const B
     cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
     attr = true;
   }
-  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("HTN_GEMM_DEBUG");  // timing experiments only (results are wrong when set)
+    dbg = e ? atoi(e) : 0;
+  }
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases, dbg, nsm);
 }
 
 // ------------------------------------------------------------------------------------

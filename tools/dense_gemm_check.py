@@ -7,7 +7,7 @@ from hubbardtn_b200 import device, sectors as S, synthetic
 ctx = device.Context(0)
 peak = ctx.probe_fp64_peak(0)
 print("DMMA peak %.2f TF/s" % peak)
-for n, chi in [(1024, 6), (512, 10), (256, 18), (168, 30), (167, 30), (128, 40), (64, 80), (56, 80)]:
+for n, chi in [(2048, 7), (1024, 13), (512, 25), (192, 97), (167, 97), (128, 97)]:
     spaces = ({(0, 0, 0): n}, {(0, 0, 0): n}, [(0, 0, 0)], [(0, 0, 0)] * chi)
     case = synthetic.HeffCase(ctx, S.U1U1, D=n, chi=chi, spaces=spaces)
     st = case.plan.stats
