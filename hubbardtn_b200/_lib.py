@@ -84,6 +84,8 @@ SIGNATURES = {
     "htn_tensor_upload": (_i32, [_p, _p, _i64]),
     "htn_tensor_download": (_i32, [_p, _p, _i64]),
     "htn_mpo_create": (_i32, [_p, _p, _p, _p, _i32, _pi32, _pi32, _pd, _pp]),
+    "htn_mpo_create_dense": (_i32, [_p, _p, _p, _p, _pd, C.c_double, _pp]),
+    "htn_mpo_entries": (_i32, [_p, _pi32, _pi32, _pi32, _pd]),
     "htn_mpo_destroy": (_i32, [_p]),
     "htn_plan_heff_ac": (_i32, [_p, _p, _p, _p, _p, _pp]),
     "htn_plan_heff_c": (_i32, [_p, _p, _p, _p, _pp]),

@@ -1,5 +1,6 @@
 // C-ABI entry points: context, spaces, tensors, MPO, vector algebra (see include/htn.h).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -154,8 +155,9 @@ int32_t htn_space_info(const htn_space* s, int32_t* nsec, int32_t* labels, int32
 }
 
 int32_t htn_legs_create(htn_ctx* ctx, int32_t sym, int32_t n, const int32_t* labels, htn_legs** out) {
-  if (!ctx || !out || n < 0 || (n > 0 && !labels)) return HTN_ERR_INVALID;
-  if (sym != HTN_SYM_SU2U1 && sym != HTN_SYM_U1U1) return ctx->fail(HTN_ERR_INVALID, "unknown symmetry kind");
+  // host-only object: ctx may be NULL (used by the CPU-side tests of the MPO projection)
+  if (!out || n < 0 || (n > 0 && !labels)) return HTN_ERR_INVALID;
+  if (sym != HTN_SYM_SU2U1 && sym != HTN_SYM_U1U1) return HTN_ERR_INVALID;
   HTN_TRY
   htn_legs* l = new htn_legs();
   l->ctx = ctx;
@@ -623,6 +625,109 @@ int32_t htn_mpo_create(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, cons
   *out = w;
   return HTN_OK;
   HTN_CATCH(ctx)
+}
+
+// Wigner-Eckart projection of an invariant dense MPO tensor onto its reduced entries.
+// dense[a m_a][s' m'][s m][b m_b], row-major, every multiplet expanded with m = -j .. +j.
+int32_t htn_mpo_create_dense(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, const htn_legs* Mr,
+                             const double* dense, double tol, htn_mpo** out) {
+  // host-only: ctx may be NULL
+  if (!Ml || !P || !Mr || !dense || !out) return HTN_ERR_INVALID;
+  if (Ml->sym != P->sym || Mr->sym != P->sym) return HTN_ERR_INVALID;
+  HTN_TRY
+  const int sym = P->sym;
+  auto offsets = [&](const htn_legs* L, std::vector<int>& off) {
+    int acc = 0;
+    for (const Sector& s : L->sec) {
+      off.push_back(acc);
+      acc += sdim(sym, s);
+    }
+    return acc;
+  };
+  std::vector<int> ol, op, orr;
+  const int Dl = offsets(Ml, ol), d = offsets(P, op), Dr = offsets(Mr, orr);
+  auto at = [&](int a, int sp, int s, int b) -> double { return dense[(((int64_t)a * d + sp) * d + s) * Dr + b]; };
+  // coupling coefficient <a ma; b mb | c mc> with state index i <-> m = -j + i (abelian: 1)
+  auto cg = [&](Sector A, int ia, Sector B, int ib, Sector Cc, int ic) -> double {
+    if (sym != HTN_SYM_SU2U1) return 1.0;
+    return cg_su2(A.q, -A.q + 2 * ia, B.q, -B.q + 2 * ib, Cc.q, -Cc.q + 2 * ic);
+  };
+  std::vector<MpoEntry> entries;
+  std::vector<double> rec((size_t)Dl * d * d * Dr, 0.0);
+  for (int a = 0; a < (int)Ml->sec.size(); ++a)
+    for (int sp = 0; sp < (int)P->sec.size(); ++sp) {
+      const Sector ca = Ml->sec[a], csp = P->sec[sp];
+      const int p2 = (ca.p + csp.p) & 1, n2 = ca.n + csp.n;
+      const int qlo = sym == HTN_SYM_SU2U1 ? std::abs(ca.q - csp.q) : ca.q + csp.q, qhi = ca.q + csp.q;
+      for (int q = qlo; q <= qhi; q += 2) {
+        const Sector c{p2, q, n2};
+        const int dc = sdim(sym, c);
+        for (int s = 0; s < (int)P->sec.size(); ++s)
+          for (int b = 0; b < (int)Mr->sec.size(); ++b) {
+            const Sector cs = P->sec[s], cb = Mr->sec[b];
+            if (!allowed(sym, cs, cb, c)) continue;
+            const int da = sdim(sym, ca), dsp = sdim(sym, csp), ds = sdim(sym, cs), db = sdim(sym, cb);
+            double w = 0.0;
+            for (int x = 0; x < da; ++x)
+              for (int y = 0; y < dsp; ++y)
+                for (int z = 0; z < ds; ++z)
+                  for (int v = 0; v < db; ++v) {
+                    const double val = at(ol[a] + x, op[sp] + y, op[s] + z, orr[b] + v);
+                    if (val == 0.0) continue;
+                    for (int mc = 0; mc < dc; ++mc) w += val * cg(ca, x, csp, y, c, mc) * cg(cs, z, cb, v, c, mc);
+                  }
+            w /= dc;
+            if (std::fabs(w) <= tol) continue;
+            entries.push_back(MpoEntry{a, sp, s, b, c, w});
+            for (int x = 0; x < da; ++x)
+              for (int y = 0; y < dsp; ++y)
+                for (int z = 0; z < ds; ++z)
+                  for (int v = 0; v < db; ++v) {
+                    double g = 0.0;
+                    for (int mc = 0; mc < dc; ++mc) g += cg(ca, x, csp, y, c, mc) * cg(cs, z, cb, v, c, mc);
+                    rec[((((int64_t)(ol[a] + x)) * d + op[sp] + y) * d + op[s] + z) * Dr + orr[b] + v] += w * g;
+                  }
+          }
+      }
+    }
+  double err = 0.0;
+  for (size_t i = 0; i < rec.size(); ++i) err = std::max(err, std::fabs(rec[i] - dense[i]));
+  if (err > 1e-10) {
+    const char* msg = "mpo_create_dense: tensor is not invariant under the symmetry (re-expansion mismatch)";
+    if (ctx) ctx->err = msg; else g_noctx_err = msg;
+    return HTN_ERR_INVALID;
+  }
+  htn_mpo* w = new htn_mpo();
+  w->ctx = ctx;
+  w->sym = sym;
+  w->Ml = *Ml;
+  w->P = *P;
+  w->Mr = *Mr;
+  w->entries = entries;
+  *out = w;
+  return HTN_OK;
+  HTN_CATCH(ctx)
+}
+
+int32_t htn_mpo_entries(const htn_mpo* w, int32_t* nnz, int32_t* idx, int32_t* clabel, double* val) {
+  if (!w) return HTN_ERR_INVALID;
+  if (nnz) *nnz = (int32_t)w->entries.size();
+  for (size_t i = 0; i < w->entries.size(); ++i) {
+    const MpoEntry& e = w->entries[i];
+    if (idx) {
+      idx[4 * i] = e.a;
+      idx[4 * i + 1] = e.sp;
+      idx[4 * i + 2] = e.s;
+      idx[4 * i + 3] = e.b;
+    }
+    if (clabel) {
+      clabel[3 * i] = e.c.p;
+      clabel[3 * i + 1] = e.c.q;
+      clabel[3 * i + 2] = e.c.n;
+    }
+    if (val) val[i] = e.w;
+  }
+  return HTN_OK;
 }
 
 int32_t htn_mpo_destroy(htn_mpo* w) {

@@ -91,7 +91,9 @@ class Legs:
         self.sectors = [tuple(int(v) for v in s) for s in sectors]
         lab, plab = _i32arr(np.array(self.sectors, dtype=np.int32).reshape(-1, 3))
         h = C.c_void_p()
-        L.check(lib.htn_legs_create(ctx.h, sym, len(self.sectors), plab, C.byref(h)), ctx.h)
+        # ctx may be None: legs are host-only objects (used by the device-free MPO projection tests)
+        L.check(lib.htn_legs_create(ctx.h if ctx else None, sym, len(self.sectors), plab, C.byref(h)),
+                ctx.h if ctx else None)
         self.h = h
 
     def __len__(self):
@@ -99,7 +101,7 @@ class Legs:
 
     def __del__(self):
         try:
-            if self.h and self.ctx.h:      # a closed context has already released the device
+            if self.h and (self.ctx is None or self.ctx.h):
                 lib.htn_legs_destroy(self.h)
             self.h = None
         except Exception:
@@ -226,6 +228,35 @@ class Tensor:
 class Mpo:
     """One site of the MPO Hamiltonian in reduced form: entries {(a,s',s,b,c): w}."""
 
+    @staticmethod
+    def from_dense(ctx: Context, Ml: Legs, P: Legs, Mr: Legs, dense: np.ndarray, tol: float = 1e-12) -> "Mpo":
+        """From the dense invariant tensor dense[a,s',s,b] (multiplets expanded, m = -j..+j); the library
+        does the Wigner-Eckart projection and rejects non-invariant input."""
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        h = C.c_void_p()
+        L.check(lib.htn_mpo_create_dense(ctx.h if ctx else None, Ml.h, P.h, Mr.h,
+                                         dense.ctypes.data_as(C.POINTER(C.c_double)), tol, C.byref(h)),
+                ctx.h if ctx else None)
+        self = Mpo.__new__(Mpo)
+        self.ctx, self.Ml, self.P, self.Mr, self.h = ctx, Ml, P, Mr, h
+        n = C.c_int32()
+        L.check(lib.htn_mpo_entries(h, C.byref(n), None, None, None), ctx.h if ctx else None)
+        self.nnz = n.value
+        return self
+
+    def entries(self) -> dict:
+        ch = self.ctx.h if self.ctx else None
+        n = C.c_int32()
+        L.check(lib.htn_mpo_entries(self.h, C.byref(n), None, None, None), ch)
+        idx = np.zeros((n.value, 4), dtype=np.int32)
+        cl = np.zeros((n.value, 3), dtype=np.int32)
+        val = np.zeros(n.value)
+        pi32 = C.POINTER(C.c_int32)
+        L.check(lib.htn_mpo_entries(self.h, C.byref(n), idx.ctypes.data_as(pi32), cl.ctypes.data_as(pi32),
+                                    val.ctypes.data_as(C.POINTER(C.c_double))), ch)
+        return {(int(i[0]), int(i[1]), int(i[2]), int(i[3]), tuple(int(v) for v in c)): float(w)
+                for i, c, w in zip(idx, cl, val)}
+
     def __init__(self, ctx: Context, Ml: Legs, P: Legs, Mr: Legs, entries: dict):
         self.ctx, self.Ml, self.P, self.Mr = ctx, Ml, P, Mr
         keys = list(entries.keys())
@@ -242,7 +273,7 @@ class Mpo:
 
     def __del__(self):
         try:
-            if self.h and self.ctx.h:      # a closed context has already released the device
+            if self.h and (self.ctx is None or self.ctx.h):
                 lib.htn_mpo_destroy(self.h)
             self.h = None
         except Exception:

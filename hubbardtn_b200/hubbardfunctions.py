@@ -1,0 +1,335 @@
+"""Host-side mirror of HubbardTN's public interface for the ground-state path, running on libhtn.
+
+Names, arguments and return conventions follow `src/HubbardFunctions.jl` of the reference so that the
+parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
+
+    OB_Sim(t, u, mu, J, P, Q, svalue, bond_dim, period; kwargs...)      HF:76-93
+    hamiltonian(simul)                                                  HF:386-472 (t, u, mu terms)
+    initialize_mps(H, P, max_dimension, spin)                           HF:917-959
+    compute_groundstate(simul; tol, verbosity, maxiter)                 HF:993-1030
+    produce_groundstate(simul; force)                                   HF:1145-1166 (in-memory cache only)
+    dim_state(psi)                                                      HF:1399-1405
+    density_state(psi)                                                  HF:1475-1542
+
+The reference delegates the numerics to MPSKit; here `compute_groundstate` drives the same schedule
+(IDMRG2 with truncbelow(10^-svalue), then VUMPS) through the C ABI on the GPU.  This module contains
+host bookkeeping only (spaces, the MPO as a finite-state machine, random initial blocks); it never
+touches `oracle/`.  Not mirrored yet: exchange / U13 / staggered-field / helix terms (HF:445-469),
+one-site unit cells (the VUMPS + SvdCut bond-growing loop, HF:1011-1022) and the GradientGrassmann
+polish (HF:1026).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import device as dev
+from . import sectors as S
+
+
+@dataclass
+class OB_Sim:
+    """One-band Hubbard simulation parameters (HF:76-93)."""
+    t: list
+    u: list
+    mu: float = 0.0
+    J: list = field(default_factory=lambda: [0.0])
+    P: int = 1
+    Q: int = 1
+    svalue: float = 2.0
+    bond_dim: int = 50
+    period: int = 0
+    kwargs: dict = field(default_factory=dict)
+
+    @property
+    def spin(self) -> bool:
+        return bool(self.kwargs.get("spin", False))
+
+    @property
+    def sym(self) -> int:
+        return S.U1U1 if self.spin else S.SU2U1
+
+    @property
+    def unit_cell(self) -> int:
+        return self.Q if self.P % 2 == 0 else 2 * self.Q          # HF:408-412
+
+
+# ---------------------------------------------------------------------------------------------------
+# Hamiltonian as a finite-state-machine MPO (dense, multiplet basis) -> reduced form inside libhtn
+# ---------------------------------------------------------------------------------------------------
+def _fermion_ops(sym: int):
+    """(c_up, c_dn, parity, n, n_up n_dn) as 4x4 matrices in the basis of `S.physical_space`:
+    SU2U1: empty, double, single(m=-1/2 = dn, m=+1/2 = up);  U1U1: empty, double, up, dn.
+    |double> = c+_up c+_dn |0>."""
+    cu = np.zeros((4, 4))
+    cd = np.zeros((4, 4))
+    cu[0, 1] = 1.0
+    cu[2, 3] = 1.0
+    cd[0, 2] = 1.0
+    cd[1, 3] = -1.0
+    par = np.diag([1.0, -1.0, -1.0, 1.0])
+    perm = [0, 3, 2, 1] if sym == S.SU2U1 else [0, 3, 1, 2]
+    ix = np.ix_(perm, perm)
+    nup, ndn = cu.T @ cu, cd.T @ cd
+    return cu[ix], cd[ix], par[ix], (nup + ndn)[ix], (nup @ ndn)[ix]
+
+
+def hamiltonian_dense(simul: OB_Sim):
+    """H = sum_i [u1 n_up n_dn - mu n]_i - sum_r t_r sum_i,s (c+_{i,s} c_{i+r,s} + h.c.) + sum_{r>=2} u_r n_i n_{i+r-1}
+    (HF:424-444) as an upper-triangular MPO W[a, s', s, b] with explicit Jordan-Wigner strings.
+    Returns (W dense, level sectors)."""
+    if simul.period != 0 or any(k in simul.kwargs for k in ("U13", "JMs")) or any(abs(j) > 0 for j in simul.J):
+        raise NotImplementedError("exchange / U13 / staggered-field / helix terms (HF:445-469) are not mirrored yet")
+    sym, Q = simul.sym, simul.Q
+    cu, cd, par, num, dbl = _fermion_ops(sym)
+    t, u = list(simul.t), list(simul.u)
+    R, Rn = len(t), max(len(u) - 1, 0)
+    levels = [(0, 0, 0)]
+    first = {}
+
+    def add(name, sectors):
+        first[name] = len(levels)
+        levels.extend(sectors)
+
+    for k in range(1, R + 1):
+        add(("A", k), [(1, 1, Q)] if sym == S.SU2U1 else [(1, -1, Q), (1, 1, Q)])
+    for k in range(1, R + 1):
+        add(("B", k), [(1, 1, -Q)] if sym == S.SU2U1 else [(1, -1, -Q), (1, 1, -Q)])
+    for k in range(1, Rn + 1):
+        add(("N", k), [(0, 0, 0)])
+    levels.append((0, 0, 0))
+    off, acc = [], 0
+    for s in levels:
+        off.append(acc)
+        acc += S.dim(sym, s)
+    Dm, end = acc, off[-1]
+    W = np.zeros((Dm, 4, 4, Dm))
+
+    def lvl(name, m):       # dense index of the doublet member with 2 m = -1 / +1
+        return off[first[name]] + (0 if m < 0 else 1)
+
+    W[0, :, :, 0] = np.eye(4)
+    W[end, :, :, end] = np.eye(4)
+    W[0, :, :, end] = (u[0] if u else 0.0) * dbl - simul.mu * num
+    cdag, cann = {1: cu.T, -1: cd.T}, {1: cu, -1: cd}
+    for k in range(1, R + 1):
+        for m in (-1, 1):
+            a = lvl(("A", k), m)                    # c+_{i,s} P ... P c_{j,s}
+            if k == 1:
+                W[0, :, :, a] = cdag[m] @ par
+            else:
+                W[lvl(("A", k - 1), m), :, :, a] = par
+            W[a, :, :, end] = -t[k - 1] * cann[m]
+            b = lvl(("B", k), m)                    # h.c.: the conjugate spinor (c_dn, -c_up)
+            sgn = 1.0 if m > 0 else -1.0
+            if k == 1:
+                W[0, :, :, b] = sgn * (par @ cann[-m])
+            else:
+                W[lvl(("B", k - 1), m), :, :, b] = par
+            W[b, :, :, end] = -t[k - 1] * sgn * cdag[-m]
+    for k in range(1, Rn + 1):
+        n_ = off[first[("N", k)]]
+        if k == 1:
+            W[0, :, :, n_] = num
+        else:
+            W[off[first[("N", k - 1)]], :, :, n_] = np.eye(4)
+        W[n_, :, :, end] = u[k] * num
+    return W, levels
+
+
+class Hamiltonian:
+    """`InfiniteMPOHamiltonian` stand-in: per-site reduced MPO tensors held by libhtn."""
+
+    def __init__(self, ctx, simul: OB_Sim):
+        self.simul, self.sym = simul, simul.sym
+        Wd, self.levels = hamiltonian_dense(simul)
+        self.phys = S.physical_space(self.sym, simul.P, simul.Q)
+        self.P = dev.Legs(ctx, self.sym, self.phys)
+        self.M = dev.Legs(ctx, self.sym, self.levels)
+        W = dev.Mpo.from_dense(ctx, self.M, self.P, self.M, Wd)
+        self.W = [W] * simul.unit_cell
+        self.chi = len(self.levels)
+
+    def __len__(self):
+        return len(self.W)
+
+
+def hamiltonian(simul: OB_Sim, ctx=None) -> Hamiltonian:
+    return Hamiltonian(ctx, simul)
+
+
+# ---------------------------------------------------------------------------------------------------
+# initial state (HF:917-959)
+# ---------------------------------------------------------------------------------------------------
+def _fuse_spaces(sym, a: dict, b: dict) -> dict:
+    out = {}
+    for sa, na in a.items():
+        for sb, nb in b.items():
+            for c in S.fuse(sym, sa, sb):
+                out[c] = out.get(c, 0) + na * nb
+    return out
+
+
+def _dual(sym, s):
+    return (s[0], s[1], -s[2]) if sym == S.SU2U1 else (s[0], -s[1], -s[2])
+
+
+def initial_spaces(sym: int, phys: list, L: int, P: int, max_dimension: int) -> list:
+    """V[i] = right bond of site i: infimum of the spaces fused from the left and (dual) from the right,
+    capped per sector at `max_dimension` inside the window of HF:931-947."""
+    pd = {}
+    for s in phys:
+        pd[s] = pd.get(s, 0) + 1
+    v_right, acc = [], None
+    for _ in range(L):
+        acc = dict(pd) if acc is None else _fuse_spaces(sym, acc, pd)
+        v_right.append(acc)
+    v_l, acc = [], {(0, 0, 0): 1}
+    dual_pd = {_dual(sym, s): n for s, n in pd.items()}
+    for _ in range(L):
+        acc = _fuse_spaces(sym, acc, dual_pd)
+        v_l.append(acc)
+    v_left = list(reversed(v_l))
+    v_left = v_left[1:] + v_left[:1]
+    out = []
+    for i in range(L):
+        v = {s: min(n, v_right[i][s]) for s, n in v_left[i].items() if s in v_right[i]}
+        capped = {}
+        for s, n in v.items():
+            inside = (s[1] <= 6 if sym == S.SU2U1 else abs(s[1]) <= L) and abs(s[2]) <= L * P
+            if inside or s == (0, 0, 0):
+                capped[s] = min(n, max_dimension) if inside else 1
+        out.append({s: n for s, n in capped.items() if n > 0})
+    return _full_rank(sym, out, phys)
+
+
+def _full_rank(sym, spaces, phys):
+    """Shrink multiplicities until every site tensor can be left- and right-isometric."""
+    L = len(spaces)
+    mult = [dict(m) for m in spaces]
+    changed = True
+    while changed:
+        changed = False
+        for i in range(L):
+            vl, vr = mult[i - 1], mult[i]
+            cap_r = {r: 0 for r in vr}
+            cap_l = {l: 0 for l in vl}
+            for l, nl in vl.items():
+                for s in phys:
+                    for r in S.fuse(sym, l, s):
+                        if r in vr:
+                            cap_r[r] += nl
+                            cap_l[l] += vr[r]
+            for r in list(vr):
+                if vr[r] > cap_r[r]:
+                    vr[r], changed = cap_r[r], True
+                if vr[r] == 0:
+                    del vr[r]
+                    changed = True
+            for l in list(vl):
+                if vl[l] > cap_l[l]:
+                    vl[l], changed = cap_l[l], True
+                if vl[l] == 0:
+                    del vl[l]
+                    changed = True
+    return mult
+
+
+class InfiniteMPS:
+    """Uniform MPS in mixed gauge, resident on the device: AL, AR, AC, C (C[i] right of site i)."""
+
+    def __init__(self, ctx, sym, AL, AR, C, AC):
+        self.ctx, self.sym, self.AL, self.AR, self.C, self.AC = ctx, sym, AL, AR, C, AC
+
+    def __len__(self):
+        return len(self.AL)
+
+    def bond_space(self, i):
+        sp = self.C[i].space(0, self.sym)
+        return dict(zip(sp.sectors, sp.mult))
+
+
+def initialize_mps(H: Hamiltonian, P: int, max_dimension: int, spin: bool = False, ctx=None, seed: int = 20261018):
+    """Random uniform MPS on the spaces of HF:917-959, brought to mixed gauge on the device."""
+    sym, L = H.sym, len(H)
+    spaces = initial_spaces(sym, H.phys, L, P, max_dimension)
+    V = [dev.Space(ctx, sym, m) for m in spaces]
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    AL, AR, AC, C = [], [], [], []
+    for i in range(L):
+        a = dev.Tensor.mps(ctx, V[i - 1], H.P, V[i])
+        a.upload(rng.standard_normal(a.nelem))
+        AL.append(a)
+        AR.append(a.like())
+        AC.append(a.like())
+        C.append(dev.Tensor.bond(ctx, V[i]))
+    guess = dev.Tensor.bond(ctx, V[L - 1])
+    g = np.zeros(guess.nelem)
+    for lab, blk in guess.block_views(g).items():
+        blk[...] = np.eye(blk.shape[0]) + 0.1 * rng.standard_normal(blk.shape)
+    guess.upload(g)
+    dev.mixed_gauge(ctx, AL, guess, AR, C, AC, tol=1e-12)
+    return InfiniteMPS(ctx, sym, AL, AR, C, AC)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ground state (HF:993-1030)
+# ---------------------------------------------------------------------------------------------------
+def _make_envs(ctx, psi: InfiniteMPS, H: Hamiltonian):
+    L = len(psi)
+    V = [psi.C[i].space(0, psi.sym) for i in range(L)]
+    GL = [dev.Tensor.env(ctx, 0, V[i - 1], H.M, identity_level=0) for i in range(L)]
+    GR = [dev.Tensor.env(ctx, 1, V[i], H.M, identity_level=H.chi - 1) for i in range(L)]
+    return GL, GR
+
+
+def compute_groundstate(simul: OB_Sim, ctx=None, tol: float = 1e-6, verbosity: int = 0, maxiter: int = 1000,
+                        init_state=None, seed: int = 20261018):
+    """HF:993-1030: IDMRG2(trscheme=truncbelow(10^-svalue), tol) followed by VUMPS(tol, maxiter).
+    Returns the dictionary of HF:1029 with an extra "energy" (per site) and iteration logs."""
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = dev.Context(0)
+    H = hamiltonian(simul, ctx)
+    if len(H) < 2:
+        raise NotImplementedError("one-site unit cells (VUMPS + SvdCut bond growing, HF:1011-1022) are not mirrored yet")
+    psi = init_state if init_state is not None else initialize_mps(H, simul.P, simul.bond_dim, simul.spin, ctx, seed)
+    schmidtcut = 10.0 ** (-simul.svalue)                                   # HF:1007
+    AL, AR, C, AC, info1 = dev.idmrg2(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=schmidtcut, tol=tol,
+                                      maxiter=min(maxiter, 200))           # HF:1010 (MPSKit default maxiter 200)
+    dev.mixed_gauge(ctx, AL, C[-1], AR, C, AC, tol=1e-12)                  # MPSKit: InfiniteMPS(psi.AR) at the end of IDMRG2
+    psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC)
+    GL, GR = _make_envs(ctx, psi, H)
+    info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))  # HF:1025-1027
+    if verbosity > 0:
+        print("IDMRG2: %d iterations, delta %.3e; VUMPS: %d iterations, galerkin %.3e, E/site %.10f"
+              % (info1["iterations"], info1["delta"], info2["iterations"], info2["delta"], info2["energy_per_site"]))
+    return {"groundstate": psi, "environments": (GL, GR), "ham": H, "delta": info2["delta"], "config": simul,
+            "energy": info2["energy_per_site"], "idmrg2": info1, "vumps": info2, "ctx": ctx}
+
+
+_CACHE = {}
+
+
+def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
+    """HF:1145-1166 without the DrWatson/JLD2 disk cache (out of scope): memoised per parameter set."""
+    key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin)
+    if force or key not in _CACHE:
+        _CACHE[key] = compute_groundstate(simul, **kw)
+    return _CACHE[key]
+
+
+def dim_state(psi: InfiniteMPS):
+    """Full (quantum-dimension weighted) bond dimension of every site's left bond (HF:1399-1405)."""
+    out = []
+    for i in range(len(psi)):
+        sp = psi.AL[i].space(0, psi.sym)
+        out.append(sum(S.dim(psi.sym, s) * n for s, n in zip(sp.sectors, sp.mult)))
+    return out
+
+
+def density_state(psi: InfiniteMPS):
+    """<n_i> per site (HF:1495-1542; `expectation_value(psi, i => n)` HF:1507)."""
+    vals = [0.0, 2.0, 1.0] if psi.sym == S.SU2U1 else [0.0, 2.0, 1.0, 1.0]
+    return [dev.expval_diag(psi.AC[i], vals) for i in range(len(psi))]

@@ -128,6 +128,15 @@ int32_t htn_tensor_download(const htn_tensor* t, double* host, int64_t nelem);
 int32_t htn_mpo_create(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, const htn_legs* Mr,
                        int32_t nnz, const int32_t* idx /*[nnz][4]*/, const int32_t* clabel /*[nnz][3]*/,
                        const double* val, htn_mpo** out);
+/* Same from a DENSE invariant tensor dense[a m_a][s' m'][s m][b m_b] (row-major, every multiplet
+ * expanded with m = -j..+j): the library does the Wigner-Eckart projection (entries with |w| <= tol are
+ * dropped) and fails with HTN_ERR_INVALID if the tensor is not invariant.  This is the form in which a
+ * host can hand over `TensorMap` operator data without knowing the library's reduced convention. */
+int32_t htn_mpo_create_dense(htn_ctx* ctx, const htn_legs* Ml, const htn_legs* P, const htn_legs* Mr,
+                             const double* dense, double tol, htn_mpo** out);
+/* reduced entries of an MPO tensor (arrays may be NULL to query nnz) */
+int32_t htn_mpo_entries(const htn_mpo* w, int32_t* nnz, int32_t* idx /*[nnz][4]*/, int32_t* clabel /*[nnz][3]*/,
+                        double* val);
 int32_t htn_mpo_destroy(htn_mpo* w);
 
 /* ---- H_eff -------------------------------------------------------------------------- */
