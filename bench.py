@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--sym", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-groundstate", action="store_true", help="skip the C1 time-to-converge leg")
     return ap.parse_args()
 
 
@@ -143,6 +144,47 @@ def reference_main(args):
 
 
 # ----------------------------------------------------------------------------------------
+# ground state time-to-converge (config C1: one-band Hubbard t=1, U=8, half filling, U1xSU2)
+# ----------------------------------------------------------------------------------------
+LIEB_WU_U8 = -0.3275305343795398      # exact E/site (tests/golden/reference_energies.json)
+
+
+def groundstate_leg(ctx, args):
+    """The reference's schedule (HubbardFunctions.jl:993-1030: IDMRG2 with truncbelow(10^-svalue) then
+    VUMPS) for BASELINE config C1 on the GPU, wall-clock, and -- unless --no-cpu -- the oracle port of
+    the same schedule on the host CPU beside it (numpy, single process; NOT MPSKit)."""
+    from hubbardtn_b200 import hubbardfunctions as hf
+    model = hf.OB_Sim([1.0], [8.0], 0.0, [0.0], 1, 1, 2.0)
+    hf.compute_groundstate(model, ctx=ctx, tol=1e-8)             # warm-up (plans, allocations)
+    t0 = time.perf_counter()
+    d = hf.compute_groundstate(model, ctx=ctx, tol=1e-8)
+    ctx.synchronize()
+    gpu_s = time.perf_counter() - t0
+    out = {
+        "workload": "C1: OB_Sim t=[1] u=[8] P=Q=1 svalue=2.0, U1xSU2; IDMRG2(truncbelow 1e-2, tol 1e-8) -> VUMPS(tol 1e-8)",
+        "gpu_seconds": gpu_s, "energy_per_site": d["energy"], "galerkin": d["delta"],
+        "idmrg2_iterations": d["idmrg2"]["iterations"], "vumps_iterations": d["vumps"]["iterations"],
+        "D_full": hf.dim_state(d["groundstate"]), "energy_above_lieb_wu": d["energy"] - LIEB_WU_U8,
+    }
+    if not args.no_cpu:
+        import numpy as np
+        from oracle import mps as M, sectors as OS, twosite as T2
+        from oracle.hubbard import OB_Sim as OSim, mpo
+        from oracle.spaces import initial_bond_spaces
+        t0 = time.perf_counter()
+        Ws, P, _ = mpo(OSim(t=[1.0], u=[8.0]))
+        sp = M.trim_spaces(OS.SU2U1, initial_bond_spaces(OS.SU2U1, [P, P], 1, 50), [P, P])
+        st = M.random_state(OS.SU2U1, sp, [P, P], np.random.default_rng(1))
+        AL, C, AR, eps, log = T2.idmrg2(st, Ws, cut=1e-2, tol=1e-8, maxiter=200)
+        st2, envs, eps2, log2 = M.vumps(T2.idmrg2_to_uniform(AL, C), Ws, tol=1e-8, maxiter=200)
+        out["cpu_port_seconds"] = time.perf_counter() - t0
+        out["cpu_port_energy_per_site"] = envs.energy_per_site
+        out["cpu_port_note"] = ("oracle restatement (numpy, 1 process, python block loops), not MPSKit/Julia; at this "
+                                "size (D_full ~ 30) both sides are latency-bound, not flop-bound")
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
@@ -211,7 +253,8 @@ def main():
 
     from hubbardtn_b200 import device, synthetic
     ctx = device.Context(local)
-    case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=rank % 4)
+    from hubbardtn_b200 import sharding
+    case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=sharding.site_for_rank(rank, 4))
     plan, x, y = case.plan, case.x, case.y
     st = plan.stats
 
@@ -278,6 +321,21 @@ def main():
     e2e_value = world * args.steps / float(te.item())
     checksum = float(yh.numpy().sum())
 
+    # ---- ncu-measured DRAM traffic of the dominant kernel (committed capture; per launch) --------
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_roofline_inputs.json")) as f:
+            ri = json.load(f)
+        if args.D == 1024 and args.chi == 96 and args.sym == 0:
+            traffic = ri["grouped_gemm_traffic_bytes_per_launch"]
+    except Exception:
+        traffic = None
+
+    # ---- ground-state time-to-converge (BASELINE metric part 2) on config C1, rank 0 only ----------
+    gs = None
+    if rank == 0 and not args.no_groundstate:
+        gs = groundstate_leg(ctx, args)
+
     line = None
     if rank == 0:
         line = {
@@ -295,7 +353,10 @@ def main():
             "stages_ms": prof,
             "roofline": {
                 "bound": "tensor", "kernel": "grouped_gemm_kernel (stage L + stage R launches)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "bytes per launch (mean of the stage-L and stage-R launches), ncu dram__bytes_read+write, "
+                                "profiles/r1_roofline_inputs.json",
+                "algorithmic_flop_per_launch": st["flops"] / 2.0,
                 "peak_source": "measured live on this GPU: max(DMMA.8x8x4 issue loop %.2f, DFMA loop %.2f, cuBLAS "
                                "DGEMM 4096^3 %.2f) TFLOP/s; MEASURED_PEAKS.json has no FP64 entry"
                                % (dmma_peak, dfma_peak, cublas_peak),
@@ -313,6 +374,8 @@ def main():
                       "D=%d spaces, first %d of %d MPO levels, %d applies; scaled by algorithmic flops (%.3g of %.3g)"
                       % (threads, args.D, chi_s, args.chi, nrep, flops_s, st["flops"])}
     if rank == 0:
+        if gs is not None:
+            line["groundstate"] = gs
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

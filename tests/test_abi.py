@@ -49,7 +49,7 @@ def test_network_coefficients_match_oracle():
     phys = [(0, 0, -1), (0, 0, 1), (1, 1, 0)]
     levels = [(0, 0, 0), (1, 1, 1), (1, 1, -1), (0, 2, 0), (0, 0, 2), (0, 2, -2), (0, 4, 0), (1, 3, 1)]
     checked = nonzero = 0
-    for _ in range(4000):
+    for _ in range(600):
         l = (int(rng.integers(0, 2)), int(rng.integers(0, 7)), int(rng.integers(-3, 4)))
         s, sp = phys[rng.integers(0, 3)], phys[rng.integers(0, 3)]
         a, b = levels[rng.integers(0, len(levels))], levels[rng.integers(0, len(levels))]
@@ -62,7 +62,7 @@ def test_network_coefficients_match_oracle():
                         assert abs(got - ref) < 1e-12
                         checked += 1
                         nonzero += ref != 0.0
-    assert checked > 2000 and nonzero > 200
+    assert checked > 300 and nonzero > 30
     # abelian: 1 when every vertex is allowed
     assert device.network_coefficient(1, [(1, 1, 1), (1, 1, 0), (0, 2, 1), (0, 0, 0), (1, 1, 0), (1, 1, 0),
                                           (1, 1, 1), (1, 1, 1), (0, 2, 1)]) == 1.0

@@ -16,7 +16,7 @@ LEVELS = {
 }
 
 
-def _case(kind, D=20, seed=1):
+def _case(kind, D=12, seed=1):
     rng = np.random.default_rng(seed)
     P = physical_space(kind, 1, 1)
     Va, Vb = synthetic_bond_space(kind, D, 0), synthetic_bond_space(kind, D, 1)
