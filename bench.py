@@ -176,7 +176,7 @@ def groundstate_leg(ctx, args):
         sp = M.trim_spaces(OS.SU2U1, initial_bond_spaces(OS.SU2U1, [P, P], 1, 50), [P, P])
         st = M.random_state(OS.SU2U1, sp, [P, P], np.random.default_rng(1))
         AL, C, AR, eps, log = T2.idmrg2(st, Ws, cut=1e-2, tol=1e-8, maxiter=200)
-        st2, envs, eps2, log2 = M.vumps(T2.idmrg2_to_uniform(AL, C), Ws, tol=1e-8, maxiter=200)
+        st2, envs, eps2, log2 = M.vumps(T2.idmrg2_to_uniform(AR, C), Ws, tol=1e-8, maxiter=200)
         out["cpu_port_seconds"] = time.perf_counter() - t0
         out["cpu_port_energy_per_site"] = envs.energy_per_site
         out["cpu_port_note"] = ("oracle restatement (numpy, 1 process, python block loops), not MPSKit/Julia; at this "

@@ -393,25 +393,42 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
   return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
 }
 
-// Turn left isometries AL[i] (e.g. the IDMRG2 result) + a guess for C[n-1] into a consistent uniform
-// MPS in mixed gauge: AL <- Q(AL) (positive QR), then AR, C by the iterated LQ, AC = AL C.
-// AR[i], AC[i] must have the structure of AL[i]; C[i] is a bond tensor on the right space of site i.
+// Gauge-fix site tensors into a consistent uniform MPS in mixed gauge (MPSKit `InfiniteMPS(A...)`).
+//   from_right = 0: AL[i] hold (approximate) left isometries: AL <- Q(AL), then AR, C by the iterated LQ;
+//   from_right = 1: AR[i] hold (approximate) right isometries -- the list whose bond spaces chain after
+//                   an IDMRG2 iteration: AL, C by the iterated QR from AR, then AR, C by the iterated LQ.
+// All of AL[i], AR[i], AC[i] share one block structure; C[i] is a bond tensor on the right space of
+// site i; C_guess lives on the last bond.  AC = AL C on exit.
 int32_t htn_mixed_gauge(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
-                        htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, double tol, int32_t maxiter,
-                        int32_t* iterations) {
+                        htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, int32_t from_right,
+                        double tol, int32_t maxiter, int32_t* iterations) {
   if (!ctx || nsites <= 0 || !AL || !C_guess || !AR || !C || !AC) return HTN_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < nsites; ++i) {
-    htn_tensor* R = nullptr;
-    RC(htn_tensor_create_like(C[i], &R));
-    int32_t rc = t_qr_inplace(AL[i], R);
-    cudaStreamSynchronize(ctx->stream);
-    htn_tensor_destroy(R);
-    RC(rc);
+  int32_t rc = HTN_OK;
+  if (from_right) {
+    int32_t it1 = 0;
+    rc = htn_gauge_left(ctx, nsites, AR, C_guess, AL, C, tol, maxiter, &it1, nullptr);
+    if (rc < 0) return rc;
+  } else {
+    for (int i = 0; i < nsites; ++i) {
+      htn_tensor* R = nullptr;
+      RC(htn_tensor_create_like(C[i], &R));
+      int32_t r2 = t_qr_inplace(AL[i], R);
+      cudaStreamSynchronize(ctx->stream);
+      htn_tensor_destroy(R);
+      RC(r2);
+    }
   }
+  htn_tensor* guess = nullptr;
+  RC(htn_tensor_create_like(C[nsites - 1], &guess));
+  if (from_right)
+    t_copy(C[nsites - 1], guess);
+  else
+    t_copy(C_guess, guess);
   double d = 0;
-  int32_t rc = htn_gauge_right(ctx, nsites, AL, C_guess, AR, C, tol, maxiter, iterations, &d);
+  rc = htn_gauge_right(ctx, nsites, AL, guess, AR, C, tol, maxiter, iterations, &d);
+  htn_tensor_destroy(guess);
   if (rc < 0) return rc;
   for (int i = 0; i < nsites; ++i) {
     htn_tensor* ac = nullptr;

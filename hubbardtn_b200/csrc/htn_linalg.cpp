@@ -443,4 +443,116 @@ int32_t gmres_solve(const htn_tensor* like, const ApplyFn& apply, const double* 
   return converged ? HTN_OK : HTN_NOT_CONVERGED;
 }
 
+// ---- dominant eigenpair of a small real (nonsymmetric) matrix on the host -------------------
+// Plain power iteration (the dominant eigenvalue of a transfer map is real, positive and simple);
+// returns false when the iteration does not settle (e.g. a complex dominant pair in a poor Krylov space).
+static bool small_dominant_eig(int m, const std::vector<double>& H, int ld, double* theta, std::vector<double>& y) {
+  y.assign(m, 0.0);
+  y[0] = 1.0;  // the start vector of the Krylov space carries the largest weight on the fixed point
+  std::vector<double> z(m);
+  double th = 0.0;
+  for (int it = 0; it < 200000; ++it) {
+    double n = 0.0, d = 0.0;
+    for (int i = 0; i < m; ++i) {
+      double sacc = 0.0;
+      for (int j = 0; j < m; ++j) sacc += H[(size_t)i * ld + j] * y[j];
+      z[i] = sacc;
+      n += sacc * sacc;
+      d += sacc * y[i];
+    }
+    n = std::sqrt(n);
+    if (!(n > 0.0)) return false;
+    const double sgn = d < 0.0 ? -1.0 : 1.0;
+    double diff = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double v = sgn * z[i] / n;
+      diff = std::max(diff, std::fabs(v - y[i]));
+      y[i] = v;
+    }
+    th = d;
+    if (diff < 1e-15) {
+      *theta = th;
+      return true;
+    }
+  }
+  *theta = th;
+  return false;
+}
+
+// Dominant eigenvector (largest |lambda|, assumed real and simple: the fixed point of a transfer map) by
+// Arnoldi with CGS2 and explicit restarts (KrylovKit `eigsolve(f, x0, 1, :LM, Arnoldi(krylovdim, tol))`
+// as used by MPSKit's uniform_leftorth!/rightorth!).  x: start vector in, eigenvector (unit norm) out.
+int32_t arnoldi_dominant(const htn_tensor* like, const ApplyFn& apply, double* x, int krylovdim, double tol, int maxiter,
+                         KrylovInfo* info) {
+  htn_ctx* ctx = like->ctx;
+  krylovdim = std::max(2, std::min(krylovdim, 60));
+  const int64_t n = like->dsize;
+  int32_t rc = ensure_krylov(ctx, krylovdim + 2, n, like->nchunks);
+  if (rc) return rc;
+  double* V = ctx->kry_V;
+  double* sc = ctx->kry_scal;
+  double* sh = ctx->kry_scal_host;
+  cudaStream_t st = ctx->stream;
+  cudaMemcpyAsync(V, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if ((rc = t_normalize(like, V))) return rc;
+  int applies = 0;
+  double theta = 0.0, res = 1e300;
+  bool converged = false;
+  for (int restart = 0; restart < maxiter && !converged; ++restart) {
+    const int ldh = krylovdim;
+    std::vector<double> H((size_t)(krylovdim + 1) * krylovdim, 0.0), y;
+    int m = 0;
+    for (int j = 0; j < krylovdim; ++j) {
+      double* w = V + (int64_t)(j + 1) * n;
+      if ((rc = apply(V + (int64_t)j * n, w))) return rc;
+      ++applies;
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
+      launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
+      launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
+      cudaMemcpyAsync(sh, sc, 130 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "arnoldi");
+      for (int i = 0; i <= j; ++i) H[(size_t)i * ldh + j] = sh[S_H + i] + sh[S_H2 + i];
+      const double hn = std::sqrt(std::max(sh[S_BETA], 0.0));
+      H[(size_t)(j + 1) * ldh + j] = hn;
+      m = j + 1;
+      if (hn < 1e-14 || j == krylovdim - 1) {
+        // (no eager evaluation: the small problem is only solved once the space is complete)
+        const bool ok = small_dominant_eig(m, H, ldh, &theta, y);
+        res = ok ? std::fabs(hn * y[m - 1]) : 1e300;
+        break;
+      }
+      launch_scale_dev(w, sc + S_BETA, 2, w, n, st);
+    }
+    if (!(res < 1e299)) {  // the small eigenproblem did not settle: give up, the caller keeps its vector
+      if (info) {
+        info->value = theta;
+        info->residual = res;
+        info->applies = applies;
+        info->converged = 0;
+      }
+      return HTN_NOT_CONVERGED;
+    }
+    for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
+    cudaMemcpyAsync(sc + S_Y, sh + S_Y, m * sizeof(double), cudaMemcpyHostToDevice, st);
+    double* acc = V + (int64_t)m * n;
+    cudaMemsetAsync(acc, 0, n * sizeof(double), st);
+    launch_multiaxpy(V, n, m, sc + S_Y, 1.0, acc, n, st);
+    if ((rc = t_normalize(like, acc))) return rc;
+    cudaMemcpyAsync(V, acc, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaStreamSynchronize(st);
+    converged = res < tol;
+  }
+  cudaMemcpyAsync(x, V, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if ((rc = cuda_rc(ctx, "arnoldi"))) return rc;
+  if (info) {
+    info->value = theta;
+    info->residual = res;
+    info->applies = applies;
+    info->converged = converged ? 1 : 0;
+  }
+  return converged ? HTN_OK : HTN_NOT_CONVERGED;
+}
+
 }  // namespace htn

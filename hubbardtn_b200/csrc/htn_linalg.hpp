@@ -24,6 +24,8 @@ int32_t t_normalize(const htn_tensor* like, double* x);
 int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunks);
 int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const double* x0, double* x_out, int krylovdim,
                        double tol, int maxiter, KrylovInfo* info);
+int32_t arnoldi_dominant(const htn_tensor* like, const ApplyFn& apply, double* x, int krylovdim, double tol, int maxiter,
+                         KrylovInfo* info);
 int32_t gmres_solve(const htn_tensor* like, const ApplyFn& apply, const double* b, double* x, int krylovdim, double tol,
                     int maxiter, KrylovInfo* info);
 

@@ -8,7 +8,10 @@
 // oracle/mps.py (the CPU restatement these drivers are parity-tested against); every tensor stays
 // in HBM, the host only steers the iteration with a few scalars per step.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -49,6 +52,23 @@ static int32_t build_mul_right(htn_ctx* ctx, const htn_tensor* A, const htn_tens
     t.M = b.rows;
     t.N = b.cols;
     t.segs.push_back(GemmSegH{Opnd{0, b.off}, b.ld, Opnd{1, c.off}, c.ld, b.cols});
+    tasks.push_back(std::move(t));
+  }
+  pg->add_gemm(tasks, TAG_L);
+  return pg->finalize(ctx, 3);
+}
+
+// out[l,s,r] = B[l] . A[l,s,r]      slots {A, B(bond on Vl), out}
+static int32_t build_mul_left(htn_ctx* ctx, const htn_tensor* A, const htn_tensor* B, Program* pg) {
+  std::vector<GemmTaskH> tasks;
+  for (const Block& b : A->blocks) {
+    const Block& c = B->blocks[b.lab[0]];
+    GemmTaskH t;
+    t.C = Opnd{2, b.off};
+    t.ldc = b.ld;
+    t.M = b.rows;
+    t.N = b.cols;
+    t.segs.push_back(GemmSegH{Opnd{1, c.off}, c.ld, Opnd{0, b.off}, b.ld, b.rows});
     tasks.push_back(std::move(t));
   }
   pg->add_gemm(tasks, TAG_L);
@@ -248,6 +268,47 @@ struct Uniform {
     return HTN_OK;
   }
 
+  // MPO-free transfer plans on bond tensors (gauge fixing, GMRES operator of the environments)
+  int32_t init_transfers1() {
+    if (!tl1.empty()) return HTN_OK;
+    for (int i = 0; i < L; ++i) {
+      htn_plan* p = nullptr;
+      std::unique_ptr<htn_mpo> id(new htn_mpo());
+      id->ctx = ctx;
+      id->sym = AL[i]->sym;
+      id->Ml.ctx = id->Mr.ctx = ctx;
+      id->Ml.sym = id->Mr.sym = AL[i]->sym;
+      id->Ml.sec.push_back(Sector{0, 0, 0});
+      id->Mr.sec.push_back(Sector{0, 0, 0});
+      id->P = AL[i]->legs;
+      for (int s = 0; s < (int)id->P.sec.size(); ++s) id->entries.push_back(MpoEntry{0, s, s, 0, id->P.sec[s], 1.0});
+      RC(htn_plan_transfer(ctx, HTN_SIDE_LEFT, id.get(), AL[i], ALt[i], C[prev(i)], C[i], &p));
+      own.plans.push_back(p);
+      tl1.push_back(p);
+      RC(htn_plan_transfer(ctx, HTN_SIDE_RIGHT, id.get(), AL[i], ALt[i], C[i], C[prev(i)], &p));
+      own.plans.push_back(p);
+      tr1.push_back(p);
+      idmpo.push_back(std::move(id));
+    }
+    return HTN_OK;
+  }
+
+  // C <- triangular factor with positive diagonal of C (lower = true: LQ, C = L Q; else QR, C = Q R)
+  int32_t triangular_factor(int b, bool lower) {
+    if (lower) {
+      RC(t_transpose(C[b], tB2[b], 0));
+      RC(t_qr_inplace(tB2[b], tB[b]));
+      RC(t_transpose(tB[b], C[b], 0));
+    } else {
+      RC(t_copy(C[b], tB2[b]));
+      RC(t_qr_inplace(tB2[b], tB[b]));
+      RC(t_copy(tB[b], C[b]));
+    }
+    return t_normalize(C[b], C[b]->d);
+  }
+
+  static constexpr int EIG_MINITER = 10;  // MPSKit: plain sweeps first, then Arnoldi-accelerated ones
+
   // AL -> (AR, C): iterated LQ through the unit cell (oracle/mps.py:uniform_rightorth)
   int32_t rightorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
     cudaStream_t st = ctx->stream;
@@ -256,6 +317,35 @@ struct Uniform {
     double delta = 1e300;
     int it = 0;
     for (it = 1; it <= maxiter; ++it) {
+      if (it > EIG_MINITER) {
+        // fixed point of X -> AL X AR^T through the unit cell (AR from the previous sweep), then its L factor
+        RC(init_transfers1());
+        for (int k = 0; k < L; ++k) RC(t_transpose(AR[k], ARt[k], 0));
+        ApplyFn op = [&](const double* X, double* out) -> int32_t {
+          // (the last GEMM stage only writes real columns: land in a tensor whose padding is zero, then
+          //  copy the whole padded range into the Krylov vector, so that flat dot products stay exact)
+          const double* cur = X;
+          for (int k = L - 1; k >= 0; --k) {
+            double* dst = nC[prev(k)]->d;
+            const double* slots[4] = {AL[k]->d, ARt[k]->d, cur, dst};
+            RC(tr1[k]->prog.run(slots));
+            cur = dst;
+          }
+          cudaMemcpyAsync(out, cur, C[L - 1]->dsize * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+          return HTN_OK;
+        };
+        KrylovInfo info;
+        RC(t_copy(C[L - 1], tB3[L - 1]));
+        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-15)), 10, &info);
+        if (rc < 0) return rc;
+        if (getenv("HTN_DEBUG_GAUGE"))
+          fprintf(stderr, "rightorth it %d delta %.3e arnoldi rc %d theta %.12f res %.3e applies %d\n", it, delta, rc,
+                  info.value, info.residual, info.applies);
+        if (rc == HTN_OK) {  // accept the accelerated guess only when the fixed-point solve converged
+          RC(t_copy(tB3[L - 1], C[L - 1]));
+          RC(triangular_factor(L - 1, true));
+        }
+      }
       RC(t_copy(C[L - 1], tB3[L - 1]));  // C_old
       for (int i = L - 1; i >= 0; --i) {
         const int pb = prev(i);
@@ -265,6 +355,62 @@ struct Uniform {
         RC(t_transpose(tB[pb], C[pb], 0));                         // L = Rt^T
         RC(t_normalize(C[pb], C[pb]->d));
         RC(t_transpose(tAt[i], AR[i], 2));                         // AR = Qt^T with the inverse weights
+      }
+      launch_axpby(-1.0, C[L - 1]->d, 1.0, tB3[L - 1]->d, C[L - 1]->dsize, st);
+      double d2 = 0.0;
+      RC(t_dot_host(C[L - 1], tB3[L - 1]->d, tB3[L - 1]->d, &d2));
+      delta = std::sqrt(std::max(d2, 0.0));
+      if (delta < tol) break;
+    }
+    RC(check_qr_status(ctx));
+    if (iters) *iters = std::min(it, maxiter);
+    if (delta_out) *delta_out = delta;
+    return delta < tol ? HTN_OK : HTN_NOT_CONVERGED;
+  }
+
+  // AR -> (AL, C): iterated positive QR through the unit cell (oracle/mps.py:uniform_leftorth)
+  int32_t leftorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
+    cudaStream_t st = ctx->stream;
+    std::vector<Program*> mulL;
+    for (int i = 0; i < L; ++i) {
+      Program* p = own.program();
+      RC(build_mul_left(ctx, AR[i], C[prev(i)], p));
+      mulL.push_back(p);
+    }
+    RC(t_copy(C_guess, C[L - 1]));
+    RC(t_normalize(C[L - 1], C[L - 1]->d));
+    double delta = 1e300;
+    int it = 0;
+    for (it = 1; it <= maxiter; ++it) {
+      if (it > EIG_MINITER) {
+        // fixed point of X -> AL^T X AR through the unit cell (AL from the previous sweep), then its R factor
+        RC(init_transfers1());
+        for (int k = 0; k < L; ++k) RC(t_transpose(AL[k], ALt[k], 0));
+        ApplyFn op = [&](const double* X, double* out) -> int32_t {
+          const double* cur = X;
+          for (int k = 0; k < L; ++k) {
+            double* dst = nC[k]->d;
+            const double* slots[4] = {AR[k]->d, ALt[k]->d, cur, dst};
+            RC(tl1[k]->prog.run(slots));
+            cur = dst;
+          }
+          cudaMemcpyAsync(out, cur, C[L - 1]->dsize * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+          return HTN_OK;
+        };
+        KrylovInfo info;
+        RC(t_copy(C[L - 1], tB3[L - 1]));
+        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-15)), 10, &info);
+        if (rc < 0) return rc;
+        if (rc == HTN_OK) {
+          RC(t_copy(tB3[L - 1], C[L - 1]));
+          RC(triangular_factor(L - 1, false));
+        }
+      }
+      RC(t_copy(C[L - 1], tB3[L - 1]));
+      for (int i = 0; i < L; ++i) {
+        RC(run3(mulL[i], AR[i]->d, C[prev(i)]->d, AL[i]->d));  // C A
+        RC(t_qr_inplace(AL[i], C[i]));                          // = AL R
+        RC(t_normalize(C[i], C[i]->d));
       }
       launch_axpby(-1.0, C[L - 1]->d, 1.0, tB3[L - 1]->d, C[L - 1]->dsize, st);
       double d2 = 0.0;
@@ -330,6 +476,7 @@ struct Uniform {
       tGR.push_back(own.like(GR[i]));
       if (!tGL[i] || !tGR[i]) return ctx->fail(HTN_ERR_OOM, "environments: work tensor allocation failed");
     }
+    RC(init_transfers1());
     for (int i = 0; i < L; ++i) {
       htn_plan* p = nullptr;
       // GL[i] (bond i-1) -> GL[i+1] (bond i) through AL[i];  GR[i] (bond i) -> GR[i-1] (bond i-1) through AR[i]
@@ -339,23 +486,6 @@ struct Uniform {
       RC(htn_plan_transfer(ctx, HTN_SIDE_RIGHT, W[i], AR[i], ARt[i], GR[i], GR[prev(i)], &p));
       own.plans.push_back(p);
       TR.push_back(p);
-      // MPO-free transfers on bond tensors
-      std::unique_ptr<htn_mpo> id(new htn_mpo());
-      id->ctx = ctx;
-      id->sym = AL[i]->sym;
-      id->Ml.ctx = id->Mr.ctx = ctx;
-      id->Ml.sym = id->Mr.sym = AL[i]->sym;
-      id->Ml.sec.push_back(Sector{0, 0, 0});
-      id->Mr.sec.push_back(Sector{0, 0, 0});
-      id->P = AL[i]->legs;
-      for (int s = 0; s < (int)id->P.sec.size(); ++s) id->entries.push_back(MpoEntry{0, s, s, 0, id->P.sec[s], 1.0});
-      RC(htn_plan_transfer(ctx, HTN_SIDE_LEFT, id.get(), AL[i], ALt[i], C[prev(i)], C[i], &p));
-      own.plans.push_back(p);
-      tl1.push_back(p);
-      RC(htn_plan_transfer(ctx, HTN_SIDE_RIGHT, id.get(), AR[i], ARt[i], C[i], C[prev(i)], &p));
-      own.plans.push_back(p);
-      tr1.push_back(p);
-      idmpo.push_back(std::move(id));
     }
     // level copies: last level of GL[0] <-> bond L-1 ; first level of GR[L-1] <-> bond L-1
     Program* q = own.program();
@@ -611,6 +741,24 @@ int32_t htn_gauge_right(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, con
   return rc;
 }
 
+// AR[0..n) (right-orthonormal) + guess for C[n-1]  ->  AL[i], C[i] with AL[i] C[i] = C[i-1] AR[i]
+int32_t htn_gauge_left(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AR, const htn_tensor* C_guess,
+                       htn_tensor* const* AL, htn_tensor* const* C, double tol, int32_t maxiter, int32_t* iterations,
+                       double* delta) {
+  if (!ctx || nsites <= 0 || !AL || !C_guess || !AR || !C) return HTN_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  RC(U.init_gauge(ctx, nsites, AL, AR, C, nullptr));
+  int it = 0;
+  double d = 0;
+  int32_t rc = U.leftorth(C_guess, tol, maxiter, &it, &d);
+  if (iterations) *iterations = it;
+  if (delta) *delta = d;
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
 // GL[i], GR[i] of a Jordan-form MPO Hamiltonian and the energy per unit cell (left / right estimate)
 int32_t htn_environments(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR,
                          htn_tensor* const* C, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
@@ -647,8 +795,9 @@ int32_t htn_eigsolve(htn_plan* p, const htn_tensor* x0, htn_tensor* x, int32_t k
   return rc;
 }
 
-// VUMPS on fixed bond spaces (oracle/mps.py:vumps).  log: per iteration 4 doubles
-// (galerkin error, energy per site, gauge iterations, H_eff applies); at most log_cap rows.
+// VUMPS on fixed bond spaces (oracle/mps.py:vumps).  log: per iteration 8 doubles (galerkin error,
+// energy per site, gauge iterations, H_eff applies, seconds in eigensolves / gauge / environments,
+// GMRES applies); at most log_cap rows.
 int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR, htn_tensor* const* C,
                   htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
                   double tol, int32_t maxiter, int32_t krylovdim, double* delta, double* energy_per_site,
@@ -665,7 +814,12 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
   double eps = 1.0, eL = 0, eR = 0;
   RC(U.environments(1e-10, krylovdim, 200, &eL, &eR, nullptr));
   int it = 0;
+  auto now = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
   for (it = 1; it <= maxiter; ++it) {
+    const double t_start = now();
     const double tol_eig = std::min(1e-4, std::max(eps * 1e-3, 1e-14));
     const double tol_env = std::min(1e-6, std::max(eps * 1e-4, 1e-14));
     const double tol_gauge = std::min(1e-8, std::max(eps * 1e-6, 1e-14));
@@ -681,6 +835,7 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
       if (rc < 0) return rc;
       napp += info.applies;
     }
+    const double t_eig = now();
     for (int i = 0; i < L; ++i) RC(U.regauge(i, U.nAC[i], U.nC[i], U.AL[i]));
     int git = 0;
     {
@@ -688,17 +843,26 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
       if (rc < 0) return rc;
     }
     RC(U.refresh_ac_and_transposes());
+    const double t_gauge = now();
+    int env_applies = 0;
     {
-      int32_t rc = U.environments(tol_env, krylovdim, 200, &eL, &eR, nullptr);
+      int32_t rc = U.environments(tol_env, krylovdim, 200, &eL, &eR, &env_applies);
       if (rc < 0) return rc;
     }
+    const double t_env = now();
     RC(U.galerkin(&eps));
+    const double t_end = now();
     if (log && it <= log_cap) {
-      double* row = log + 4 * (it - 1);
+      double* row = log + 8 * (it - 1);
       row[0] = eps;
       row[1] = 0.5 * (eL + eR) / L;
       row[2] = git;
       row[3] = napp;
+      row[4] = t_eig - t_start;    // seconds: eigensolves (H_AC, H_C for every site)
+      row[5] = t_gauge - t_eig;    // regauge + uniform right-orthonormalisation
+      row[6] = t_env - t_gauge;    // environments (transfers + GMRES)
+      row[7] = env_applies;        // GMRES operator applications
+      (void)t_end;
     }
     if (eps < tol) break;
   }

@@ -482,7 +482,7 @@ def environments(ctx: Context, AL, AR, Cs, Ws, GL, GR, tol=1e-12, krylovdim=30, 
 def vumps(ctx: Context, AL, AR, Cs, AC, Ws, GL, GR, tol=1e-10, maxiter=100, krylovdim=30):
     """`find_groundstate(psi, H, VUMPS(; tol, maxiter))` on fixed bond spaces (in/out tensors)."""
     delta, e, it = C.c_double(), C.c_double(), C.c_int32()
-    log = np.zeros((maxiter, 4))
+    log = np.zeros((maxiter, 8))
     rc = L.check(lib.htn_vumps(ctx.h, len(AL), _harr(AL), _harr(AR), _harr(Cs), _harr(AC), _harr(Ws), _harr(GL),
                                _harr(GR), tol, maxiter, krylovdim, C.byref(delta), C.byref(e), C.byref(it),
                                log.ctypes.data_as(C.POINTER(C.c_double)), maxiter), ctx.h)
@@ -513,11 +513,25 @@ def idmrg2(ctx: Context, AL, AR, Cs, AC, Ws, cut=1e-2, tol=1e-6, maxiter=100, kr
                                                  log=log[:it.value])
 
 
-def mixed_gauge(ctx: Context, AL, C_guess: Tensor, AR, Cs, AC, tol=1e-12, maxiter=10000):
+def mixed_gauge(ctx: Context, AL, C_guess: Tensor, AR, Cs, AC, tol=1e-12, maxiter=10000, from_right=False):
+    """`InfiniteMPS(A...)` gauge fixing.  from_right=False: AL holds left isometries (in/out), AR, C, AC are
+    outputs.  from_right=True: AR holds right isometries (MPSKit `InfiniteMPS(psi.AR)` after IDMRG2); AL, C, AC
+    must have AR's block structure / right bond spaces and are overwritten."""
     it = C.c_int32()
-    rc = L.check(lib.htn_mixed_gauge(ctx.h, len(AL), _harr(AL), C_guess.h, _harr(AR), _harr(Cs), _harr(AC), tol, maxiter,
-                                     C.byref(it)), ctx.h)
+    rc = L.check(lib.htn_mixed_gauge(ctx.h, len(AL), _harr(AL), C_guess.h, _harr(AR), _harr(Cs), _harr(AC),
+                                     1 if from_right else 0, tol, maxiter, C.byref(it)), ctx.h)
     return dict(converged=rc == 0, iterations=it.value)
+
+
+def uniform_from_right(ctx: Context, AR, C_last: Tensor, sym: int = 0, tol=1e-12):
+    """Consistent mixed-gauge uniform MPS from the right isometries an IDMRG2 run ends with: creates AL, AC
+    (structure of AR[i]) and C (bond tensors on the right spaces) and gauge-fixes.  Returns (AL, AR, C, AC)."""
+    n = len(AR)
+    AL = [a.like() for a in AR]
+    AC = [a.like() for a in AR]
+    Cs = [Tensor.bond(ctx, AR[i].space(1, sym)) for i in range(n)]
+    mixed_gauge(ctx, AL, C_last, AR, Cs, AC, tol=tol, from_right=True)
+    return AL, AR, Cs, AC
 
 
 def expval_diag(AC: Tensor, values) -> float:

@@ -298,7 +298,7 @@ def compute_groundstate(simul: OB_Sim, ctx=None, tol: float = 1e-6, verbosity: i
     schmidtcut = 10.0 ** (-simul.svalue)                                   # HF:1007
     AL, AR, C, AC, info1 = dev.idmrg2(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=schmidtcut, tol=tol,
                                       maxiter=min(maxiter, 200))           # HF:1010 (MPSKit default maxiter 200)
-    dev.mixed_gauge(ctx, AL, C[-1], AR, C, AC, tol=1e-12)                  # MPSKit: InfiniteMPS(psi.AR) at the end of IDMRG2
+    AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], simul.sym)      # MPSKit: InfiniteMPS(psi.AR) at the end of IDMRG2
     psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC)
     GL, GR = _make_envs(ctx, psi, H)
     info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))  # HF:1025-1027

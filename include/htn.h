@@ -217,6 +217,12 @@ int32_t htn_gauge_right(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, con
 int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, htn_space** Vm, htn_tensor** AL, htn_tensor** C,
                  htn_tensor** AR, double* discarded_weight, int32_t* kept);
 
+/* Mirror image (MPSKit `uniform_leftorth!`): from right-orthonormal AR[0..n) and a guess for C[n-1]
+ * compute AL[i], C[i] with AL[i] C[i] = C[i-1] AR[i]. */
+int32_t htn_gauge_left(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AR, const htn_tensor* C_guess,
+                       htn_tensor* const* AL, htn_tensor* const* C, double tol, int32_t maxiter, int32_t* iterations,
+                       double* delta);
+
 /* ---- environments and ground-state driver ------------------------------------------------ */
 /* Replaces: MPSKit `environments(psi, H)` / `recalculate!` for an InfiniteMPOHamiltonian in Jordan
  * form (level 0 and level chi-1 carry the identity): GL[i] on the bond left of site i (created with
@@ -227,8 +233,9 @@ int32_t htn_environments(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, ht
                          double tol, int32_t krylovdim, int32_t maxiter, double* energy_left, double* energy_right);
 /* Replaces: `find_groundstate(psi, H, VUMPS(; tol, maxiter))` (HubbardFunctions.jl:1012,1017,1025-1027)
  * on fixed bond spaces.  In/out: AL, AR, C, AC (mixed gauge), GL, GR.  delta = final Galerkin error
- * (the `δ` MPSKit returns, HF:1027).  log (may be NULL): rows of 4 doubles per iteration
- * (galerkin error, energy per site, gauge iterations, H_eff applies). Returns HTN_NOT_CONVERGED when
+ * (the `δ` MPSKit returns, HF:1027).  log (may be NULL): rows of 8 doubles per iteration
+ * (galerkin error, energy per site, gauge iterations, H_eff applies, seconds spent in the eigensolves,
+ * in gauge fixing, in the environments, GMRES operator applications). Returns HTN_NOT_CONVERGED when
  * maxiter is reached (state usable, as MPSKit does). */
 int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR, htn_tensor* const* C,
                   htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
@@ -244,11 +251,15 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
 int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** AR, htn_tensor** C, htn_tensor** AC,
                    const htn_mpo* const* W, double cut, double tol, int32_t maxiter, int32_t krylovdim, double eig_tol,
                    int32_t maxdim, double* delta, int32_t* iterations, double* log, int32_t log_cap);
-/* Replaces: `InfiniteMPS(AL...)` gauge fixing (MPSKit `uniform_leftorth!/uniform_rightorth!`): AL <- Q(AL),
- * then AR, C (iterated LQ) and AC = AL C.  AL is modified in place. */
+/* Replaces: `InfiniteMPS(A...)` gauge fixing (MPSKit `uniform_leftorth!/uniform_rightorth!`).
+ *   from_right = 0: AL[i] hold left isometries (modified in place: AL <- Q(AL));
+ *   from_right = 1: AR[i] hold right isometries -- the list whose bond spaces chain after an IDMRG2
+ *                   iteration (MPSKit: `InfiniteMPS(psi.AR)`); AL, C follow by the iterated QR.
+ * Then AR, C by the iterated LQ and AC = AL C.  AL[i], AR[i], AC[i] share one block structure, C[i] is a
+ * bond tensor on the right space of site i, C_guess lives on the last bond. */
 int32_t htn_mixed_gauge(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
-                        htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, double tol, int32_t maxiter,
-                        int32_t* iterations);
+                        htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, int32_t from_right,
+                        double tol, int32_t maxiter, int32_t* iterations);
 /* Replaces: `expectation_value(psi, i => op)` (HubbardFunctions.jl:1448-1449,1507,1533) for one-site
  * operators that are scalars on every physical multiplet (n, n_up, n_dn): values[s] per multiplet s. */
 int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out);

@@ -162,6 +162,63 @@ def regauge(AC: MPSTensor, C: BondTensor) -> MPSTensor:
     return out
 
 
+EIG_MINITER = 10     # MPSKit: plain QR/LQ sweeps first, then sweeps preceded by an Arnoldi fixed-point solve
+
+
+def arnoldi_dominant(apply, x0, tol=1e-12, krylovdim=30, maxiter=10):
+    """Dominant eigenvector of a (non-symmetric) linear map by Arnoldi with CGS2 and explicit restarts
+    (KrylovKit `eigsolve(f, x0, 1, :LM, Arnoldi(...))` as used by MPSKit's uniform_left/rightorth!)."""
+    x = vscale(vcopy(x0), 1.0 / vnorm(x0))
+    res = np.inf
+    for _ in range(maxiter):
+        V = [x]
+        H = np.zeros((krylovdim + 1, krylovdim))
+        m = 0
+        for j in range(krylovdim):
+            w = apply(V[j])
+            for _pass in range(2):
+                for i, q in enumerate(V):
+                    c = vdot(q, w)
+                    H[i, j] += c
+                    vaxpy(-c, q, w)
+            hn = vnorm(w)
+            H[j + 1, j] = hn
+            m = j + 1
+            ev, evec = np.linalg.eig(H[:m, :m])
+            k = int(np.argmax(np.abs(ev)))
+            y = np.real(evec[:, k])
+            y /= np.linalg.norm(y)
+            res = abs(hn * y[-1])
+            if res < tol or hn < 1e-14 or j == krylovdim - 1:
+                break
+            V.append(vscale(w, 1.0 / hn))
+        xn = vscale(vcopy(V[0]), y[0])
+        for q, c in zip(V[1:m], y[1:m]):
+            vaxpy(c, q, xn)
+        x = vscale(xn, 1.0 / vnorm(xn))
+        if res < tol:
+            break
+    return x, res
+
+
+def _bond_env(C: BondTensor, side: str, triv) -> "EnvTensor":
+    return EnvTensor(side, C.V, triv, {(0, c, c): b.copy() for c, b in C.blocks.items()})
+
+
+def _env_bond(E: "EnvTensor") -> BondTensor:
+    return BondTensor(E.V, {k[1]: b.copy() for k, b in E.blocks.items()})
+
+
+def _tri_factor(C: BondTensor, lower: bool) -> BondTensor:
+    out = BondTensor(C.V)
+    for c, b in C.blocks.items():
+        out.blocks[c] = _qrpos(b.T)[1].T if lower else _qrpos(b)[1]
+    nrm = bond_norm(out)
+    for b in out.blocks.values():
+        b /= nrm
+    return out
+
+
 def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
     """From left-orthonormal AL[0..L-1] and a guess for C[L-1]: AR[i], C[i] with
     AL[i] C[i] = C[i-1] AR[i]  (iterated LQ through the unit cell until C[L-1] is stationary)."""
@@ -174,7 +231,21 @@ def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
     AR = [None] * L
     delta = np.inf
     its = 0
+    idR = None
     for its in range(1, maxiter + 1):
+        if its > EIG_MINITER:
+            if idR is None:
+                triv = Legs(AL[0].kind, [S.trivial(AL[0].kind)])
+                idR = [TransferPlan("R", identity_mpo(AL[i].P), AL[i].Vl, AL[i].P, AL[i].Vr) for i in range(L)]
+
+            def op(X):
+                T = _bond_env(X, "R", triv)
+                for k in range(L - 1, -1, -1):
+                    T = idR[k].apply(T, AL[k], AR[k])
+                return _env_bond(T)
+
+            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-15)))
+            C[L - 1] = _tri_factor(x, lower=True)
         Cold = C[L - 1]
         for i in range(L - 1, -1, -1):
             Lm, Q = right_orth(mul_right(AL[i], C[i]))
@@ -188,6 +259,47 @@ def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
         if delta < tol:
             break
     return AR, C, dict(iterations=its, delta=float(delta))
+
+
+def uniform_leftorth(AR, C_last: BondTensor, tol=1e-13, maxiter=10000):
+    """Mirror of `uniform_rightorth`: from (approximately) right-orthonormal AR[0..L-1] and a guess for
+    C[L-1]: AL[i], C[i] with AL[i] C[i] = C[i-1] AR[i]  (iterated positive QR, MPSKit `uniform_leftorth!`)."""
+    L = len(AR)
+    C = [None] * L
+    C[L - 1] = C_last.copy()
+    nrm = bond_norm(C[L - 1])
+    for b in C[L - 1].blocks.values():
+        b /= nrm
+    AL = [None] * L
+    delta, its = np.inf, 0
+    idL = None
+    for its in range(1, maxiter + 1):
+        if its > EIG_MINITER:
+            if idL is None:
+                triv = Legs(AR[0].kind, [S.trivial(AR[0].kind)])
+                idL = [TransferPlan("L", identity_mpo(AR[i].P), AR[i].Vl, AR[i].P, AR[i].Vr) for i in range(L)]
+
+            def op(X):
+                T = _bond_env(X, "L", triv)
+                for k in range(L):
+                    T = idL[k].apply(T, AR[k], AL[k])
+                return _env_bond(T)
+
+            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-15)))
+            C[L - 1] = _tri_factor(x, lower=False)
+        Cold = C[L - 1]
+        for i in range(L):
+            Q, R = left_orth(mul_left(C[i - 1 if i > 0 else L - 1], AR[i]))
+            nrm = bond_norm(R)
+            for b in R.blocks.values():
+                b /= nrm
+            C[i] = R
+            AL[i] = Q
+        delta = np.sqrt(sum(C[L - 1].V.dims[c] * np.sum((C[L - 1].blocks[c] - Cold.blocks[c]) ** 2)
+                            for c in Cold.blocks))
+        if delta < tol:
+            break
+    return AL, C, dict(iterations=its, delta=float(delta))
 
 
 def random_state(kind, spaces, phys, rng):

@@ -357,10 +357,11 @@ def idmrg2(state, W_list, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol
     return AL, C, AR, eps, log
 
 
-def idmrg2_to_uniform(AL, C, tol=1e-12):
-    """Gauge-fix the IDMRG2 result into a consistent uniform MPS (MPSKit: `InfiniteMPS(psi.AR)` at the
-    end of IDMRG2); here from the left isometries, followed by the iterated LQ."""
-    from .mps import left_orth
-    ALq = [left_orth(a)[0] for a in AL]
-    AR, Cn, _ = uniform_rightorth(ALq, C[-1], tol=tol)
-    return dict(AL=ALq, AR=AR, C=Cn, AC=[mul_right(ALq[i], Cn[i]) for i in range(len(AL))])
+def idmrg2_to_uniform(AR, C, tol=1e-12):
+    """Gauge-fix the IDMRG2 result into a consistent uniform MPS, as MPSKit does with
+    `InfiniteMPS(psi.AR)` at the end of IDMRG2 (the AR list is the one whose bond spaces chain after a
+    full iteration): AL, C by the iterated QR from AR, then AR, C by the iterated LQ from AL."""
+    from .mps import uniform_leftorth
+    ALq, Cl, _ = uniform_leftorth(AR, C[-1], tol=tol)
+    ARq, Cn, _ = uniform_rightorth(ALq, Cl[-1], tol=tol)
+    return dict(AL=ALq, AR=ARq, C=Cn, AC=[mul_right(ALq[i], Cn[i]) for i in range(len(AR))])

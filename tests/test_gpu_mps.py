@@ -145,7 +145,7 @@ def test_gauge_right_matches_oracle(ctx, kind):
     g = dev.Tensor.bond(ctx, du.V[1])
     g.upload(pack_blocks(g, C0.blocks, key=lambda lab: lab[0]))
     res = dev.gauge_right(ctx, du.AL, g, du.AR, du.C, tol=1e-13)
-    assert res["converged"] and abs(res["iterations"] - info["iterations"]) <= 1
+    assert res["converged"] and abs(res["iterations"] - info["iterations"]) <= 2
     for i in range(2):
         assert max_block_err(du.mps_blocks(du.AR[i]), ARo[i].blocks) < 1e-9
         assert max_block_err(du.bond_blocks(du.C[i]), Co[i].blocks) < 1e-9

@@ -119,9 +119,9 @@ def test_idmrg2_then_vumps_reproduces_reference_golden(ctx):
         assert V.sectors == Co[i].V.sectors and V.mult == Co[i].V.mult        # same truncated bond spaces
         assert max_block_err(unpack_blocks(Cs[i], key=lambda lab: lab[0]), Co[i].blocks) < 1e-6
     # gauge-fix and polish with VUMPS on the grown spaces, both sides
-    sto = T2.idmrg2_to_uniform(ALo, Co)
+    sto = T2.idmrg2_to_uniform(ARo, Co)
     sto, envs, eps, _ = M.vumps(sto, Ws, tol=1e-8, maxiter=60)
-    dev.mixed_gauge(ctx, AL, Cs[1], AR, Cs, AC)
+    AL, AR, Cs, AC = dev.uniform_from_right(ctx, AR, Cs[1], kind)
     V = [Cs[i].space(0, kind) for i in range(2)]
     chi = len(Ws[0].Ml)
     GL = [dev.Tensor.env(ctx, 0, V[i - 1], du.M, identity_level=0) for i in range(2)]

@@ -54,5 +54,5 @@ def test_reference_schedule_reproduces_golden_energy(u):
     st = M.random_state(kind, sp, [P, P], np.random.default_rng(1))
     AL, C, AR, eps, log = T2.idmrg2(st, Ws, cut=1e-2, tol=1e-6, maxiter=60)
     assert eps < 1e-6
-    st2, envs, eps2, _ = M.vumps(T2.idmrg2_to_uniform(AL, C), Ws, tol=1e-6, maxiter=80)
+    st2, envs, eps2, _ = M.vumps(T2.idmrg2_to_uniform(AR, C), Ws, tol=1e-6, maxiter=80)
     assert abs(envs.energy_per_site - g["E"]) < 1e-6, (g["cite"], envs.energy_per_site, g["E"])
