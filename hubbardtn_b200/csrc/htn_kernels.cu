@@ -657,12 +657,13 @@ void launch_multiaxpy(const double* V, long long stride, int nvec, const double*
   multiaxpy_kernel<<<grid, 256, 0, st>>>(V, stride, nvec, h, sign, w, n);
 }
 
-// mode 0: y = x * s ; 1: y = x / s ; 2: y = x / sqrt(s)
+// mode 0: y = x * s ; 1: y = x / s ; 2: y = x / sqrt(s) ; 3: y = x / sqrt(s), or 0 when s < 1e-28
 __global__ void scale_dev_kernel(const double* __restrict__ x, const double* __restrict__ scal, int mode,
                                  double* __restrict__ y, long long n) {
   double s = *scal;
   if (mode == 1) s = 1.0 / s;
   if (mode == 2) s = 1.0 / sqrt(s);
+  if (mode == 3) s = s < 1e-28 ? 0.0 : 1.0 / sqrt(s);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gs = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += gs) y[i] = x[i] * s;

@@ -8,6 +8,7 @@
 // rank-k update, and a single readback of <= 130 scalars.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <cstring>
 
@@ -187,7 +188,7 @@ int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunk
 }
 
 // device scalar slots inside ctx->kry_scal
-enum { S_H = 0, S_H2 = 64, S_BETA = 128, S_NRM = 129, S_Y = 192, S_TMP = 300 };
+enum { S_H = 0, S_H2 = 64, S_BETA = 128, S_NRM = 129, S_Y = 192, S_TMP = 300, S_A1 = 512, S_A2 = 576, S_B = 640 };
 
 int32_t t_dot_dev(const htn_tensor* like, const double* x, const double* y, double* out_dev) {
   htn_ctx* ctx = like->ctx;
@@ -280,6 +281,11 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
   double theta = 0.0, res = 1e300;
   bool converged = false;
   std::vector<double> alphas, betas, Tm, Z, ev;
+  // Semi-eager recurrence: the Lanczos coefficients of every step are parked in device arrays and read
+  // back (one synchronisation) only every LANCZOS_CHECK steps, so the launches of up to LANCZOS_CHECK
+  // steps queue up behind each other instead of paying a host round trip per step (KrylovKit's `eager`
+  // mode checks every step; the Ritz pair is the same, at most LANCZOS_CHECK - 1 applies later).
+  constexpr int LANCZOS_CHECK = 5;
   for (int restart = 0; restart < maxiter && !converged; ++restart) {
     alphas.clear();
     betas.clear();
@@ -294,12 +300,28 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
       launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
       launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
-      cudaMemcpyAsync(sh, sc, 130 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(sc + S_A1 + j, sc + S_H + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(sc + S_A2 + j, sc + S_H2 + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(sc + S_B + j, sc + S_BETA, sizeof(double), cudaMemcpyDeviceToDevice, st);
+      const bool check = (j % LANCZOS_CHECK) == LANCZOS_CHECK - 1 || j == krylovdim - 1;
+      if (!check) {
+        launch_scale_dev(w, sc + S_BETA, 3, w, n, st);  // next basis vector (0 on breakdown)
+        continue;
+      }
+      cudaMemcpyAsync(sh + S_A1, sc + S_A1, 192 * sizeof(double), cudaMemcpyDeviceToHost, st);
       if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "lanczos");
-      const double a = sh[S_H + j] + sh[S_H2 + j];
-      const double b = std::sqrt(std::max(sh[S_BETA], 0.0));
-      alphas.push_back(a);
       m = j + 1;
+      alphas.assign(m, 0.0);
+      betas.assign(m, 0.0);
+      for (int i = 0; i < m; ++i) {
+        alphas[i] = sh[S_A1 + i] + sh[S_A2 + i];
+        betas[i] = std::sqrt(std::max(sh[S_B + i], 0.0));
+      }
+      for (int i = 0; i < m; ++i)
+        if (betas[i] < 1e-14) {  // invariant subspace reached at step i
+          m = i + 1;
+          break;
+        }
       Tm.assign((size_t)m * m, 0.0);
       for (int i = 0; i < m; ++i) {
         Tm[(size_t)i * m + i] = alphas[i];
@@ -312,10 +334,10 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       theta = ev[lo];
       y.assign(m, 0.0);
       for (int i = 0; i < m; ++i) y[i] = Z[(size_t)i * m + lo];
-      res = std::fabs(b * y[m - 1]);
-      if (res < tol || b < 1e-14 || j == krylovdim - 1) break;
-      betas.push_back(b);
-      launch_scale_dev(w, sc + S_BETA, 2, w, n, st);
+      const double bm = betas[m - 1];
+      res = std::fabs(bm * y[m - 1]);
+      if (res < tol || bm < 1e-14 || m < j + 1 || j == krylovdim - 1) break;
+      launch_scale_dev(w, sc + S_BETA, 3, w, n, st);
     }
     // Ritz vector -> V[0]  (built in the spare slot, then copied)
     for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
@@ -443,41 +465,136 @@ int32_t gmres_solve(const htn_tensor* like, const ApplyFn& apply, const double* 
   return converged ? HTN_OK : HTN_NOT_CONVERGED;
 }
 
-// ---- dominant eigenpair of a small real (nonsymmetric) matrix on the host -------------------
-// Plain power iteration (the dominant eigenvalue of a transfer map is real, positive and simple);
-// returns false when the iteration does not settle (e.g. a complex dominant pair in a poor Krylov space).
-static bool small_dominant_eig(int m, const std::vector<double>& H, int ld, double* theta, std::vector<double>& y) {
-  y.assign(m, 0.0);
-  y[0] = 1.0;  // the start vector of the Krylov space carries the largest weight on the fixed point
-  std::vector<double> z(m);
-  double th = 0.0;
-  for (int it = 0; it < 200000; ++it) {
-    double n = 0.0, d = 0.0;
-    for (int i = 0; i < m; ++i) {
-      double sacc = 0.0;
-      for (int j = 0; j < m; ++j) sacc += H[(size_t)i * ld + j] * y[j];
-      z[i] = sacc;
-      n += sacc * sacc;
-      d += sacc * y[i];
+// ---- dominant eigenpair of a small real upper-Hessenberg matrix on the host ------------------
+// Eigenvalues by the single-shift QR algorithm in complex arithmetic (Wilkinson shifts, Givens
+// rotations, deflation); the eigenvector of the eigenvalue of largest modulus (real for a transfer
+// map) by inverse iteration.  m <= 60.
+static bool hessenberg_eigenvalues(int m, const std::vector<double>& Hin, int ld, std::vector<std::complex<double>>& ev) {
+  typedef std::complex<double> cd;
+  std::vector<cd> H((size_t)m * m);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) H[(size_t)i * m + j] = (j >= i - 1) ? Hin[(size_t)i * ld + j] : 0.0;
+  ev.assign(m, cd(0.0));
+  int hi = m - 1, iter = 0;
+  std::vector<cd> cs(m), sn(m);
+  while (hi >= 0) {
+    if (hi == 0) {
+      ev[0] = H[0];
+      break;
     }
-    n = std::sqrt(n);
-    if (!(n > 0.0)) return false;
-    const double sgn = d < 0.0 ? -1.0 : 1.0;
-    double diff = 0.0;
-    for (int i = 0; i < m; ++i) {
-      const double v = sgn * z[i] / n;
-      diff = std::max(diff, std::fabs(v - y[i]));
-      y[i] = v;
+    int l = hi;
+    for (; l > 0; --l) {
+      const double sub = std::abs(H[(size_t)l * m + l - 1]);
+      const double scale = std::abs(H[(size_t)l * m + l]) + std::abs(H[(size_t)(l - 1) * m + l - 1]);
+      if (sub <= 1e-16 * (scale > 0 ? scale : 1.0)) {
+        H[(size_t)l * m + l - 1] = 0.0;
+        break;
+      }
     }
-    th = d;
-    if (diff < 1e-15) {
-      *theta = th;
-      return true;
+    if (l == hi) {
+      ev[hi] = H[(size_t)hi * m + hi];
+      --hi;
+      iter = 0;
+      continue;
     }
+    if (++iter > 300) return false;
+    // Wilkinson shift: eigenvalue of the trailing 2x2 closer to H[hi][hi]
+    const cd a = H[(size_t)(hi - 1) * m + hi - 1], b = H[(size_t)(hi - 1) * m + hi], c = H[(size_t)hi * m + hi - 1],
+             d = H[(size_t)hi * m + hi];
+    const cd tr = a + d, det = a * d - b * c;
+    const cd disc = std::sqrt(tr * tr - 4.0 * det);
+    const cd l1 = 0.5 * (tr + disc), l2 = 0.5 * (tr - disc);
+    cd mu = std::abs(l1 - d) < std::abs(l2 - d) ? l1 : l2;
+    if (iter % 11 == 10) mu += cd(std::abs(c), 0.0);  // exceptional shift
+    for (int i = l; i <= hi; ++i) H[(size_t)i * m + i] -= mu;
+    for (int k = l; k < hi; ++k) {
+      const cd x = H[(size_t)k * m + k], y = H[(size_t)(k + 1) * m + k];
+      const double r = std::sqrt(std::norm(x) + std::norm(y));
+      if (r == 0.0) {
+        cs[k] = 1.0;
+        sn[k] = 0.0;
+        continue;
+      }
+      cs[k] = x / r;
+      sn[k] = y / r;
+      for (int j = k; j <= hi; ++j) {
+        const cd u = H[(size_t)k * m + j], v = H[(size_t)(k + 1) * m + j];
+        H[(size_t)k * m + j] = std::conj(cs[k]) * u + std::conj(sn[k]) * v;
+        H[(size_t)(k + 1) * m + j] = -sn[k] * u + cs[k] * v;
+      }
+    }
+    for (int k = l; k < hi; ++k) {
+      const int top = std::min(k + 2, hi);
+      for (int i = l; i <= top; ++i) {
+        const cd u = H[(size_t)i * m + k], v = H[(size_t)i * m + k + 1];
+        H[(size_t)i * m + k] = u * cs[k] + v * sn[k];
+        H[(size_t)i * m + k + 1] = -u * std::conj(sn[k]) + v * std::conj(cs[k]);
+      }
+    }
+    for (int i = l; i <= hi; ++i) H[(size_t)i * m + i] += mu;
   }
-  *theta = th;
-  return false;
+  return true;
 }
+
+static bool small_dominant_eig(int m, const std::vector<double>& H, int ld, double* theta, std::vector<double>& y) {
+  std::vector<std::complex<double>> ev;
+  if (!hessenberg_eigenvalues(m, H, ld, ev)) return false;
+  int k = 0;
+  for (int i = 1; i < m; ++i)
+    if (std::abs(ev[i]) > std::abs(ev[k])) k = i;
+  if (std::fabs(ev[k].imag()) > 1e-8 * std::abs(ev[k])) return false;  // not a transfer-map fixed point
+  const double lam = ev[k].real();
+  const double sigma = lam * (1.0 + 1e-10) + 1e-300;
+  y.assign(m, 1.0 / std::sqrt((double)m));
+  for (int it = 0; it < 4; ++it) {
+    std::vector<double> A((size_t)m * m), b(y);
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) A[(size_t)i * m + j] = H[(size_t)i * ld + j] - (i == j ? sigma : 0.0);
+    for (int c = 0; c < m; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < m; ++r)
+        if (std::fabs(A[(size_t)r * m + c]) > std::fabs(A[(size_t)piv * m + c])) piv = r;
+      if (std::fabs(A[(size_t)piv * m + c]) < 1e-300) A[(size_t)piv * m + c] = 1e-300;
+      if (piv != c) {
+        for (int j = 0; j < m; ++j) std::swap(A[(size_t)piv * m + j], A[(size_t)c * m + j]);
+        std::swap(b[piv], b[c]);
+      }
+      for (int r = c + 1; r < m; ++r) {
+        const double f = A[(size_t)r * m + c] / A[(size_t)c * m + c];
+        if (f == 0.0) continue;
+        for (int j = c; j < m; ++j) A[(size_t)r * m + j] -= f * A[(size_t)c * m + j];
+        b[r] -= f * b[c];
+      }
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double sacc = b[i];
+      for (int j = i + 1; j < m; ++j) sacc -= A[(size_t)i * m + j] * b[j];
+      b[i] = sacc / A[(size_t)i * m + i];
+    }
+    double n = 0.0;
+    for (int i = 0; i < m; ++i) n += b[i] * b[i];
+    n = std::sqrt(n);
+    if (!(n > 0.0) || !std::isfinite(n)) return false;
+    for (int i = 0; i < m; ++i) y[i] = b[i] / n;
+  }
+  if (y[0] < 0.0)
+    for (int i = 0; i < m; ++i) y[i] = -y[i];
+  *theta = lam;
+  return true;
+}
+
+}  // namespace htn
+
+// test hook (host only): dominant eigenpair of a small upper-Hessenberg matrix H[m][m] (row-major)
+extern "C" int32_t htn_test_hessenberg_dominant(int32_t m, const double* H, double* theta, double* y) {
+  if (m <= 0 || m > 60 || !H || !theta || !y) return HTN_ERR_INVALID;
+  std::vector<double> h(H, H + (size_t)m * m), v;
+  if (!htn::small_dominant_eig(m, h, m, theta, v)) return HTN_NOT_CONVERGED;
+  for (int i = 0; i < m; ++i) y[i] = v[i];
+  return HTN_OK;
+}
+
+namespace htn {
 
 // Dominant eigenvector (largest |lambda|, assumed real and simple: the fixed point of a transfer map) by
 // Arnoldi with CGS2 and explicit restarts (KrylovKit `eigsolve(f, x0, 1, :LM, Arnoldi(krylovdim, tol))`

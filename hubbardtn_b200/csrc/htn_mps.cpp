@@ -336,7 +336,7 @@ struct Uniform {
         };
         KrylovInfo info;
         RC(t_copy(C[L - 1], tB3[L - 1]));
-        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-15)), 10, &info);
+        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-13)), 10, &info);
         if (rc < 0) return rc;
         if (getenv("HTN_DEBUG_GAUGE"))
           fprintf(stderr, "rightorth it %d delta %.3e arnoldi rc %d theta %.12f res %.3e applies %d\n", it, delta, rc,
@@ -399,8 +399,11 @@ struct Uniform {
         };
         KrylovInfo info;
         RC(t_copy(C[L - 1], tB3[L - 1]));
-        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-15)), 10, &info);
+        int32_t rc = arnoldi_dominant(C[L - 1], op, tB3[L - 1]->d, 30, std::min(1e-3, std::max(delta * delta, 1e-13)), 10, &info);
         if (rc < 0) return rc;
+        if (getenv("HTN_DEBUG_GAUGE"))
+          fprintf(stderr, "leftorth it %d delta %.3e arnoldi rc %d theta %.12f res %.3e applies %d\n", it, delta, rc,
+                  info.value, info.residual, info.applies);
         if (rc == HTN_OK) {
           RC(t_copy(tB3[L - 1], C[L - 1]));
           RC(triangular_factor(L - 1, false));
@@ -827,11 +830,11 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
     for (int i = 0; i < L; ++i) {
       KrylovInfo info;
       ApplyFn hac = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hac[i], a, b, 0xF); };
-      int32_t rc = lanczos_lowest(U.AC[i], hac, U.AC[i]->d, U.nAC[i]->d, krylovdim, tol_eig, 5, &info);
+      int32_t rc = lanczos_lowest(U.AC[i], hac, U.AC[i]->d, U.nAC[i]->d, krylovdim, tol_eig, 20, &info);
       if (rc < 0) return rc;
       napp += info.applies;
       ApplyFn hc = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hc[i], a, b, 0xF); };
-      rc = lanczos_lowest(U.C[i], hc, U.C[i]->d, U.nC[i]->d, krylovdim, tol_eig, 5, &info);
+      rc = lanczos_lowest(U.C[i], hc, U.C[i]->d, U.nC[i]->d, krylovdim, tol_eig, 20, &info);
       if (rc < 0) return rc;
       napp += info.applies;
     }

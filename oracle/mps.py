@@ -244,7 +244,7 @@ def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
                     T = idR[k].apply(T, AL[k], AR[k])
                 return _env_bond(T)
 
-            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-15)))
+            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-13)))
             C[L - 1] = _tri_factor(x, lower=True)
         Cold = C[L - 1]
         for i in range(L - 1, -1, -1):
@@ -285,7 +285,7 @@ def uniform_leftorth(AR, C_last: BondTensor, tol=1e-13, maxiter=10000):
                     T = idL[k].apply(T, AR[k], AL[k])
                 return _env_bond(T)
 
-            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-15)))
+            x, _ = arnoldi_dominant(op, C[L - 1], tol=min(1e-3, max(delta * delta, 1e-13)))
             C[L - 1] = _tri_factor(x, lower=False)
         Cold = C[L - 1]
         for i in range(L):
@@ -581,11 +581,11 @@ def vumps(state, W_list, tol=1e-10, maxiter=100, krylovdim=30, verbose=False, en
         newAC, newC = [], []
         for i in range(L):
             plan = HeffACPlan(envs.GL[i], W_list[i], envs.GR[i], state["AC"][i])
-            _, ac, _ = lanczos_lowest(plan.apply, state["AC"][i], tol=tol_eig, krylovdim=krylovdim, maxiter=5)
+            _, ac, _ = lanczos_lowest(plan.apply, state["AC"][i], tol=tol_eig, krylovdim=krylovdim, maxiter=20)
             if vdot(ac, state["AC"][i]) < 0:
                 vscale(ac, -1.0)
             hc = _HC(envs.GL[(i + 1) % L], envs.GR[i])
-            _, c, _ = lanczos_lowest(hc, state["C"][i], tol=tol_eig, krylovdim=krylovdim, maxiter=5)
+            _, c, _ = lanczos_lowest(hc, state["C"][i], tol=tol_eig, krylovdim=krylovdim, maxiter=20)
             if vdot(c, state["C"][i]) < 0:
                 vscale(c, -1.0)
             newAC.append(ac)

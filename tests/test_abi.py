@@ -66,3 +66,49 @@ def test_network_coefficients_match_oracle():
     # abelian: 1 when every vertex is allowed
     assert device.network_coefficient(1, [(1, 1, 1), (1, 1, 0), (0, 2, 1), (0, 0, 0), (1, 1, 0), (1, 1, 0),
                                           (1, 1, 1), (1, 1, 1), (0, 2, 1)]) == 1.0
+
+
+def test_small_hessenberg_eigensolver_matches_numpy():
+    """Host part of the Arnoldi fixed-point solver (gauge fixing): complex single-shift QR + inverse
+    iteration against numpy.linalg.eig, including clustered and complex sub-dominant spectra."""
+    import ctypes as C
+    from hubbardtn_b200 import _lib
+    rng = np.random.default_rng(3)
+    pd = C.POINTER(C.c_double)
+    for m in (1, 2, 5, 17, 30):
+        for trial in range(6):
+            # spectrum: dominant real eigenvalue, a close real neighbour, complex pairs inside the disc
+            lam = np.zeros(m, dtype=complex)
+            lam[0] = 0.93 + 0.07 * rng.random()
+            for i in range(1, m):
+                lam[i] = (0.999 * lam[0] if i == 1 and trial % 2 else 0.9 * rng.random() * np.exp(2j * np.pi * rng.random()))
+            if m > 2 and m % 2 == 0:
+                lam[-1] = 0.5 * rng.random()
+            # real matrix with that spectrum (complex pairs as 2x2 rotations), random similarity, then Hessenberg
+            B = np.zeros((m, m))
+            i = 0
+            while i < m:
+                if abs(lam[i].imag) > 0 and i + 1 < m and i >= 2:
+                    a, b = lam[i].real, lam[i].imag
+                    B[i:i + 2, i:i + 2] = [[a, b], [-b, a]]
+                    lam[i + 1] = np.conj(lam[i])
+                    i += 2
+                else:
+                    lam[i] = lam[i].real if i else lam[i]
+                    B[i, i] = lam[i].real
+                    i += 1
+            S_ = rng.standard_normal((m, m)) + 2 * np.eye(m)
+            A = S_ @ B @ np.linalg.inv(S_)
+            from scipy.linalg import hessenberg
+            H = np.ascontiguousarray(hessenberg(A))
+            ev, evec = np.linalg.eig(H)
+            k = int(np.argmax(np.abs(ev)))
+            theta, y = C.c_double(), np.zeros(m)
+            rc = _lib.lib.htn_test_hessenberg_dominant(m, H.ctypes.data_as(pd), C.byref(theta), y.ctypes.data_as(pd))
+            assert rc == 0
+            assert abs(theta.value - ev[k].real) < 1e-9 * abs(ev[k])
+            ref = np.real(evec[:, k])
+            ref /= np.linalg.norm(ref)
+            if ref @ y < 0:
+                ref = -ref
+            assert np.abs(ref - y).max() < 1e-6
