@@ -114,6 +114,7 @@ SIGNATURES = {
     "htn_tensor_axpby": (_i32, [C.c_double, _p, C.c_double, _p]),
     "htn_network_coefficient": (_i32, [_i32, _pi32, _pd]),
     "htn_test_hessenberg_dominant": (_i32, [_i32, _pd, _pd, _pd]),
+    "htn_probe_krylov": (_i32, [_p, _i32, _i32, _pf, _pd]),
     "htn_probe_fp64_peak": (_i32, [_p, _i32, _pd]),
 }
 

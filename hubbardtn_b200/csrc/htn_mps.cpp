@@ -876,6 +876,49 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
   return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
 }
 
+// Times one classical Gram-Schmidt pass of the Krylov solvers on vectors shaped like `like`:
+// multidot (all <V_j, w>, j < nvec) + multiaxpy (w -= V h), device-timed over `reps` repetitions.
+// ms[0] = multidot pair per pass, ms[1] = multiaxpy per pass; bytes[0], bytes[1] = algorithmic bytes.
+int32_t htn_probe_krylov(const htn_tensor* like, int32_t nvec, int32_t reps, float* ms, double* bytes) {
+  if (!like || !ms || !bytes || nvec <= 0 || nvec > 60 || reps <= 0) return HTN_ERR_INVALID;
+  htn_ctx* ctx = like->ctx;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const int64_t n = like->dsize;
+  RC(ensure_krylov(ctx, nvec + 2, n, like->nchunks));
+  cudaStream_t st = ctx->stream;
+  cudaMemsetAsync(ctx->kry_V, 0, (nvec + 2) * n * sizeof(double), st);
+  double* w = ctx->kry_V + (int64_t)nvec * n;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int which = 0; which < 2; ++which) {
+    for (int r = 0; r < 3; ++r) {  // warm-up
+      if (which == 0)
+        launch_multidot(like->dblocks, like->dchunks, like->nchunks, ctx->kry_V, n, nvec, w, ctx->kry_partial, ctx->kry_scal, st);
+      else
+        launch_multiaxpy(ctx->kry_V, n, nvec, ctx->kry_scal, -1.0, w, n, st);
+    }
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps; ++r) {
+      if (which == 0)
+        launch_multidot(like->dblocks, like->dchunks, like->nchunks, ctx->kry_V, n, nvec, w, ctx->kry_partial, ctx->kry_scal, st);
+      else
+        launch_multiaxpy(ctx->kry_V, n, nvec, ctx->kry_scal, -1.0, w, n, st);
+    }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    ms[which] = t / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  bytes[0] = 8.0 * n * (nvec + 1);  // read V (nvec vectors) and w
+  bytes[1] = 8.0 * n * (nvec + 2);  // read V, read + write w
+  return cuda_rc(ctx, "probe_krylov");
+}
+
 // <op> for a one-site operator that is the scalar values[s] on physical multiplet s
 // (number operator of HubbardFunctions.jl:316-323 evaluated as at HF:1507)
 int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out) {

@@ -541,6 +541,15 @@ def expval_diag(AC: Tensor, values) -> float:
     return out.value
 
 
+def probe_krylov(like: Tensor, nvec: int = 30, reps: int = 20) -> dict:
+    """Device-timed Gram-Schmidt pass (multidot + multiaxpy) on vectors shaped like `like`."""
+    ms = (C.c_float * 2)()
+    by = (C.c_double * 2)()
+    L.check(lib.htn_probe_krylov(like.h, nvec, reps, ms, by), like.ctx.h)
+    return {"multidot_ms": ms[0], "multiaxpy_ms": ms[1], "multidot_GBs": by[0] / (ms[0] * 1e-3) / 1e9,
+            "multiaxpy_GBs": by[1] / (ms[1] * 1e-3) / 1e9, "nvec": nvec, "vector_bytes": by[0] / (nvec + 1)}
+
+
 def network_coefficient(sym: int, nine_labels) -> float:
     lab, plab = _i32arr(np.array(nine_labels, dtype=np.int32).reshape(9, 3))
     out = C.c_double()

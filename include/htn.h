@@ -272,6 +272,9 @@ int32_t htn_tensor_axpby(double alpha, const htn_tensor* x, double beta, htn_ten
 /* ---- test hooks --------------------------------------------------------------------- */
 /* recoupling network N(l',s',r'; l,s,r; a,b,c) of DESIGN.md (labels are int32 triples) */
 int32_t htn_network_coefficient(int32_t sym, const int32_t* nine_labels /*[9][3]*/, double* out);
+/* device-timed Gram-Schmidt pass of the Krylov solvers on vectors shaped like `like` with nvec basis
+ * vectors: ms[0] multidot, ms[1] multiaxpy (per pass), bytes[0..1] the algorithmic bytes of either */
+int32_t htn_probe_krylov(const htn_tensor* like, int32_t nvec, int32_t reps, float* ms, double* bytes);
 /* host-only: dominant eigenpair of a small upper-Hessenberg matrix (the Arnoldi inner problem) */
 int32_t htn_test_hessenberg_dominant(int32_t m, const double* H, double* theta, double* y);
 /* FP64 peak probes (dependent-free DMMA.8x8x4 / DFMA loops): TFLOP/s on the ctx device */
