@@ -237,6 +237,9 @@ void launch_qr(const QrPanel* panels, int npanels, double* A, double* R, int* st
 int gemm_max_ctas_per_sm();
 double probe_fp64(int which, int sm_count, cudaStream_t st);
 
-constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = 16;
+#ifndef HTN_BK
+#define HTN_BK 16
+#endif
+constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = HTN_BK;  // K extent of one staged chunk (16 or 32)
 
 }  // namespace htn

@@ -43,7 +43,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // grouped GEMM
 // ------------------------------------------------------------------------------------
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
+constexpr int STAGES = 64 / BK;  // 64 k-columns (64 KB) in flight per CTA: 4 x 16 or 2 x 32
 constexpr int NCONS_WARPS = 4, NPROD_WARPS = 1;
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NTHREADS = (NCONS_WARPS + NPROD_WARPS) * 32;
@@ -104,7 +104,7 @@ template <int FLEX, bool LAYB>
 __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __restrict__ as,
                                        const double* __restrict__ bs, const FragAddr& fa, int kk) {
   double fx[FLEX], ff[2];
-  const double* ap = as + fa.a_base + fa.koff[kk];
+  const double* ap = as + fa.a_base + fa.koff[kk & 3] + (kk >> 2) * 16;
   const double* bp = bs + kk * 4 * LDBS;
   if (!LAYB) {
 #pragma unroll
@@ -262,7 +262,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&rg.full[s], 2 * NPROD);     // per producer thread: one plain arrive + one cp.async arrive
+      mbar_init(&rg.full[s], NPROD + 1);     // every producer lane: one cp.async (noinc) arrive; lane 0: one plain arrive
       mbar_init(&rg.empty[s], NCONS_WARPS);  // one elected lane per consumer warp
     }
   }
@@ -336,33 +336,38 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
             }
 #undef HTN_BDST
           }
-          const int arow = lane >> 3, aseg = lane & 7;  // A: 4 rows x 8 segments per pass
+          constexpr int ASEGS = BK / 2, ARPP = 32 / ASEGS;  // 16-byte segments per A row, rows per pass
+          const int arow = lane / ASEGS, aseg = lane % ASEGS;
           {
           // ---- A operand straight from one array; rows >= mt feed only discarded outputs ----
           int bytes_k = (K - (k0 + aseg * 2)) * 8;
           bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
           const char* src = reinterpret_cast<const char*>(Ag + (long long)arow * sg.lda + k0 + aseg * 2);
-          const long long step = (long long)sg.lda * 32;  // 4 rows
-          double* dst = as + arow * LDAS + ((aseg * 2) ^ (arow << 2));  // rows q*4+arow: (row & 3) == arow
-          const int nq = (mt - arow + 3) >> 2;  // rows q*4+arow < mt
-          if (nq == BM / 4) {
+          const long long step = (long long)sg.lda * 8 * ARPP;
+          // row = q * ARPP + arow; swizzle (row & 3) << 2 applied to the low 16 k of the segment position
+          double* dstv[4 / ARPP > 0 ? 4 / ARPP : 1];
 #pragma unroll
-            for (int q = 0; q < BM / 4; ++q)
-              cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
+          for (int v = 0; v < 4 / ARPP; ++v)
+            dstv[v] = as + arow * LDAS + (((aseg * 2) & ~15) | (((aseg * 2) & 15) ^ ((((v * ARPP) + arow) & 3) << 2)));
+          const int nq = (mt - arow + ARPP - 1) / ARPP;  // rows q*ARPP+arow < mt
+          if (nq == BM / ARPP) {
+#pragma unroll
+            for (int q = 0; q < BM / ARPP; ++q)
+              cp_async16(dstv[q % (4 / ARPP)] + q * ARPP * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
           } else {
 #pragma unroll
-            for (int q = 0; q < BM / 4; ++q)
+            for (int q = 0; q < BM / ARPP; ++q)
               if (q < nq)
-                cp_async16(dst + q * 4 * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
+                cp_async16(dstv[q % (4 / ARPP)] + q * ARPP * LDAS, bytes_k ? src + q * step : reinterpret_cast<const char*>(Ag), bytes_k);
           }
           }
           }
+          cp_async_mbar_arrive(&rg.full[rg.stage]);   // fires when this lane's copies have landed
           if (lane == 0) {
             int krem = K - k0;
             rg.meta[rg.stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
+            mbar_arrive(&rg.full[rg.stage]);          // releases the meta word
           }
-          cp_async_mbar_arrive(&rg.full[rg.stage]);
-          mbar_arrive(&rg.full[rg.stage]);
           rg.advance();
         }
         sg = sg_next;

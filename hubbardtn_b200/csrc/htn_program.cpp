@@ -2,6 +2,7 @@
 #include "htn_program.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace htn {
@@ -158,7 +159,7 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
   // split-K: a reduce task has few tiles but a K loop over every (level, sector) pair; cut the
   // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy of
   // the output block (summed in fixed order by the mix => deterministic, no atomics)
-  const int SPLIT_CHUNKS = 40, SPLIT_MAX = 32;
+  const int SPLIT_CHUNKS = 640 / GEMM_BK, SPLIT_MAX = 32;
   Stage st;
   st.kind = 0;
   st.tag = tag_gemm;
@@ -271,7 +272,9 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
       base = 0;
     }
   };
-  const int cap = ctx->sm_count * gemm_max_ctas_per_sm();
+  int per_sm = gemm_max_ctas_per_sm();
+  if (const char* e = getenv("HTN_GEMM_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // occupancy experiments
+  const int cap = ctx->sm_count * per_sm;
   int32_t rc;
   for (Stage& st : stages) {
     if (st.kind == 0) {
