@@ -213,13 +213,18 @@ struct Idmrg {
     int32_t rc = htn_tensor_create_mps2(ctx, &A1->s0, &A1->legs, &A2->legs, &A2->s1, &x2);
     if (rc == HTN_OK) rc = htn_contract_two_site(A1, A2, x2);
     if (rc == HTN_OK) rc = htn_tensor_create_like(x2, &y2);
-    if (rc == HTN_OK) rc = htn_plan_heff_ac2(ctx, GL[i], W[i], W[j], GR[j], x2, &p);
-    if (rc == HTN_OK) {
-      ApplyFn op = [&](const double* a, double* b) -> int32_t { return htn_heff_run(p, a, b, 0xF); };
-      KrylovInfo info;
-      rc = lanczos_lowest(x2, op, x2->d, y2->d, krylovdim, eig_tol, 3, &info);
-      applies += info.applies;
-      if (rc > 0) rc = HTN_OK;
+    if (krylovdim <= 0) {
+      // truncation-only sweep (MPSKit `changebonds(psi, SvdCut(trscheme))`): no eigensolve, x2 is split as is
+      if (rc == HTN_OK) rc = t_copy(x2, y2);
+    } else {
+      if (rc == HTN_OK) rc = htn_plan_heff_ac2(ctx, GL[i], W[i], W[j], GR[j], x2, &p);
+      if (rc == HTN_OK) {
+        ApplyFn op = [&](const double* a, double* b) -> int32_t { return htn_heff_run(p, a, b, 0xF); };
+        KrylovInfo info;
+        rc = lanczos_lowest(x2, op, x2->d, y2->d, krylovdim, eig_tol, 3, &info);
+        applies += info.applies;
+        if (rc > 0) rc = HTN_OK;
+      }
     }
     if (rc == HTN_OK) rc = htn_tsvd(y2, cut, maxdim, &Vm, al, c, ar, nullptr, nullptr);
     if (rc == HTN_OK) rc = t_normalize(*c, (*c)->d);

@@ -186,6 +186,12 @@ class Tensor:
         L.check(lib.htn_tensor_transpose(self.h, dst.h, 1 if weighted else 0), self.ctx.h)
         return dst
 
+    def like_copy(self) -> "Tensor":
+        """New tensor with the same structure AND data (device-to-device)."""
+        t = self.like()
+        t.axpby(1.0, self, 0.0)
+        return t
+
     # -- data movement -------------------------------------------------------------------
     def upload(self, packed: np.ndarray):
         packed = np.ascontiguousarray(packed, dtype=np.float64)
@@ -511,6 +517,14 @@ def idmrg2(ctx: Context, AL, AR, Cs, AC, Ws, cut=1e-2, tol=1e-6, maxiter=100, kr
     L.check(rc, ctx.h)
     return out[0], out[1], out[2], out[3], dict(converged=rc == 0, delta=delta.value, iterations=it.value,
                                                  log=log[:it.value])
+
+
+def changebonds_svdcut(ctx: Context, AL, AR, Cs, AC, Ws, cut=0.0, maxdim=0, sym=0):
+    """`changebonds(psi, SvdCut(trscheme))` (HF:1013,1018,1365): one truncation-only two-site sweep (every
+    bond is re-split by the truncated SVD, no eigensolve), then the gauge fixing of `InfiniteMPS(psi.AR)`.
+    Returns new (AL, AR, C, AC)."""
+    AL, AR, Cs, AC, _ = idmrg2(ctx, AL, AR, Cs, AC, Ws, cut=cut, tol=0.0, maxiter=1, krylovdim=0, maxdim=maxdim)
+    return uniform_from_right(ctx, AR, Cs[-1], sym)
 
 
 def mixed_gauge(ctx: Context, AL, C_guess: Tensor, AR, Cs, AC, tol=1e-12, maxiter=10000, from_right=False):

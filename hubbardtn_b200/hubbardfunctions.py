@@ -8,6 +8,7 @@ parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
     initialize_mps(H, P, max_dimension, spin)                           HF:917-959
     compute_groundstate(simul; tol, verbosity, maxiter)                 HF:993-1030
     produce_groundstate(simul; force)                                   HF:1145-1166 (in-memory cache only)
+    TruncState(simul, trunc_dim; trunc_scheme=1)                        HF:1351-1387 (SvdCut scheme)
     dim_state(psi)                                                      HF:1399-1405
     density_state(psi)                                                  HF:1475-1542
 
@@ -318,6 +319,35 @@ def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
     if force or key not in _CACHE:
         _CACHE[key] = compute_groundstate(simul, **kw)
     return _CACHE[key]
+
+
+def TruncState(simul: OB_Sim, trunc_dim: int, trunc_scheme: int = 1, **kw):
+    """HF:1351-1366: ground state truncated to (full) bond dimension `trunc_dim` with
+    `changebonds(psi, SvdCut(trscheme = truncdim(trunc_dim)))` (trunc_scheme 1; the VUMPSSvdCut variant,
+    scheme 0, is not mirrored).  The cap is applied to the number of kept multiplets such that the full
+    dimension sum_c dim(c) n_c stays <= trunc_dim (TensorKit's truncdim counts the full dimension)."""
+    if trunc_scheme != 1:
+        raise NotImplementedError("VUMPSSvdCut truncation (HF:1363) is not mirrored yet")
+    if trunc_dim <= 0:
+        raise ValueError("trunc_dim should be a positive integer.")           # HF:1353
+    d = produce_groundstate(simul, **kw)
+    psi, H, ctx = d["groundstate"], d["ham"], d["ctx"]
+    # multiplets are kept largest-first; find the largest multiplet count whose full dimension fits
+    best = None
+    lo, hi = 1, max(sum(sp.values()) for sp in (psi.bond_space(i) for i in range(len(psi))))
+    while lo <= hi:
+        mid = (lo + hi) // 2
+        AL, AR, C, AC = dev.changebonds_svdcut(ctx, [t.like_copy() for t in psi.AL], [t.like_copy() for t in psi.AR],
+                                               [t.like_copy() for t in psi.C], [t.like_copy() for t in psi.AC], H.W,
+                                               maxdim=mid, sym=psi.sym)
+        cand = InfiniteMPS(ctx, psi.sym, AL, AR, C, AC)
+        if max(dim_state(cand)) <= trunc_dim:
+            best, lo = cand, mid + 1
+        else:
+            hi = mid - 1
+    if best is None:
+        raise ValueError("trunc_dim is smaller than the smallest non-trivial bond dimension")
+    return best
 
 
 def dim_state(psi: InfiniteMPS):

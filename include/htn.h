@@ -247,7 +247,9 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
  * In/out handle arrays: the library destroys every tensor it replaces and stores the new handle; the
  * caller destroys the final ones.  delta = || C_new - C_old || on the common subspace of the edge bond.
  * log (may be NULL): rows of 3 doubles (delta, sum of D_red over the bonds, cumulative H_AC2 applies).
- * The result is NOT yet a consistent uniform MPS: call htn_mixed_gauge (MPSKit does `InfiniteMPS(psi.AR)`). */
+ * The result is NOT yet a consistent uniform MPS: call htn_mixed_gauge (MPSKit does `InfiniteMPS(psi.AR)`).
+ * krylovdim <= 0 skips the eigensolves: one such iteration is the truncation-only sweep of
+ * `changebonds(psi, SvdCut(trscheme = truncdim(D) | truncbelow(cut)))` (HubbardFunctions.jl:1013,1018,1365). */
 int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** AR, htn_tensor** C, htn_tensor** AC,
                    const htn_mpo* const* W, double cut, double tol, int32_t maxiter, int32_t krylovdim, double eig_tol,
                    int32_t maxdim, double* delta, int32_t* iterations, double* log, int32_t log_cap);

@@ -29,3 +29,24 @@ def test_energy_matches_reference_golden(ctx, idx):
     assert all(isinstance(d, int) and d > 0 for d in D)
     n = hf.density_state(psi)
     assert abs(sum(n) / len(n) - g["P"] / g["Q"]) < 1e-8
+
+
+def test_truncstate_tools(ctx):
+    """test/MB.jl:95-106 / docs 'Tools': a truncated state has bond dimension <= trunc_dim, is still a
+    normalised uniform MPS with conserved filling, and its energy is variational (above the untruncated one)."""
+    from hubbardtn_b200 import device as dev
+    model = hf.OB_Sim([1.0], [5.0], 0.0, [0.0], 1, 1, 2.5)
+    d = hf.produce_groundstate(model, ctx=ctx, force=True)
+    psi = d["groundstate"]
+    full = max(hf.dim_state(psi))
+    target = max(4, full // 2)
+    cut = hf.TruncState(model, target, ctx=ctx)
+    assert max(hf.dim_state(cut)) <= target < full
+    n = hf.density_state(cut)
+    assert abs(sum(n) / len(n) - 1.0) < 1e-8
+    GL, GR = hf._make_envs(ctx, cut, d["ham"])
+    e = dev.environments(ctx, cut.AL, cut.AR, cut.C, d["ham"].W, GL, GR, tol=1e-12)
+    E_cut = 0.5 * (e["energy_cell_left"] + e["energy_cell_right"]) / 2
+    assert E_cut > d["energy"] - 1e-10 and E_cut < d["energy"] + 0.05
+    with pytest.raises(ValueError):
+        hf.TruncState(model, 0, ctx=ctx)
