@@ -75,7 +75,7 @@ int32_t htn_ctx_create(int32_t device, htn_ctx** out) {
   cudaMalloc(&c->kry_scal, 1024 * sizeof(double));
   cudaMallocHost(&c->kry_scal_host, 1024 * sizeof(double));
   cudaMalloc(&c->d_status, sizeof(int));
-  cudaMemset(c->d_status, 0, sizeof(int));
+  cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
   *out = c;
   return HTN_OK;
 }

@@ -69,7 +69,7 @@ int32_t inv_diag(htn_ctx* ctx, const htn_tensor* C, htn_tensor** out) {
   FillBlock* d = nullptr;
   if (fb.empty()) return HTN_OK;
   if (cudaMalloc(&d, fb.size() * sizeof(FillBlock)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "idmrg2: table allocation failed");
-  cudaMemcpy(d, fb.data(), fb.size() * sizeof(FillBlock), cudaMemcpyHostToDevice);
+  htn::h2d_on_stream(d, fb.data(), fb.size() * sizeof(FillBlock), ctx->stream);
   launch_diag_inv(d, (int)fb.size(), C->d, (*out)->d, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(d);

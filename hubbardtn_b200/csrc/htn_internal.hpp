@@ -32,6 +32,16 @@ double cg_su2(int tj1, int tm1, int tj2, int tm2, int tj3, int tm3);
 double network(int sym, Sector lp, Sector sp, Sector rp, Sector l, Sector s, Sector r, Sector a,
                Sector b, Sector c);
 
+// Host -> device table upload ORDERED ON THE LIBRARY STREAM.  A plain cudaMemcpy runs on the legacy
+// default stream, which does not synchronise with the (non-blocking) library stream, and returns
+// before the DMA of a small pageable buffer has landed: a kernel launched right after could read a
+// half-written table.  Returns after the copy has completed (the host buffer may be freed).
+inline cudaError_t h2d_on_stream(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
 inline int even_up(int x) { return (x + 1) & ~1; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -40,7 +40,7 @@ static int32_t cached_table(htn_tensor* owner, const void* partner, int mode, co
   T* d = nullptr;
   if (!host.empty()) {
     if (cudaMalloc(&d, host.size() * sizeof(T)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "device table allocation failed");
-    cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+    h2d_on_stream(d, host.data(), host.size() * sizeof(T), ctx->stream);
   }
   owner->devtables[key] = {d, (int)host.size()};
   *dev = d;

@@ -93,7 +93,7 @@ int32_t to_device(htn_ctx* ctx, const std::vector<T>& v, T** out) {
   if (v.empty()) return HTN_OK;
   cudaError_t e = cudaMalloc(out, v.size() * sizeof(T));
   if (e != cudaSuccess) return ctx->fail(HTN_ERR_OOM, std::string("cudaMalloc(program table): ") + cudaGetErrorString(e));
-  e = cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  e = h2d_on_stream(*out, v.data(), v.size() * sizeof(T), ctx->stream);
   if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("cudaMemcpy(program table): ") + cudaGetErrorString(e));
   return HTN_OK;
 }
@@ -265,7 +265,7 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
     ws = nullptr;
     return ctx->fail(HTN_ERR_OOM, "program workspace allocation failed");
   }
-  cudaMemset(ws, 0, ws_elems * sizeof(double));
+  cudaMemsetAsync(ws, 0, ws_elems * sizeof(double), ctx->stream);  // ordered before the first run on this stream
   auto fix = [&](long long& off, int& base) {
     if (base == -1) {
       off = reinterpret_cast<long long>(ws + off);

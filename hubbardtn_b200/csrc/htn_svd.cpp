@@ -9,6 +9,8 @@
 // `maxdim` multiplets (largest first).  Only the singular values travel to the host.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 
 #include "htn_linalg.hpp"
@@ -61,6 +63,13 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
     if (Vm) htn_space_destroy(Vm);
     return ctx->fail(code, msg);
   };
+  const bool dbg = getenv("HTN_DEBUG_SYNC") != nullptr;
+  auto dbg_sync = [&](const char* what) {
+    if (!dbg) return;
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "tsvd debug: %s -> %s\n", what, cudaGetErrorString(e));
+  };
+  dbg_sync("entry (kernels queued before tsvd)");
   try {
     // ---- panels ----
     std::map<int, PanelInfo> pm;
@@ -135,17 +144,37 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
     auto upload_tiles = [&](const std::vector<TrBlock>& v, TrBlock** d) -> bool {
       if (v.empty()) return true;
       if (cudaMalloc(d, v.size() * sizeof(TrBlock)) != cudaSuccess) return false;
-      return cudaMemcpy(*d, v.data(), v.size() * sizeof(TrBlock), cudaMemcpyHostToDevice) == cudaSuccess;
+      return h2d_on_stream(*d, v.data(), v.size() * sizeof(TrBlock), st) == cudaSuccess;
     };
     if (!upload_tiles(tT, &dT1) || !upload_tiles(tC, &dT2)) return fail(HTN_ERR_OOM, "tsvd: table allocation failed");
+    if (dbg) {
+      fprintf(stderr, "tsvd debug: x2 dsize %lld blocks %zu totG %lld totQ %lld tiles T %zu C %zu\n", (long long)x2->dsize,
+              x2->blocks.size(), (long long)totG, (long long)totQ, tT.size(), tC.size());
+      for (PanelInfo* p : panels)
+        fprintf(stderr, "   panel m=%d nrow=%d ncol=%d k=%d len=%d ldg=%d offG=%lld u_in_g=%d\n", p->m, p->nrow, p->ncol, p->k, p->len,
+                p->ldg, (long long)p->offG, (int)p->u_in_g);
+      long long maxs = 0, maxd = 0;
+      for (const TrBlock& t : tT) {
+        maxs = std::max(maxs, t.soff + (long long)(t.rows - 1) * t.lds + t.cols);
+        maxd = std::max(maxd, t.doff + (long long)(t.cols - 1) * t.ldd + t.rows);
+      }
+      fprintf(stderr, "   transposing tiles: max src end %lld (dsize %lld)  max dst end %lld (totG %lld)\n", maxs, (long long)x2->dsize, maxd,
+              (long long)totG);
+    }
     launch_transpose(dT1, (int)tT.size(), x2->d, dG, st);
+    dbg_sync("gather (transposing tiles)");
     launch_copy2d(dT2, (int)tC.size(), x2->d, dG, st);
+    dbg_sync("gather (straight tiles)");
     // ---- Jacobi ----
     std::vector<SvdPanel> sp;
     for (PanelInfo* p : panels) sp.push_back(SvdPanel{p->offG, p->offQ, p->offS, p->k, p->len, p->ldg, p->ldq, p->u_in_g ? 1 : 0, 0});
     if (cudaMalloc(&dP, sp.size() * sizeof(SvdPanel)) != cudaSuccess) return fail(HTN_ERR_OOM, "tsvd: table allocation failed");
-    cudaMemcpy(dP, sp.data(), sp.size() * sizeof(SvdPanel), cudaMemcpyHostToDevice);
+    h2d_on_stream(dP, sp.data(), sp.size() * sizeof(SvdPanel), st);
     launch_svd(dP, (int)sp.size(), dG, dQ, dG2, dQ2, dS, ctx->d_status, st);
+    if (dbg) {
+      dbg_sync("jacobi");
+      for (PanelInfo* p : panels) fprintf(stderr, "   panel m=%d k=%d len=%d u_in_g=%d\n", p->m, p->k, p->len, (int)p->u_in_g);
+    }
     std::vector<double> sig(totS);
     int status = 0;
     cudaMemcpyAsync(sig.data(), dS, totS * 8, cudaMemcpyDeviceToHost, st);
@@ -265,7 +294,7 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
       if (v.empty()) return true;
       TrBlock* d = nullptr;
       if (cudaMalloc(&d, v.size() * sizeof(TrBlock)) != cudaSuccess) return false;
-      cudaMemcpy(d, v.data(), v.size() * sizeof(TrBlock), cudaMemcpyHostToDevice);
+      h2d_on_stream(d, v.data(), v.size() * sizeof(TrBlock), st);
       if (transpose)
         launch_transpose(d, (int)v.size(), src, dst, st);
       else
