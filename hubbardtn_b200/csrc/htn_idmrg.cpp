@@ -8,6 +8,7 @@
 // environments and contraction programs are re-planned on the host per step; all block data stay in
 // HBM (only singular values and a few scalars travel).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -151,6 +152,12 @@ struct Idmrg {
   double eig_tol, cut;
   int maxdim;
   long applies = 0;
+  double t_plan = 0, t_eig = 0, t_svd = 0, t_env = 0;  // seconds (stream-synchronised phase timers)
+
+  double now() {
+    cudaStreamSynchronize(ctx->stream);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
 
   ~Idmrg() {
     for (htn_tensor* t : GL) htn_tensor_destroy(t);
@@ -164,6 +171,12 @@ struct Idmrg {
 
   // GL of site i+1 from site i
   int32_t grow_left(int i) {
+    const double t0 = now();
+    struct Acc {
+      Idmrg* d;
+      double t0;
+      ~Acc() { d->t_env += d->now() - t0; }
+    } acc{this, t0};
     const int j = (i + 1) % L;
     htn_tensor *At = nullptr, *nw = nullptr;
     htn_plan* p = nullptr;
@@ -185,6 +198,12 @@ struct Idmrg {
 
   // GR of site j-1 from site j
   int32_t grow_right(int j) {
+    const double t0 = now();
+    struct Acc {
+      Idmrg* d;
+      double t0;
+      ~Acc() { d->t_env += d->now() - t0; }
+    } acc{this, t0};
     const int i = (j + L - 1) % L;
     htn_tensor *At = nullptr, *nw = nullptr;
     htn_plan* p = nullptr;
@@ -210,6 +229,7 @@ struct Idmrg {
     htn_tensor *x2 = nullptr, *y2 = nullptr;
     htn_plan* p = nullptr;
     htn_space* Vm = nullptr;
+    const double t0 = now();
     int32_t rc = htn_tensor_create_mps2(ctx, &A1->s0, &A1->legs, &A2->legs, &A2->s1, &x2);
     if (rc == HTN_OK) rc = htn_contract_two_site(A1, A2, x2);
     if (rc == HTN_OK) rc = htn_tensor_create_like(x2, &y2);
@@ -218,6 +238,8 @@ struct Idmrg {
       if (rc == HTN_OK) rc = t_copy(x2, y2);
     } else {
       if (rc == HTN_OK) rc = htn_plan_heff_ac2(ctx, GL[i], W[i], W[j], GR[j], x2, &p);
+      const double t1 = now();
+      t_plan += t1 - t0;
       if (rc == HTN_OK) {
         ApplyFn op = [&](const double* a, double* b) -> int32_t { return htn_heff_run(p, a, b, 0xF); };
         KrylovInfo info;
@@ -225,9 +247,12 @@ struct Idmrg {
         applies += info.applies;
         if (rc > 0) rc = HTN_OK;
       }
+      t_eig += now() - t1;
     }
+    const double t2 = now();
     if (rc == HTN_OK) rc = htn_tsvd(y2, cut, maxdim, &Vm, al, c, ar, nullptr, nullptr);
     if (rc == HTN_OK) rc = t_normalize(*c, (*c)->d);
+    t_svd += now() - t2;
     cudaStreamSynchronize(ctx->stream);
     if (p) htn_plan_destroy(p);
     if (x2) htn_tensor_destroy(x2);
@@ -258,7 +283,8 @@ struct Idmrg {
 extern "C" {
 
 // In/out: AL, AR, C, AC handle arrays (the driver destroys the tensors it replaces and stores the new
-// handles; the caller destroys the final ones).  log rows: (eps, sum of D_red over bonds, H_AC2 applies).
+// handles; the caller destroys the final ones).  log rows of 8 doubles: eps, sum of D_red over bonds, cumulative
+// H_AC2 applies, cumulative seconds in planning / Lanczos / SVD / environment growth, 0.
 int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** AR, htn_tensor** C, htn_tensor** AC,
                    const htn_mpo* const* W, double cut, double tol, int32_t maxiter, int32_t krylovdim, double eig_tol,
                    int32_t maxdim, double* delta, int32_t* iterations, double* log, int32_t log_cap) {
@@ -381,9 +407,15 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
         double dsum = 0;
         for (int i = 0; i < L; ++i)
           for (int m : D.C[i]->s0.mult) dsum += m;
-        log[3 * (it - 1)] = eps;
-        log[3 * (it - 1) + 1] = dsum;
-        log[3 * (it - 1) + 2] = (double)D.applies;
+        double* row = log + 8 * (it - 1);
+        row[0] = eps;
+        row[1] = dsum;
+        row[2] = (double)D.applies;
+        row[3] = D.t_plan;  // cumulative seconds: tensors + two-site contraction + H_AC2 planning (host)
+        row[4] = D.t_eig;   // Lanczos
+        row[5] = D.t_svd;   // truncated SVD
+        row[6] = D.t_env;   // environment growth (planning + transfers)
+        row[7] = 0.0;
       }
       if (eps < tol) break;
     }

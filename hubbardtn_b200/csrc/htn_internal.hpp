@@ -228,8 +228,9 @@ struct SvdPanel {
   long long offG, offQ, offS;
   int k, len, ldg, ldq, u_in_g, pad_;
 };
-void launch_svd(const SvdPanel* panels, int npanels, double* G, double* Q, double* G2, double* Q2, double* sig,
-                int* status, cudaStream_t st);
+// returns 0 ok, 1 sweeps did not converge, < 0 CUDA / allocation failure
+int launch_svd(const SvdPanel* panels_dev, const SvdPanel* panels_host, int npanels, double* G, double* Q, double* G2,
+               double* Q2, double* sig, cudaStream_t st);
 // set blocks to 0 (mode 0) or to the unit matrix (mode 1): table entries (off, rows, cols, ld)
 struct FillBlock {
   long long off;

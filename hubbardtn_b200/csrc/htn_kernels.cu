@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 
 #include "htn_internal.hpp"
 
@@ -817,87 +818,87 @@ void launch_copy2d(const TrBlock* tiles, int ntiles, const double* src, double* 
 }
 
 // ------------------------------------------------------------------------------------
-// One-sided Jacobi SVD (Hestenes) of row panels, one CTA per panel (replaces LAPACK gesdd/gesvd
-// behind TensorKit `tsvd!`).  The k rows of G (length len) are rotated pairwise
-// until mutually orthogonal; the same rotations accumulate in Q (k x k, starts as identity):
-//   G_final = Q G_0 = diag(sigma) W^T .
-// Output (sorted by descending sigma, sign-fixed so that the largest entry of every LEFT singular
-// vector is positive): sig[k], G2 = W^T (unit rows), Q2 = Q.  High relative accuracy; tournament
-// ordering gives k/2 independent rotations per round, one warp per pair.
+// One-sided Jacobi SVD kernels (see launch_svd below): tournament ordering gives k/2 independent
+// rotations per round, one warp per rotation pair.
 // ------------------------------------------------------------------------------------
 constexpr int SVD_WARPS = 16;
 
-__global__ void __launch_bounds__(32 * SVD_WARPS)
-svd_jacobi_kernel(const SvdPanel* __restrict__ panels, double* __restrict__ Gb, double* __restrict__ Qb,
-                  double* __restrict__ G2b, double* __restrict__ Q2b, double* __restrict__ sigb, int* __restrict__ status) {
+// Q = identity for every panel
+__global__ void __launch_bounds__(256) svd_init_kernel(const SvdPanel* __restrict__ panels, double* __restrict__ Qb) {
   const SvdPanel P = panels[blockIdx.x];
-  double* G = Gb + P.offG;
   double* Q = Qb + P.offQ;
+  for (int e = threadIdx.x; e < P.k * P.ldq; e += blockDim.x) Q[e] = (e / P.ldq == e % P.ldq) ? 1.0 : 0.0;
+}
+
+// One tournament round for ALL panels: entry e = (panel, pair slot j); one warp per rotation pair, so a
+// round exposes sum_p k_p / 2 independent rotations to the whole GPU (a single CTA per panel left 147 SMs
+// idle on the largest coupled block, which dominates: profiles/r1c notes).  nrot[panel] counts rotations.
+__global__ void __launch_bounds__(256)
+svd_round_kernel(const SvdPanel* __restrict__ panels, const int2* __restrict__ entries, int nentries, int round,
+                 double* __restrict__ Gb, double* __restrict__ Qb, int* __restrict__ nrot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 8 + warp;
+  if (e >= nentries) return;
+  const int2 en = entries[e];
+  const SvdPanel P = panels[en.x];
+  const int k = P.k, len = P.len, ldg = P.ldg, ldq = P.ldq;
+  const int kk = (k + 1) & ~1, n1 = kk - 1, j = en.y;
+  if (round >= n1) return;
+  int p = j == 0 ? round : (round + j) % n1;
+  int q = j == 0 ? n1 : (round - j + n1) % n1;
+  if (p > q) {
+    const int t = p;
+    p = q;
+    q = t;
+  }
+  if (q >= k) return;
+  double* gp = Gb + P.offG + (long long)p * ldg;
+  double* gq = Gb + P.offG + (long long)q * ldg;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int i = lane; i < len; i += 32) {
+    const double x = gp[i], y = gq[i];
+    a = fma(x, x, a);
+    b = fma(y, y, b);
+    c = fma(x, y, c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const double tol = fmax(1e-15, 5e-16 * sqrt((double)len));
+  if (a == 0.0 || b == 0.0 || fabs(c) <= tol * sqrt(a * b)) return;
+  const double zeta = (b - a) / (2.0 * c);
+  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+  for (int i = lane; i < len; i += 32) {
+    const double x = gp[i], y = gq[i];
+    gp[i] = cs * x - sn * y;
+    gq[i] = sn * x + cs * y;
+  }
+  double* qp = Qb + P.offQ + (long long)p * ldq;
+  double* qq = Qb + P.offQ + (long long)q * ldq;
+  for (int i = lane; i < k; i += 32) {
+    const double x = qp[i], y = qq[i];
+    qp[i] = cs * x - sn * y;
+    qq[i] = sn * x + cs * y;
+  }
+  if (lane == 0) atomicAdd(nrot + en.x, 1);
+}
+
+// singular values, descending sort, normalisation and sign fix per panel (one CTA per panel)
+__global__ void __launch_bounds__(32 * SVD_WARPS)
+svd_finish_kernel(const SvdPanel* __restrict__ panels, const double* __restrict__ Gb, const double* __restrict__ Qb,
+                  double* __restrict__ G2b, double* __restrict__ Q2b, double* __restrict__ sigb) {
+  const SvdPanel P = panels[blockIdx.x];
+  const double* G = Gb + P.offG;
+  const double* Q = Qb + P.offQ;
   double* G2 = G2b + P.offG;
   double* Q2 = Q2b + P.offQ;
   double* sig = sigb + P.offS;
   const int k = P.k, len = P.len, ldg = P.ldg, ldq = P.ldq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ int nrot;
   __shared__ double ssig[1024];
-  // Q = identity
-  for (int e = threadIdx.x; e < k * ldq; e += blockDim.x) Q[e] = (e / ldq == e % ldq) ? 1.0 : 0.0;
-  __syncthreads();
-  const int kk = (k + 1) & ~1, n1 = kk - 1;
-  const double tol = fmax(1e-15, 5e-16 * sqrt((double)len));
-  bool converged = k < 2;
-  for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
-    if (threadIdx.x == 0) nrot = 0;
-    __syncthreads();
-    for (int r = 0; r < n1; ++r) {
-      for (int j = warp; j < kk / 2; j += SVD_WARPS) {
-        int p = j == 0 ? r : (r + j) % n1;
-        int q = j == 0 ? n1 : (r - j + n1) % n1;
-        if (p > q) {
-          const int t = p;
-          p = q;
-          q = t;
-        }
-        if (q >= k) continue;
-        double* gp = G + (long long)p * ldg;
-        double* gq = G + (long long)q * ldg;
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int e = lane; e < len; e += 32) {
-          const double x = gp[e], y = gq[e];
-          a = fma(x, x, a);
-          b = fma(y, y, b);
-          c = fma(x, y, c);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b += __shfl_xor_sync(0xffffffffu, b, o);
-          c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
-        if (a == 0.0 || b == 0.0 || fabs(c) <= tol * sqrt(a * b)) continue;
-        const double zeta = (b - a) / (2.0 * c);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-        for (int e = lane; e < len; e += 32) {
-          const double x = gp[e], y = gq[e];
-          gp[e] = cs * x - sn * y;
-          gq[e] = sn * x + cs * y;
-        }
-        double* qp = Q + (long long)p * ldq;
-        double* qq = Q + (long long)q * ldq;
-        for (int e = lane; e < k; e += 32) {
-          const double x = qp[e], y = qq[e];
-          qp[e] = cs * x - sn * y;
-          qq[e] = sn * x + cs * y;
-        }
-        if (lane == 0) atomicAdd(&nrot, 1);
-      }
-      __syncthreads();
-    }
-    converged = nrot == 0;
-    __syncthreads();
-  }
-  if (!converged && threadIdx.x == 0) atomicOr(status, 2);
-  // singular values
   for (int i = warp; i < k; i += SVD_WARPS) {
     const double* gi = G + (long long)i * ldg;
     double a = 0.0;
@@ -906,7 +907,6 @@ svd_jacobi_kernel(const SvdPanel* __restrict__ panels, double* __restrict__ Gb, 
     if (lane == 0) ssig[i] = sqrt(a);
   }
   __syncthreads();
-  // sorted, normalised, sign-fixed output
   for (int i = warp; i < k; i += SVD_WARPS) {
     const double si = ssig[i];
     int rank = 0;
@@ -942,9 +942,54 @@ svd_jacobi_kernel(const SvdPanel* __restrict__ panels, double* __restrict__ Gb, 
   }
 }
 
-void launch_svd(const SvdPanel* panels, int npanels, double* G, double* Q, double* G2, double* Q2, double* sig,
-                int* status, cudaStream_t st) {
-  if (npanels > 0) svd_jacobi_kernel<<<npanels, 32 * SVD_WARPS, 0, st>>>(panels, G, Q, G2, Q2, sig, status);
+// One-sided Jacobi SVD (Hestenes) of row panels (replaces LAPACK gesdd/gesvd behind TensorKit `tsvd!`;
+// SURVEY.md 8(a) a9).  The k rows of G (length len) are rotated pairwise until mutually orthogonal; the
+// same rotations accumulate in Q (k x k, starts as identity):  G_final = Q G_0 = diag(sigma) W^T.
+// Output (sorted by descending sigma, sign-fixed so that the largest entry of every LEFT singular vector
+// is positive): sig[k], G2 = W^T (unit rows), Q2 = Q.  High relative accuracy.  Host-steered: one launch
+// per tournament round over all panels, one readback of the rotation counters per sweep.
+int launch_svd(const SvdPanel* panels_dev, const SvdPanel* panels_host, int npanels, double* G, double* Q, double* G2,
+               double* Q2, double* sig, cudaStream_t st) {
+  if (npanels <= 0) return 0;
+  std::vector<int2> entries;
+  int max_n1 = 0;
+  for (int p = 0; p < npanels; ++p) {
+    const int kk = (panels_host[p].k + 1) & ~1;
+    max_n1 = std::max(max_n1, kk - 1);
+    if (panels_host[p].k >= 2)
+      for (int j = 0; j < kk / 2; ++j) entries.push_back(make_int2(p, j));
+  }
+  int2* d_entries = nullptr;
+  int* d_nrot = nullptr;
+  int rc = 0;
+  svd_init_kernel<<<npanels, 256, 0, st>>>(panels_dev, Q);
+  if (!entries.empty()) {
+    if (cudaMalloc(&d_entries, entries.size() * sizeof(int2)) != cudaSuccess ||
+        cudaMalloc(&d_nrot, npanels * sizeof(int)) != cudaSuccess) {
+      cudaFree(d_entries);
+      return -1;
+    }
+    h2d_on_stream(d_entries, entries.data(), entries.size() * sizeof(int2), st);
+    const int ne = (int)entries.size(), grid = (ne + 7) / 8;
+    std::vector<int> nrot(npanels);
+    bool converged = false;
+    for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
+      cudaMemsetAsync(d_nrot, 0, npanels * sizeof(int), st);
+      for (int r = 0; r < max_n1; ++r) svd_round_kernel<<<grid, 256, 0, st>>>(panels_dev, d_entries, ne, r, G, Q, d_nrot);
+      cudaMemcpyAsync(nrot.data(), d_nrot, npanels * sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) {
+        rc = -2;
+        break;
+      }
+      converged = true;
+      for (int v : nrot) converged = converged && v == 0;
+    }
+    if (rc == 0 && !converged) rc = 1;
+    cudaFree(d_entries);
+    cudaFree(d_nrot);
+  }
+  if (rc >= 0) svd_finish_kernel<<<npanels, 32 * SVD_WARPS, 0, st>>>(panels_dev, G, Q, G2, Q2, sig);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------

@@ -170,20 +170,16 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
     for (PanelInfo* p : panels) sp.push_back(SvdPanel{p->offG, p->offQ, p->offS, p->k, p->len, p->ldg, p->ldq, p->u_in_g ? 1 : 0, 0});
     if (cudaMalloc(&dP, sp.size() * sizeof(SvdPanel)) != cudaSuccess) return fail(HTN_ERR_OOM, "tsvd: table allocation failed");
     h2d_on_stream(dP, sp.data(), sp.size() * sizeof(SvdPanel), st);
-    launch_svd(dP, (int)sp.size(), dG, dQ, dG2, dQ2, dS, ctx->d_status, st);
+    const int svd_rc = launch_svd(dP, sp.data(), (int)sp.size(), dG, dQ, dG2, dQ2, dS, st);
+    if (svd_rc < 0) return fail(HTN_ERR_CUDA, "tsvd: Jacobi launch failed");
+    if (svd_rc > 0) return fail(HTN_ERR_INVALID, "tsvd: Jacobi sweeps did not converge");
     if (dbg) {
       dbg_sync("jacobi");
       for (PanelInfo* p : panels) fprintf(stderr, "   panel m=%d k=%d len=%d u_in_g=%d\n", p->m, p->k, p->len, (int)p->u_in_g);
     }
     std::vector<double> sig(totS);
-    int status = 0;
     cudaMemcpyAsync(sig.data(), dS, totS * 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return fail(HTN_ERR_CUDA, std::string("tsvd: ") + cudaGetErrorString(cudaGetLastError()));
-    if (status & 2) {
-      cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st);
-      return fail(HTN_ERR_INVALID, "tsvd: Jacobi sweeps did not converge");
-    }
     // ---- global truncation (oracle/twosite.py:tsvd) ----
     struct SV {
       double s;

@@ -502,7 +502,7 @@ def idmrg2(ctx: Context, AL, AR, Cs, AC, Ws, cut=1e-2, tol=1e-6, maxiter=100, kr
     lists = [list(AL), list(AR), list(Cs), list(AC)]
     arrs = [_harr(x) for x in lists]
     delta, it = C.c_double(), C.c_int32()
-    log = np.zeros((maxiter, 3))
+    log = np.zeros((maxiter, 8))
     rc = lib.htn_idmrg2(ctx.h, len(AL), arrs[0], arrs[1], arrs[2], arrs[3], _harr(Ws), cut, tol, maxiter, krylovdim,
                         eig_tol, maxdim, C.byref(delta), C.byref(it), log.ctypes.data_as(C.POINTER(C.c_double)), maxiter)
     out = []

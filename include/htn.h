@@ -246,7 +246,8 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
  * re-defined by the truncated SVD (keep Schmidt values >= cut, at most maxdim multiplets if maxdim > 0).
  * In/out handle arrays: the library destroys every tensor it replaces and stores the new handle; the
  * caller destroys the final ones.  delta = || C_new - C_old || on the common subspace of the edge bond.
- * log (may be NULL): rows of 3 doubles (delta, sum of D_red over the bonds, cumulative H_AC2 applies).
+ * log (may be NULL): rows of 8 doubles (delta, sum of D_red over the bonds, cumulative H_AC2 applies, cumulative
+ * seconds in host planning / Lanczos / truncated SVD / environment growth, 0).
  * The result is NOT yet a consistent uniform MPS: call htn_mixed_gauge (MPSKit does `InfiniteMPS(psi.AR)`).
  * krylovdim <= 0 skips the eigensolves: one such iteration is the truncation-only sweep of
  * `changebonds(psi, SvdCut(trscheme = truncdim(D) | truncbelow(cut)))` (HubbardFunctions.jl:1013,1018,1365). */

@@ -26,6 +26,9 @@ AL, AR, C, AC, info1 = dev.idmrg2(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=c
 t1 = time.perf_counter()
 print("IDMRG2: %.2f s, %d iterations, delta %.2e, D_red per bond %s, applies %d"
       % (t1 - t0, info1["iterations"], info1["delta"], [sum(c.space(0, model.sym).mult) for c in C], int(info1["log"][-1][2])))
+print("   cumulative seconds: planning %.2f  lanczos %.2f  svd %.2f  env growth %.2f" % tuple(info1["log"][-1][3:7]))
+if os.environ.get("STOP_AFTER_IDMRG"):
+    sys.exit(0)
 AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], model.sym)
 t2 = time.perf_counter()
 print("mixed gauge: %.2f s" % (t2 - t1))
