@@ -739,6 +739,10 @@ int32_t htn_mpo_destroy(htn_mpo* w) {
 static bool same_structure(const htn_tensor* x, const htn_tensor* y) {
   if (x->kind != y->kind || x->sym != y->sym || x->blocks.size() != y->blocks.size() || x->dsize != y->dsize)
     return false;
+  // same layout is not enough: the tensors must live on the same graded spaces
+  if (!(x->s0.sec == y->s0.sec) || x->s0.mult != y->s0.mult || !(x->s1.sec == y->s1.sec) || x->s1.mult != y->s1.mult ||
+      !(x->legs.sec == y->legs.sec))
+    return false;
   for (size_t i = 0; i < x->blocks.size(); ++i) {
     const Block &a = x->blocks[i], &b = y->blocks[i];
     if (a.lab[0] != b.lab[0] || a.lab[1] != b.lab[1] || a.lab[2] != b.lab[2] || a.lab[3] != b.lab[3] ||
