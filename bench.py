@@ -34,8 +34,8 @@ METRIC = "H_eff (H_AC) applies/s at D=1024, U(1)xSU(2), chi=96"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--D", type=int, default=1024)
     ap.add_argument("--chi", type=int, default=96)
@@ -199,7 +199,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -300,7 +300,7 @@ def main():
     value = world * args.steps / (ms_max * 1e-3)
 
     # ---- per-stage times (dominant kernel = grouped_gemm_kernel, stages L and R) -----------
-    prof = plan.profile(x, y, reps=max(5, min(args.steps, 50)))
+    prof = plan.profile(x, y, reps=max(5, min(args.steps, 100)))
     gemm_ms = prof["stage_L_ms"] + prof["stage_R_ms"]
     achieved = st["flops"] / (gemm_ms * 1e-3) / 1e12
 

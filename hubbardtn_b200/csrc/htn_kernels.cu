@@ -600,12 +600,34 @@ multidot_partial_kernel(const DevBlock* __restrict__ blocks, const int* __restri
   const int n = nr * B.ld;  // pads are zero in every vector
   __shared__ double sh[MD_MAXVEC][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = 0; j < nvec; ++j) {
-    const double* vj = V + (long long)j * stride + base;
-    double acc = 0.0;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) acc = fma(vj[e], w[base + e], acc);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) sh[j][warp] = acc;
+  // eight basis vectors at a time: every element of w is read once per group and meets eight
+  // independent loads (memory-level parallelism), instead of one dependent pass per vector
+  for (int g0 = 0; g0 < nvec; g0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    const int ng = min(8, nvec - g0);
+    const double* vg = V + (long long)g0 * stride + base;
+    if (ng == 8) {
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double wv = w[base + e];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fma(vg[(long long)q * stride + e], wv, acc[q]);
+      }
+    } else {
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double wv = w[base + e];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < ng) acc[q] = fma(vg[(long long)q * stride + e], wv, acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double a = acc[q];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+      if (lane == 0 && q < ng) sh[g0 + q][warp] = a;
+    }
   }
   __syncthreads();
   if (threadIdx.x < nvec) {
