@@ -208,7 +208,7 @@ static int32_t finalize_tensor(htn_tensor* t) {
   for (size_t i = 0; i < t->blocks.size(); ++i) {
     const Block& b = t->blocks[i];
     db[i] = DevBlock{b.off, b.hoff, b.rows, b.cols, b.ld, b.weight};
-    int rows_per = std::max(1, 4096 / std::max(1, b.ld));
+    int rows_per = std::max(1, 1024 / std::max(1, b.ld));  // ~1k elements per CTA: enough CTAs to fill 148 SMs at 3 MB vectors
     for (int r0 = 0; r0 < b.rows; r0 += rows_per) {
       chunks.push_back((int)i);
       chunks.push_back(r0);
