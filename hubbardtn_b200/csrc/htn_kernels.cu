@@ -45,7 +45,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ------------------------------------------------------------------------------------
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
 constexpr int STAGES = 64 / BK;  // 64 k-columns (64 KB) in flight per CTA: 4 x 16 or 2 x 32
-constexpr int NCONS_WARPS = 4, NPROD_WARPS = 1;
+#ifndef HTN_NPROD
+#define HTN_NPROD 1
+#endif
+constexpr int NCONS_WARPS = 4, NPROD_WARPS = HTN_NPROD;  // 2: one warp stages B, the other A (experiment)
 constexpr int NPROD = NPROD_WARPS * 32;
 constexpr int NTHREADS = (NCONS_WARPS + NPROD_WARPS) * 32;
 // Shared-memory tiles are UNPADDED and XOR-swizzled in units of 4 doubles (32 B):
@@ -245,7 +248,7 @@ __device__ __forceinline__ void consume_dispatch(int flex, const GemmItem& item,
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 3)
+__global__ void __launch_bounds__(NTHREADS, NPROD_WARPS == 1 ? 3 : 2)
 grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
                     const __grid_constant__ Bases bases, int dbg, int nsm) {
   extern __shared__ __align__(16) double smem[];
@@ -309,7 +312,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           if (!(dbg & 2)) {  // timing experiment HTN_GEMM_DEBUG=2: no operand loads
           // ---- B operand: 16 x 64 chunk: lane = 16-byte segment of a row, q = row ---------
           // (columns >= nt feed only discarded outputs: loaded only up to the tile extent)
-          {
+          if (NPROD_WARPS == 1 || warp == NCONS_WARPS) {
             int bytes_row = (nt - lane * 2) * 8;
             bytes_row = bytes_row < 0 ? 0 : (bytes_row > 16 ? 16 : bytes_row);
             const char* src = reinterpret_cast<const char*>(Bg + (long long)k0 * sg.ldb + lane * 2);
@@ -339,7 +342,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           }
           constexpr int ASEGS = BK / 2, ARPP = 32 / ASEGS;  // 16-byte segments per A row, rows per pass
           const int arow = lane / ASEGS, aseg = lane % ASEGS;
-          {
+          if (NPROD_WARPS == 1 || warp == NCONS_WARPS + 1) {
           // ---- A operand straight from one array; rows >= mt feed only discarded outputs ----
           int bytes_k = (K - (k0 + aseg * 2)) * 8;
           bytes_k = bytes_k < 0 ? 0 : (bytes_k > 16 ? 16 : bytes_k);
@@ -364,7 +367,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
           }
           }
           cp_async_mbar_arrive(&rg.full[rg.stage]);   // fires when this lane's copies have landed
-          if (lane == 0) {
+          if (lane == 0 && warp == NCONS_WARPS) {
             int krem = K - k0;
             rg.meta[rg.stage] = krem >= BK ? BK / 4 : (krem + 3) >> 2;
             mbar_arrive(&rg.full[rg.stage]);          // releases the meta word
