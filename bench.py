@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-groundstate", action="store_true", help="skip the C1 time-to-converge leg")
+    ap.add_argument("--shard", default="site", choices=["site", "mpo"],
+                    help="N>1: 'site' = independent per-site replicas (default, no collective); 'mpo' = ONE apply "
+                         "sharded over MPO levels with an NCCL allreduce of y per apply (strong scaling)")
     return ap.parse_args()
 
 
@@ -242,6 +245,58 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
+def mpo_sharded_main(args, ctx, case, plan, x, y, y_t, full_flops, rank, world, local):
+    """Strong-scaling mode: one H_AC apply split over MPO level pairs, NCCL allreduce of y per apply."""
+    import torch
+    import torch.distributed as dist
+
+    def step():
+        plan.apply(x, y)
+        ctx.synchronize()                  # library stream -> torch's stream hand-over
+        dist.all_reduce(y_t, op=dist.ReduceOp.SUM)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max = float(t.item())
+    checksum = float(y_t.sum().item())     # of the reduced y (before the shard-only timing below overwrites it)
+    shard_ms = plan.time(x, y, min(args.steps, 50)) / min(args.steps, 50)
+    tt = torch.tensor([shard_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = args.steps / wall_max
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"parallelism": "ONE apply sharded over MPO level pairs by left level (hubbardtn_b200/sharding.py "
+                                             "partition_rows; the synthetic level graph is one connected component, so the "
+                                             "chain-preserving partition cannot split it), NCCL allreduce(sum) of y (%d B) per apply"
+                                             % (y_t.numel() * 8),
+                                             "algorithmic_gflop_per_apply": full_flops / 1e9,
+                                             "this_rank_gflop": plan.stats["flops"] / 1e9}),
+            "tflops_fp64": value * full_flops / 1e12,
+            "slowest_shard_apply_ms": float(tt.item()), "allreduce_bytes": int(y_t.numel() * 8),
+            "timing": "host wall clock around apply + stream sync + NCCL allreduce, max over ranks",
+            "gpu_launches": int(plan.stats["launches_per_apply"]) * args.steps, "checksum": checksum}))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
@@ -261,9 +316,22 @@ def main():
     from hubbardtn_b200 import device, synthetic
     ctx = device.Context(local)
     from hubbardtn_b200 import sharding
-    case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=sharding.site_for_rank(rank, 4))
+    mpo_sharded = args.shard == "mpo" and world > 1
+    if mpo_sharded:
+        # every rank holds the SAME site problem but only its share of the MPO level pairs; y is the
+        # allreduce(sum) of the partial applies (SURVEY.md 8(e) axis 2)
+        case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=0)
+        full_flops = case.plan.stats["flops"]
+        mine = sharding.shard_mpo_entries(case.w_entries, args.chi, world, rank, mode="rows")
+        Wr = device.Mpo(ctx, case.M, case.P, case.M, mine)
+        case.plan = device.HeffAC(ctx, case.GL, Wr, case.GR, case.x)
+        y_t = torch.as_tensor(case.y.device_array(), device="cuda")
+    else:
+        case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=sharding.site_for_rank(rank, 4))
     plan, x, y = case.plan, case.x, case.y
     st = plan.stats
+    if mpo_sharded:
+        return mpo_sharded_main(args, ctx, case, plan, x, y, y_t, full_flops, rank, world, local)
 
     def barrier():
         ctx.synchronize()

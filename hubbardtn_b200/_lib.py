@@ -75,6 +75,7 @@ SIGNATURES = {
     "htn_tensor_blocktable5": (_i32, [_p, _pi32, _pi64, _pi32, _pi32, _pi32, _pi64]),
     "htn_tensor_kind": (_i32, [_p]),
     "htn_tensor_space": (_i32, [_p, _i32, _pp]),
+    "htn_tensor_device_ptr": (_i32, [_p, _pp, _pi64]),
     "htn_plan_heff_ac2": (_i32, [_p, _p, _p, _p, _p, _p, _pp]),
     "htn_contract_two_site": (_i32, [_p, _p, _p]),
     "htn_tsvd": (_i32, [_p, C.c_double, _i32, _pp, _pp, _pp, _pp, _pd, _pi32]),

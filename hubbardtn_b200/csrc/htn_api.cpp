@@ -511,6 +511,13 @@ int32_t htn_tensor_destroy(htn_tensor* t) {
 
 int32_t htn_tensor_kind(const htn_tensor* t) { return t ? t->kind : HTN_ERR_INVALID; }
 
+int32_t htn_tensor_device_ptr(const htn_tensor* t, void** ptr, int64_t* nelem_padded) {
+  if (!t || !ptr) return HTN_ERR_INVALID;
+  *ptr = t->d;
+  if (nelem_padded) *nelem_padded = t->dsize;
+  return HTN_OK;
+}
+
 int32_t htn_tensor_space(const htn_tensor* t, int32_t which, htn_space** out) {
   if (!t || !out) return HTN_ERR_INVALID;
   HTN_TRY

@@ -176,6 +176,17 @@ class Tensor:
         L.check(lib.htn_tensor_space(self.h, which, C.byref(h)), self.ctx.h)
         return _OwnedSpace(self.ctx, sym, h)
 
+    def device_array(self):
+        """Object exposing the padded device arena through `__cuda_array_interface__` (1-D float64), e.g. for
+        `torch.as_tensor(t.device_array(), device="cuda")` -> NCCL allreduce in place."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        L.check(lib.htn_tensor_device_ptr(self.h, C.byref(ptr), C.byref(n)), self.ctx.h)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 3,
+                                        "strides": None}
+        return _Arr()
+
     def transposed(self) -> "Tensor":
         """Blockwise-transposed companion (kind MPST) of an MPS tensor (structure only)."""
         h = C.c_void_p()

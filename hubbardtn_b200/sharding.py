@@ -51,3 +51,28 @@ def partition_levels(level_pairs, chi: int, world: int):
         for p in pairs:
             owner[p] = r
     return owner
+
+
+def partition_rows(level_pairs, chi: int, world: int):
+    """Alternative for a single H_eff apply (no environment update involved): all pairs (a, .) of one left
+    level a go to one rank, levels dealt out by descending pair count.  Stage L (GL[a] . x) then splits
+    without duplication; stage R is duplicated where several ranks feed the same right level."""
+    by_a = {}
+    for (a, b) in level_pairs:
+        by_a.setdefault(a, []).append((a, b))
+    load = [0] * world
+    owner = {}
+    for a, pairs in sorted(by_a.items(), key=lambda kv: (-len(kv[1]), kv[0])):
+        r = min(range(world), key=lambda i: load[i])
+        load[r] += len(pairs)
+        for p in pairs:
+            owner[p] = r
+    return owner
+
+
+def shard_mpo_entries(entries: dict, chi: int, world: int, rank: int, mode: str = "chains") -> dict:
+    """Entries {(a,s',s,b,c): w} of the MPO tensor owned by `rank`: the plan built from them computes this
+    rank's partial sum of y = sum_{a,b} GL[a] x W[a,b] GR[b]; allreduce(sum) over the ranks gives y."""
+    pairs = sorted({(k[0], k[3]) for k in entries})
+    owner = partition_levels(pairs, chi, world) if mode == "chains" else partition_rows(pairs, chi, world)
+    return {k: v for k, v in entries.items() if owner[(k[0], k[3])] == rank}

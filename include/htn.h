@@ -110,6 +110,9 @@ int32_t htn_tensor_create_transposed(const htn_tensor* t, htn_tensor** out);
 int32_t htn_tensor_transpose(const htn_tensor* src, htn_tensor* dst, int32_t weighted);
 int32_t htn_tensor_destroy(htn_tensor* t);
 int32_t htn_tensor_kind(const htn_tensor* t); /* HTN_T_* */
+/* raw device arena of a tensor (padded layout, zero padding; nelem_padded doubles) -- for collectives over
+ * NVLink that reduce whole vectors in place (NCCL allreduce of the sharded H_eff sums) */
+int32_t htn_tensor_device_ptr(const htn_tensor* t, void** ptr, int64_t* nelem_padded);
 /* copy of the bond space a tensor was built on: which = 0 left / first, 1 right / second (caller destroys) */
 int32_t htn_tensor_space(const htn_tensor* t, int32_t which, htn_space** out);
 /* Block table: nblocks rows of (label0,label1,label2) POSITIONS into the spaces, rows, cols,

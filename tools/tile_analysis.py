@@ -87,3 +87,22 @@ for (lp,sp,rp),Ks in byy.items():
     for K in Ks: alg+=2*Mm*N*K
 print("stage R alg GF %.2f warp-slot GF %.2f slot efficiency %.1f%%"%(alg/1e9,slot*512/1e9,100*alg/(slot*512)))
 tot=sum(hist.values()); print("   ",sorted(((k,round(100*v/tot,1)) for k,v in hist.items()),key=lambda t:-t[1])[:12])
+
+# ---- mix statistics: how many sources feed each U block, how often a T block is used ----
+import collections as _c
+nsrc = _c.Counter()
+t_use = _c.Counter()
+elems_by_nsrc = _c.Counter()
+for dst, srcs in plan.mix.items():
+    if dst[0] != "U":
+        continue
+    nsrc[len(srcs)] += 1
+    b, lp, sp, rp, r = plan.u_list[dst[1]]
+    elems_by_nsrc[len(srcs)] += Vl.mult[lp] * Vr.mult[r]
+    for (kind, i), cf in srcs:
+        if kind == "T":
+            t_use[i] += 1
+print("U blocks by number of sources:", sorted(nsrc.items()))
+tot = sum(elems_by_nsrc.values())
+print("U elements by number of sources (%):", sorted((k, round(100 * v / tot, 1)) for k, v in elems_by_nsrc.items()))
+print("T blocks by number of U targets:", sorted(_c.Counter(t_use.values()).items()))
