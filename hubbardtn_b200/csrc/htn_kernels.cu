@@ -998,9 +998,30 @@ int launch_svd(const SvdPanel* panels_dev, const SvdPanel* panels_host, int npan
     const int ne = (int)entries.size(), grid = (ne + 7) / 8;
     std::vector<int> nrot(npanels);
     bool converged = false;
+    // one sweep = max_n1 dependent round launches: captured once into a CUDA graph and replayed per sweep
+    // (a round on the largest panel runs ~5 us, so per-launch overhead would otherwise dominate)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool use_graph = max_n1 >= 16;
+    if (use_graph) {
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        for (int r = 0; r < max_n1; ++r) svd_round_kernel<<<grid, 256, 0, st>>>(panels_dev, d_entries, ne, r, G, Q, d_nrot);
+        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || graph == nullptr ||
+            cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+          use_graph = false;
+          cudaGetLastError();
+        }
+      } else {
+        use_graph = false;
+        cudaGetLastError();
+      }
+    }
     for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
       cudaMemsetAsync(d_nrot, 0, npanels * sizeof(int), st);
-      for (int r = 0; r < max_n1; ++r) svd_round_kernel<<<grid, 256, 0, st>>>(panels_dev, d_entries, ne, r, G, Q, d_nrot);
+      if (use_graph)
+        cudaGraphLaunch(gexec, st);
+      else
+        for (int r = 0; r < max_n1; ++r) svd_round_kernel<<<grid, 256, 0, st>>>(panels_dev, d_entries, ne, r, G, Q, d_nrot);
       cudaMemcpyAsync(nrot.data(), d_nrot, npanels * sizeof(int), cudaMemcpyDeviceToHost, st);
       if (cudaStreamSynchronize(st) != cudaSuccess) {
         rc = -2;
@@ -1010,6 +1031,8 @@ int launch_svd(const SvdPanel* panels_dev, const SvdPanel* panels_host, int npan
       for (int v : nrot) converged = converged && v == 0;
     }
     if (rc == 0 && !converged) rc = 1;
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     cudaFree(d_entries);
     cudaFree(d_nrot);
   }
