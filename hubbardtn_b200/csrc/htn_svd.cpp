@@ -317,3 +317,67 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
     return fail(HTN_ERR_INVALID, std::string("tsvd: ") + e.what());
   }
 }
+
+// Schmidt values of a bond matrix C per sector (descending), by the same one-sided Jacobi kernels.
+// Replaces `entanglement_spectrum(psi, site)` of MPSKit (SVD of C, the observable the north star names);
+// every value of sector c appears dim(c) times in the full spectrum.  out: concatenation over the
+// sectors in block order, counts[c] = n_c values each (arrays sized by htn_tensor_blocktable).
+extern "C" int32_t htn_entanglement_spectrum(const htn_tensor* C, double* out, int64_t nout) {
+  if (!C || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = C->ctx;
+  if (C->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "entanglement_spectrum: C must be a bond tensor");
+  int64_t total = 0;
+  for (const Block& b : C->blocks) total += b.rows;
+  if (nout != total) return ctx->fail(HTN_ERR_SHAPE, "entanglement_spectrum: output must hold sum_c n_c values");
+  if (total == 0) return HTN_OK;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  std::vector<SvdPanel> sp;
+  int64_t totG = 0, totS = 0;
+  for (const Block& b : C->blocks) {
+    if (b.rows > 1024) return ctx->fail(HTN_ERR_SHAPE, "entanglement_spectrum: sector multiplicity above 1024 is not supported");
+    if (b.rows == 0) continue;
+    sp.push_back(SvdPanel{totG, totG, totS, b.rows, b.cols, b.ld, b.ld, 1, 0});
+    totG = align_up(totG + (int64_t)b.rows * b.ld, 16);
+    totS += b.rows;
+  }
+  double *dG = nullptr, *dQ = nullptr, *dG2 = nullptr, *dQ2 = nullptr, *dS = nullptr;
+  SvdPanel* dP = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dG);
+    cudaFree(dQ);
+    cudaFree(dG2);
+    cudaFree(dQ2);
+    cudaFree(dS);
+    cudaFree(dP);
+  };
+  if (cudaMalloc(&dG, totG * 8) != cudaSuccess || cudaMalloc(&dQ, totG * 8) != cudaSuccess ||
+      cudaMalloc(&dG2, totG * 8) != cudaSuccess || cudaMalloc(&dQ2, totG * 8) != cudaSuccess ||
+      cudaMalloc(&dS, totS * 8) != cudaSuccess || cudaMalloc(&dP, sp.size() * sizeof(SvdPanel)) != cudaSuccess) {
+    cleanup();
+    return ctx->fail(HTN_ERR_OOM, "entanglement_spectrum: workspace allocation failed");
+  }
+  // panels = the blocks of C themselves (row-major, ld as in the tensor): copy block by block
+  {
+    size_t pi = 0;
+    for (const Block& b : C->blocks) {
+      if (b.rows == 0) continue;
+      cudaMemcpyAsync(dG + sp[pi].offG, C->d + b.off, (size_t)b.rows * b.ld * 8, cudaMemcpyDeviceToDevice, st);
+      ++pi;
+    }
+  }
+  h2d_on_stream(dP, sp.data(), sp.size() * sizeof(SvdPanel), st);
+  const int rc = launch_svd(dP, sp.data(), (int)sp.size(), dG, dQ, dG2, dQ2, dS, st);
+  int32_t ret = HTN_OK;
+  if (rc < 0)
+    ret = ctx->fail(HTN_ERR_CUDA, "entanglement_spectrum: Jacobi launch failed");
+  else if (rc > 0)
+    ret = ctx->fail(HTN_ERR_INVALID, "entanglement_spectrum: Jacobi sweeps did not converge");
+  else {
+    cudaMemcpyAsync(out, dS, totS * 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) ret = ctx->fail(HTN_ERR_CUDA, "entanglement_spectrum: readback failed");
+  }
+  cleanup();
+  return ret;
+}

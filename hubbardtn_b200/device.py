@@ -559,6 +559,19 @@ def uniform_from_right(ctx: Context, AR, C_last: Tensor, sym: int = 0, tol=1e-12
     return AL, AR, Cs, AC
 
 
+def entanglement_spectrum(Cb: Tensor) -> dict:
+    """{sector position c: Schmidt values (descending)} of a bond matrix, computed on the device."""
+    n = int(sum(int(r) for r in Cb.rows))
+    out = np.zeros(n)
+    L.check(lib.htn_entanglement_spectrum(Cb.h, out.ctypes.data_as(C.POINTER(C.c_double)), n), Cb.ctx.h)
+    res, o = {}, 0
+    for i in range(Cb.nblocks):
+        r = int(Cb.rows[i])
+        res[int(Cb.labels[i][0])] = out[o:o + r].copy()
+        o += r
+    return res
+
+
 def expval_diag(AC: Tensor, values) -> float:
     v = np.ascontiguousarray(values, dtype=np.float64)
     out = C.c_double()

@@ -359,6 +359,13 @@ def dim_state(psi: InfiniteMPS):
     return out
 
 
+def entanglement_spectrum(psi: InfiniteMPS, site: int = 0):
+    """MPSKit `entanglement_spectrum(psi, site)`: {sector label: Schmidt values} of the bond right of `site`."""
+    sp = psi.C[site].space(0, psi.sym)
+    spec = dev.entanglement_spectrum(psi.C[site])
+    return {sp.sectors[c]: v for c, v in spec.items()}
+
+
 def density_state(psi: InfiniteMPS):
     """<n_i> per site (HF:1495-1542; `expectation_value(psi, i => n)` HF:1507)."""
     vals = [0.0, 2.0, 1.0] if psi.sym == S.SU2U1 else [0.0, 2.0, 1.0, 1.0]

@@ -270,6 +270,12 @@ int32_t htn_mixed_gauge(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, con
  * operators that are scalars on every physical multiplet (n, n_up, n_dn): values[s] per multiplet s. */
 int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out);
 
+/* Replaces: MPSKit `entanglement_spectrum(psi, site)` (the Schmidt spectrum the north star names as a parity
+ * target; C from HubbardFunctions.jl's ground state): singular values of every block of the bond matrix C,
+ * descending per sector, concatenated in block order (nout = sum_c n_c; sector c counts dim(c) times in
+ * the full spectrum). */
+int32_t htn_entanglement_spectrum(const htn_tensor* C, double* out, int64_t nout);
+
 /* ---- vector algebra on tensors of identical structure (KrylovKit inner products) ------ */
 /* <x,y> = sum_blocks dim(coupled sector) tr(x^T y)   (TensorKit inner product) */
 int32_t htn_tensor_dot(const htn_tensor* x, const htn_tensor* y, double* out);
