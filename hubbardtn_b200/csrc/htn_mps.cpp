@@ -307,7 +307,9 @@ struct Uniform {
     return t_normalize(C[b], C[b]->d);
   }
 
-  static constexpr int EIG_MINITER = 10;  // MPSKit: plain sweeps first, then Arnoldi-accelerated ones
+  // plain sweeps before the Arnoldi-accelerated ones: 10 from a cold start (MPSKit's eig_miniter), 2 inside
+  // VUMPS where the guess for C is already close to the fixed point
+  int eig_miniter = 10;
 
   // AL -> (AR, C): iterated LQ through the unit cell (oracle/mps.py:uniform_rightorth)
   int32_t rightorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
@@ -316,8 +318,9 @@ struct Uniform {
     RC(t_normalize(C[L - 1], C[L - 1]->d));
     double delta = 1e300;
     int it = 0;
+    int next_eig = eig_miniter + 1;
     for (it = 1; it <= maxiter; ++it) {
-      if (it > EIG_MINITER) {
+      if (it >= next_eig) {
         // fixed point of X -> AL X AR^T through the unit cell (AR from the previous sweep), then its L factor
         RC(init_transfers1());
         for (int k = 0; k < L; ++k) RC(t_transpose(AR[k], ARt[k], 0));
@@ -345,6 +348,7 @@ struct Uniform {
           RC(t_copy(tB3[L - 1], C[L - 1]));
           RC(triangular_factor(L - 1, true));
         }
+        next_eig = it + 1;
       }
       RC(t_copy(C[L - 1], tB3[L - 1]));  // C_old
       for (int i = L - 1; i >= 0; --i) {
@@ -381,8 +385,9 @@ struct Uniform {
     RC(t_normalize(C[L - 1], C[L - 1]->d));
     double delta = 1e300;
     int it = 0;
+    int next_eig = eig_miniter + 1;
     for (it = 1; it <= maxiter; ++it) {
-      if (it > EIG_MINITER) {
+      if (it >= next_eig) {
         // fixed point of X -> AL^T X AR through the unit cell (AL from the previous sweep), then its R factor
         RC(init_transfers1());
         for (int k = 0; k < L; ++k) RC(t_transpose(AL[k], ALt[k], 0));
@@ -408,6 +413,7 @@ struct Uniform {
           RC(t_copy(tB3[L - 1], C[L - 1]));
           RC(triangular_factor(L - 1, false));
         }
+        next_eig = it + 1;
       }
       RC(t_copy(C[L - 1], tB3[L - 1]));
       for (int i = 0; i < L; ++i) {
@@ -813,6 +819,7 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
   RC(U.refresh_ac_and_transposes());
   RC(U.init_envs(W, GL, GR));
   RC(U.init_heff());
+  U.eig_miniter = 2;
   const int L = nsites;
   double eps = 1.0, eL = 0, eR = 0;
   RC(U.environments(1e-10, krylovdim, 200, &eL, &eR, nullptr));

@@ -162,7 +162,7 @@ def regauge(AC: MPSTensor, C: BondTensor) -> MPSTensor:
     return out
 
 
-EIG_MINITER = 10     # MPSKit: plain QR/LQ sweeps first, then sweeps preceded by an Arnoldi fixed-point solve
+EIG_MINITER = 10     # plain QR/LQ sweeps before the Arnoldi-accelerated ones from a cold start (MPSKit); VUMPS passes 2
 
 
 def arnoldi_dominant(apply, x0, tol=1e-12, krylovdim=30, maxiter=10):
@@ -219,7 +219,7 @@ def _tri_factor(C: BondTensor, lower: bool) -> BondTensor:
     return out
 
 
-def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
+def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000, eig_miniter=EIG_MINITER):
     """From left-orthonormal AL[0..L-1] and a guess for C[L-1]: AR[i], C[i] with
     AL[i] C[i] = C[i-1] AR[i]  (iterated LQ through the unit cell until C[L-1] is stationary)."""
     L = len(AL)
@@ -233,7 +233,7 @@ def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
     its = 0
     idR = None
     for its in range(1, maxiter + 1):
-        if its > EIG_MINITER:
+        if its > eig_miniter:
             if idR is None:
                 triv = Legs(AL[0].kind, [S.trivial(AL[0].kind)])
                 idR = [TransferPlan("R", identity_mpo(AL[i].P), AL[i].Vl, AL[i].P, AL[i].Vr) for i in range(L)]
@@ -261,7 +261,7 @@ def uniform_rightorth(AL, C_last: BondTensor, tol=1e-13, maxiter=10000):
     return AR, C, dict(iterations=its, delta=float(delta))
 
 
-def uniform_leftorth(AR, C_last: BondTensor, tol=1e-13, maxiter=10000):
+def uniform_leftorth(AR, C_last: BondTensor, tol=1e-13, maxiter=10000, eig_miniter=EIG_MINITER):
     """Mirror of `uniform_rightorth`: from (approximately) right-orthonormal AR[0..L-1] and a guess for
     C[L-1]: AL[i], C[i] with AL[i] C[i] = C[i-1] AR[i]  (iterated positive QR, MPSKit `uniform_leftorth!`)."""
     L = len(AR)
@@ -274,7 +274,7 @@ def uniform_leftorth(AR, C_last: BondTensor, tol=1e-13, maxiter=10000):
     delta, its = np.inf, 0
     idL = None
     for its in range(1, maxiter + 1):
-        if its > EIG_MINITER:
+        if its > eig_miniter:
             if idL is None:
                 triv = Legs(AR[0].kind, [S.trivial(AR[0].kind)])
                 idL = [TransferPlan("L", identity_mpo(AR[i].P), AR[i].Vl, AR[i].P, AR[i].Vr) for i in range(L)]
@@ -591,7 +591,7 @@ def vumps(state, W_list, tol=1e-10, maxiter=100, krylovdim=30, verbose=False, en
             newAC.append(ac)
             newC.append(c)
         AL = [regauge(newAC[i], newC[i]) for i in range(L)]
-        AR, C, ginfo = uniform_rightorth(AL, newC[L - 1], tol=min(1e-8, max(eps * 1e-6, 1e-14)))
+        AR, C, ginfo = uniform_rightorth(AL, newC[L - 1], tol=min(1e-8, max(eps * 1e-6, 1e-14)), eig_miniter=2)
         state = dict(AL=AL, AR=AR, C=C, AC=[mul_right(AL[i], C[i]) for i in range(L)])
         envs = Environments(state, W_list, tol=tol_env)
         plans = [HeffACPlan(envs.GL[i], W_list[i], envs.GR[i], state["AC"][i]) for i in range(L)]
