@@ -244,7 +244,7 @@ struct QrPanel {
   long long off_a, off_r;
   int m, n, lda, ldr;
 };
-void launch_qr(const QrPanel* panels, int npanels, double* A, double* R, int* status, cudaStream_t st);
+void launch_qr(const QrPanel* panels, int npanels, int max_m, double* A, double* R, int* status, cudaStream_t st);
 int gemm_max_ctas_per_sm();
 double probe_fp64(int which, int sm_count, cudaStream_t st);
 

@@ -825,8 +825,141 @@ __global__ void __launch_bounds__(32 * QR_TY) qr_cgs2_kernel(const QrPanel* __re
   }
 }
 
-void launch_qr(const QrPanel* panels, int npanels, double* A, double* R, int* status, cudaStream_t st) {
-  if (npanels > 0) qr_cgs2_kernel<<<npanels, 32 * QR_TY, 0, st>>>(panels, A, R, status);
+// Blocked variant (BCGS2 with the current column block resident in shared memory): per block of QB columns
+//   (1) P = A[:, J] -> smem,  (2) twice: for every 32-column chunk of the finished Q: H = Q_chunk^T P, P -= Q_chunk H,
+//   (3) column-by-column CGS2 inside the block (all in smem),  (4) P -> A[:, J].
+// Same result as qr_cgs2_kernel (the thin QR with diag(R) > 0 is unique) with ~20x fewer block-wide barriers
+// and 16 FMAs per global load in the projection step; used when m * QB doubles fit in shared memory.
+constexpr int QB = 16;
+
+__global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict__ panels, double* __restrict__ Abase,
+                                                       double* __restrict__ Rbase, int* __restrict__ status) {
+  extern __shared__ __align__(16) double qsm[];
+  const QrPanel Pn = panels[blockIdx.x];
+  double* A = Abase + Pn.off_a;
+  double* R = Rbase + Pn.off_r;
+  const int m = Pn.m, n = Pn.n, lda = Pn.lda, ldr = Pn.ldr;
+  double* P = qsm;                       // [m][QB]
+  double* red = P + (size_t)m * QB;      // [16 warps][QB][32 lanes]  (also reused as [32][QB] partials)
+  double* Hc = red + 16 * QB * 32;       // [32][QB]
+  double* hs = Hc + 32 * QB;             // [QB] + scalar
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < n * ldr; e += blockDim.x) R[e] = 0.0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += QB) {
+    const int nb = min(QB, n - j0);
+    for (int idx = tid; idx < m * QB; idx += blockDim.x) {
+      const int i = idx / QB, b = idx % QB;
+      P[idx] = b < nb ? A[(long long)i * lda + j0 + b] : 0.0;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int c0 = 0; c0 < j0; c0 += 32) {
+        const int c = c0 + lane;
+        const bool valid = c < j0;
+        double acc[QB];
+#pragma unroll
+        for (int b = 0; b < QB; ++b) acc[b] = 0.0;
+        for (int i = warp; i < m; i += 16) {
+          const double q = valid ? A[(long long)i * lda + c] : 0.0;
+          const double* pr = P + (size_t)i * QB;
+#pragma unroll
+          for (int b = 0; b < QB; ++b) acc[b] = fma(q, pr[b], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < QB; ++b) red[(warp * QB + b) * 32 + lane] = acc[b];
+        __syncthreads();
+        {  // sum over the 16 row groups: thread -> (b, l)
+          const int b = tid >> 5, l = tid & 31;
+          double sacc = 0.0;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) sacc += red[(w * QB + b) * 32 + l];
+          Hc[l * QB + b] = sacc;
+          if (c0 + l < j0 && b < nb) R[(long long)(c0 + l) * ldr + j0 + b] += sacc;
+        }
+        __syncthreads();
+        {  // P -= Q_chunk H
+          const int b = tid % QB, ig = tid / QB;  // 32 row groups
+          const int nc = min(32, j0 - c0);
+          for (int i = ig; i < m; i += 32) {
+            const double* qr = A + (long long)i * lda + c0;
+            double sacc = 0.0;
+            for (int l = 0; l < nc; ++l) sacc = fma(qr[l], Hc[l * QB + b], sacc);
+            P[(size_t)i * QB + b] -= sacc;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // CGS2 inside the block
+    for (int jb = 0; jb < nb; ++jb) {
+      for (int pass = 0; pass < 2; ++pass) {
+        if (jb > 0) {
+          const int cb = tid % QB, ig = tid / QB;
+          double sacc = 0.0;
+          if (cb < jb)
+            for (int i = ig; i < m; i += 32) sacc = fma(P[(size_t)i * QB + cb], P[(size_t)i * QB + jb], sacc);
+          red[ig * QB + cb] = sacc;
+          __syncthreads();
+          if (tid < jb) {
+            double h = 0.0;
+            for (int g = 0; g < 32; ++g) h += red[g * QB + tid];
+            hs[tid] = h;
+            R[(long long)(j0 + tid) * ldr + j0 + jb] += h;
+          }
+          __syncthreads();
+          for (int i = tid; i < m; i += blockDim.x) {
+            double sacc = 0.0;
+            for (int cbb = 0; cbb < jb; ++cbb) sacc = fma(P[(size_t)i * QB + cbb], hs[cbb], sacc);
+            P[(size_t)i * QB + jb] -= sacc;
+          }
+          __syncthreads();
+        }
+      }
+      double sacc = 0.0;
+      for (int i = tid; i < m; i += blockDim.x) {
+        const double v = P[(size_t)i * QB + jb];
+        sacc = fma(v, v, sacc);
+      }
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[warp] = sacc;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 16; ++w) tot += red[w];
+        const double nrm = sqrt(tot);
+        hs[QB] = nrm;
+        R[(long long)(j0 + jb) * ldr + j0 + jb] = nrm;
+        if (!(nrm > 0.0)) atomicOr(status, 1);
+      }
+      __syncthreads();
+      const double inv = hs[QB] > 0.0 ? 1.0 / hs[QB] : 0.0;
+      for (int i = tid; i < m; i += blockDim.x) P[(size_t)i * QB + jb] *= inv;
+      __syncthreads();
+    }
+    for (int idx = tid; idx < m * QB; idx += blockDim.x) {
+      const int i = idx / QB, b = idx % QB;
+      if (b < nb) A[(long long)i * lda + j0 + b] = P[idx];
+    }
+    __syncthreads();
+  }
+}
+
+// max_m: largest panel height (host knows it); the blocked kernel needs (max_m*QB + 16*QB*32 + 32*QB + QB + 8) doubles
+void launch_qr(const QrPanel* panels, int npanels, int max_m, double* A, double* R, int* status, cudaStream_t st) {
+  if (npanels <= 0) return;
+  const size_t need = ((size_t)max_m * QB + 16 * QB * 32 + 32 * QB + QB + 8) * sizeof(double);
+  static const bool force_old = getenv("HTN_QR_UNBLOCKED") != nullptr;
+  if (need <= 220 * 1024 && !force_old) {
+    static size_t configured = 0;
+    if (need > configured) {
+      cudaFuncSetAttribute(qr_bcgs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      configured = 220 * 1024;
+    }
+    qr_bcgs2_kernel<<<npanels, 512, need, st>>>(panels, A, R, status);
+  } else {
+    qr_cgs2_kernel<<<npanels, 32 * QR_TY, 0, st>>>(panels, A, R, status);
+  }
 }
 
 // straight 2-D block copy with scale (tiles listed by the host): dst[r][c] = scale * src[r][c]

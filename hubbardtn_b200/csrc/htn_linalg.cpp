@@ -161,7 +161,24 @@ int32_t t_qr_inplace(htn_tensor* A, htn_tensor* R) {
     n = A->devtables[key].second;
   }
   cudaMemsetAsync(R->d, 0, R->dsize * sizeof(double), ctx->stream);
-  launch_qr(d, n, A->d, R->d, ctx->d_status, ctx->stream);
+  int max_m = 0;  // panel heights: group sizes (host side of the cached table)
+  {
+    const int gidx = A->kind == HTN_T_MPS ? 2 : 0;
+    size_t i = 0;
+    while (i < A->blocks.size()) {
+      size_t j = i;
+      int m = 0;
+      if (A->kind == HTN_T_BOND) {
+        m = A->blocks[i].rows;
+        j = i + 1;
+      } else {
+        while (j < A->blocks.size() && A->blocks[j].lab[gidx] == A->blocks[i].lab[gidx]) m += A->blocks[j++].rows;
+      }
+      max_m = std::max(max_m, m);
+      i = j;
+    }
+  }
+  launch_qr(d, n, max_m, A->d, R->d, ctx->d_status, ctx->stream);
   return cuda_rc(ctx, "qr");
 }
 
