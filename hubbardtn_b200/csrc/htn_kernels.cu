@@ -825,11 +825,13 @@ __global__ void __launch_bounds__(32 * QR_TY) qr_cgs2_kernel(const QrPanel* __re
   }
 }
 
-// Blocked variant (BCGS2 with the current column block resident in shared memory): per block of QB columns
-//   (1) P = A[:, J] -> smem,  (2) twice: for every 32-column chunk of the finished Q: H = Q_chunk^T P, P -= Q_chunk H,
-//   (3) column-by-column CGS2 inside the block (all in smem),  (4) P -> A[:, J].
-// Same result as qr_cgs2_kernel (the thin QR with diag(R) > 0 is unique) with ~20x fewer block-wide barriers
-// and 16 FMAs per global load in the projection step; used when m * QB doubles fit in shared memory.
+// Blocked variant (BCGS2 with the current column block resident in shared memory): per block J of QB columns
+//   P = A[:, J] -> smem; then TWICE { project P against the finished Q (32-column chunks: H = Q_c^T P, P -= Q_c H);
+//   column-by-column CGS2 inside the block (all in smem) };  P -> A[:, J].
+// The second round acts on an already orthonormal block, which restores orthogonality against the finished
+// columns to machine precision even when the block itself is ill-conditioned (a single round loses
+// eps * cond(block): seen as 1e-8 at cond ~ 1e8).  R = [H1 + H2 R1 ; R2 R1].  Same result as qr_cgs2_kernel (the
+// thin QR with diag(R) > 0 is unique) with ~20x fewer block-wide barriers and 16 FMAs per global load.
 constexpr int QB = 16;
 
 __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict__ panels, double* __restrict__ Abase,
@@ -842,7 +844,9 @@ __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict
   double* P = qsm;                       // [m][QB]
   double* red = P + (size_t)m * QB;      // [16 warps][QB][32 lanes]  (also reused as [32][QB] partials)
   double* Hc = red + 16 * QB * 32;       // [32][QB]
-  double* hs = Hc + 32 * QB;             // [QB] + scalar
+  double* hs = Hc + 32 * QB;             // [QB] + scalar (+ padding to 32)
+  double* Rb1 = hs + 32;                 // [QB][QB] intra-block factor of the first round
+  double* Rcur = Rb1 + QB * QB;          // [QB][QB] intra-block factor of the current round
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int e = tid; e < n * ldr; e += blockDim.x) R[e] = 0.0;
   __syncthreads();
@@ -853,7 +857,8 @@ __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict
       P[idx] = b < nb ? A[(long long)i * lda + j0 + b] : 0.0;
     }
     __syncthreads();
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int rep = 0; rep < 2; ++rep) {
+      // ---- projection against the finished columns ----
       for (int c0 = 0; c0 < j0; c0 += 32) {
         const int c = c0 + lane;
         const bool valid = c < j0;
@@ -875,9 +880,21 @@ __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict
 #pragma unroll
           for (int w = 0; w < 16; ++w) sacc += red[(w * QB + b) * 32 + l];
           Hc[l * QB + b] = sacc;
-          if (c0 + l < j0 && b < nb) R[(long long)(c0 + l) * ldr + j0 + b] += sacc;
         }
         __syncthreads();
+        {  // R[prev, J] += H (first round) or H R1 (second round)
+          const int b = tid >> 5, l = tid & 31;
+          if (c0 + l < j0 && b < nb) {
+            double v;
+            if (rep == 0) {
+              v = Hc[l * QB + b];
+            } else {
+              v = 0.0;
+              for (int k = 0; k <= b; ++k) v = fma(Hc[l * QB + k], Rb1[k * QB + b], v);
+            }
+            R[(long long)(c0 + l) * ldr + j0 + b] += v;
+          }
+        }
         {  // P -= Q_chunk H
           const int b = tid % QB, ig = tid / QB;  // 32 row groups
           const int nc = min(32, j0 - c0);
@@ -890,51 +907,64 @@ __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict
         }
         __syncthreads();
       }
-    }
-    // CGS2 inside the block
-    for (int jb = 0; jb < nb; ++jb) {
-      for (int pass = 0; pass < 2; ++pass) {
-        if (jb > 0) {
-          const int cb = tid % QB, ig = tid / QB;
-          double sacc = 0.0;
-          if (cb < jb)
-            for (int i = ig; i < m; i += 32) sacc = fma(P[(size_t)i * QB + cb], P[(size_t)i * QB + jb], sacc);
-          red[ig * QB + cb] = sacc;
-          __syncthreads();
-          if (tid < jb) {
-            double h = 0.0;
-            for (int g = 0; g < 32; ++g) h += red[g * QB + tid];
-            hs[tid] = h;
-            R[(long long)(j0 + tid) * ldr + j0 + jb] += h;
-          }
-          __syncthreads();
-          for (int i = tid; i < m; i += blockDim.x) {
+      // ---- CGS2 inside the block (factor Rcur, upper triangular) ----
+      for (int e = tid; e < QB * QB; e += blockDim.x) Rcur[e] = 0.0;
+      __syncthreads();
+      for (int jb = 0; jb < nb; ++jb) {
+        for (int pass = 0; pass < 2; ++pass) {
+          if (jb > 0) {
+            const int cb = tid % QB, ig = tid / QB;
             double sacc = 0.0;
-            for (int cbb = 0; cbb < jb; ++cbb) sacc = fma(P[(size_t)i * QB + cbb], hs[cbb], sacc);
-            P[(size_t)i * QB + jb] -= sacc;
+            if (cb < jb)
+              for (int i = ig; i < m; i += 32) sacc = fma(P[(size_t)i * QB + cb], P[(size_t)i * QB + jb], sacc);
+            red[ig * QB + cb] = sacc;
+            __syncthreads();
+            if (tid < jb) {
+              double h = 0.0;
+              for (int g = 0; g < 32; ++g) h += red[g * QB + tid];
+              hs[tid] = h;
+              Rcur[tid * QB + jb] += h;
+            }
+            __syncthreads();
+            for (int i = tid; i < m; i += blockDim.x) {
+              double sacc2 = 0.0;
+              for (int cbb = 0; cbb < jb; ++cbb) sacc2 = fma(P[(size_t)i * QB + cbb], hs[cbb], sacc2);
+              P[(size_t)i * QB + jb] -= sacc2;
+            }
+            __syncthreads();
           }
-          __syncthreads();
+        }
+        double sacc = 0.0;
+        for (int i = tid; i < m; i += blockDim.x) {
+          const double v = P[(size_t)i * QB + jb];
+          sacc = fma(v, v, sacc);
+        }
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+        if (lane == 0) red[warp] = sacc;
+        __syncthreads();
+        if (tid == 0) {
+          double tot = 0.0;
+          for (int w = 0; w < 16; ++w) tot += red[w];
+          const double nrm = sqrt(tot);
+          hs[QB] = nrm;
+          Rcur[jb * QB + jb] = nrm;
+          if (!(nrm > 0.0)) atomicOr(status, 1);
+        }
+        __syncthreads();
+        const double inv = hs[QB] > 0.0 ? 1.0 / hs[QB] : 0.0;
+        for (int i = tid; i < m; i += blockDim.x) P[(size_t)i * QB + jb] *= inv;
+        __syncthreads();
+      }
+      if (rep == 0) {
+        for (int e = tid; e < QB * QB; e += blockDim.x) Rb1[e] = Rcur[e];
+      } else if (tid < QB * QB) {  // R[J, J] = R2 R1
+        const int r = tid / QB, cc = tid % QB;
+        if (r < nb && cc < nb && r <= cc) {
+          double v = 0.0;
+          for (int k = r; k <= cc; ++k) v = fma(Rcur[r * QB + k], Rb1[k * QB + cc], v);
+          R[(long long)(j0 + r) * ldr + j0 + cc] = v;
         }
       }
-      double sacc = 0.0;
-      for (int i = tid; i < m; i += blockDim.x) {
-        const double v = P[(size_t)i * QB + jb];
-        sacc = fma(v, v, sacc);
-      }
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
-      if (lane == 0) red[warp] = sacc;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < 16; ++w) tot += red[w];
-        const double nrm = sqrt(tot);
-        hs[QB] = nrm;
-        R[(long long)(j0 + jb) * ldr + j0 + jb] = nrm;
-        if (!(nrm > 0.0)) atomicOr(status, 1);
-      }
-      __syncthreads();
-      const double inv = hs[QB] > 0.0 ? 1.0 / hs[QB] : 0.0;
-      for (int i = tid; i < m; i += blockDim.x) P[(size_t)i * QB + jb] *= inv;
       __syncthreads();
     }
     for (int idx = tid; idx < m * QB; idx += blockDim.x) {
@@ -945,10 +975,10 @@ __global__ void __launch_bounds__(512) qr_bcgs2_kernel(const QrPanel* __restrict
   }
 }
 
-// max_m: largest panel height (host knows it); the blocked kernel needs (max_m*QB + 16*QB*32 + 32*QB + QB + 8) doubles
+// max_m: largest panel height (host knows it); shared-memory need of the blocked kernel below
 void launch_qr(const QrPanel* panels, int npanels, int max_m, double* A, double* R, int* status, cudaStream_t st) {
   if (npanels <= 0) return;
-  const size_t need = ((size_t)max_m * QB + 16 * QB * 32 + 32 * QB + QB + 8) * sizeof(double);
+  const size_t need = ((size_t)max_m * QB + 16 * QB * 32 + 32 * QB + 32 + 2 * QB * QB) * sizeof(double);
   static const bool force_old = getenv("HTN_QR_UNBLOCKED") != nullptr;
   if (need <= 220 * 1024 && !force_old) {
     static size_t configured = 0;

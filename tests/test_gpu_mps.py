@@ -209,3 +209,33 @@ def test_vumps_ground_state_matches_oracle(ctx, kind, u, D):
     # same algorithm, but the inexact inner solves stop at slightly different points (the device checks
     # the Lanczos residual every 5 steps, the oracle every step): iteration counts are close, not equal
     assert abs(res["iterations"] - len(log)) <= 0.5 * len(log) + 2
+
+
+def test_qrpos_is_orthogonal_on_ill_conditioned_panels(ctx):
+    """Gauge fixing meets AL.C with cond(C) ~ 1/smallest Schmidt value (1e8 and beyond): the blocked QR kernel must
+    keep Q^T Q = 1 at machine precision there (one block-Gram-Schmidt round would lose eps * cond)."""
+    kind = S.SU2U1
+    rng = np.random.default_rng(11)
+    P = physical_space(kind)
+    spaces = M.trim_spaces(kind, [synthetic_bond_space(kind, 150, 1), synthetic_bond_space(kind, 150, 0)], [P, P])
+    A = MPSTensor(spaces[1], P, spaces[0]).randomize(rng)
+    for k, v in A.blocks.items():                       # graded columns: singular values from 1 down to 1e-9
+        n = v.shape[1]
+        A.blocks[k] = v * np.logspace(0, -9, n)[None, :]
+    dVl, dVr = dev.Space(ctx, kind, spaces[1].as_dict()), dev.Space(ctx, kind, spaces[0].as_dict())
+    dA = dev.Tensor.mps(ctx, dVl, dev.Legs(ctx, kind, P.sectors), dVr)
+    dA.upload(pack_blocks(dA, A.blocks))
+    Q, R = dA.like(), dev.Tensor.bond(ctx, dVr)
+    dev.qrpos(dA, Q, R)
+    Qb = unpack_blocks(Q)
+    Rb = unpack_blocks(R, key=lambda lab: lab[0])
+    by_r = {}
+    for (l, s, r), blk in Qb.items():
+        by_r.setdefault(r, []).append(((l, s, r), blk))
+    for r, lst in by_r.items():
+        Qr = np.vstack([b for _, b in sorted(lst, key=lambda t: (t[0][1], t[0][0]))])
+        Ar = np.vstack([A.blocks[k] for k, _ in sorted(lst, key=lambda t: (t[0][1], t[0][0]))])
+        n = Qr.shape[1]
+        assert np.abs(Qr.T @ Qr - np.eye(n)).max() < 5e-13
+        assert np.abs(Qr @ Rb[r] - Ar).max() < 1e-13 * np.abs(Ar).max() * 10
+        assert (np.diag(Rb[r]) > 0).all()

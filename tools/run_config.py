@@ -29,7 +29,14 @@ print("IDMRG2: %.2f s, %d iterations, delta %.2e, D_red per bond %s, applies %d"
 print("   cumulative seconds: planning %.2f  lanczos %.2f  svd %.2f  env growth %.2f" % tuple(info1["log"][-1][3:7]))
 if os.environ.get("STOP_AFTER_IDMRG"):
     sys.exit(0)
-AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], model.sym)
+n = len(AR)
+AL = [a.like() for a in AR]
+AC = [a.like() for a in AR]
+Cn = [dev.Tensor.bond(ctx, AR[i].space(1, model.sym)) for i in range(n)]
+ginfo = dev.mixed_gauge(ctx, AL, C[-1], AR, Cn, AC, tol=1e-12, maxiter=int(os.environ.get("GAUGE_MAXITER", "10000")),
+                        from_right=True)
+C = Cn
+print("mixed gauge:", ginfo)
 t2 = time.perf_counter()
 print("mixed gauge: %.2f s" % (t2 - t1))
 psi = hf.InfiniteMPS(ctx, model.sym, AL, AR, C, AC)
