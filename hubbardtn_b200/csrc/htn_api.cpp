@@ -72,8 +72,8 @@ int32_t htn_ctx_create(int32_t device, htn_ctx** out) {
     return HTN_ERR_NO_DEVICE;
   }
   cudaMallocHost(&c->red_host, 64 * sizeof(double));
-  cudaMalloc(&c->kry_scal, 1024 * sizeof(double));
-  cudaMallocHost(&c->kry_scal_host, 1024 * sizeof(double));
+  cudaMalloc(&c->kry_scal, 8192 * sizeof(double));
+  cudaMallocHost(&c->kry_scal_host, 8192 * sizeof(double));
   cudaMalloc(&c->d_status, sizeof(int));
   cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
   *out = c;

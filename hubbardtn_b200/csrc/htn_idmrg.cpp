@@ -243,7 +243,7 @@ struct Idmrg {
       if (rc == HTN_OK) {
         ApplyFn op = [&](const double* a, double* b) -> int32_t { return htn_heff_run(p, a, b, 0xF); };
         KrylovInfo info;
-        rc = lanczos_lowest(x2, op, x2->d, y2->d, krylovdim, eig_tol, 3, &info);
+        rc = lanczos_lowest(x2, op, x2->d, y2->d, krylovdim, eig_tol, 6, &info);  // 30 + 5 x 12 applies: the budget of 3 explicit restarts
         applies += info.applies;
         if (rc > 0) rc = HTN_OK;
       }

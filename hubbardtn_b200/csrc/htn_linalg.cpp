@@ -205,7 +205,7 @@ int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunk
 }
 
 // device scalar slots inside ctx->kry_scal
-enum { S_H = 0, S_H2 = 64, S_BETA = 128, S_NRM = 129, S_Y = 192, S_TMP = 300, S_A1 = 512, S_A2 = 576, S_B = 640 };
+enum { S_H = 0, S_H2 = 64, S_BETA = 128, S_NRM = 129, S_Y = 192, S_TMP = 300, S_A1 = 512, S_A2 = 576, S_B = 640, S_Z = 1024 };
 
 int32_t t_dot_dev(const htn_tensor* like, const double* x, const double* y, double* out_dev) {
   htn_ctx* ctx = like->ctx;
@@ -276,39 +276,38 @@ static void jacobi_eigh(int n, std::vector<double>& A, std::vector<double>& V, s
   for (int i = 0; i < n; ++i) w[i] = A[(size_t)i * n + i];
 }
 
-// Lowest eigenpair of the symmetric operator `apply` (Lanczos, full CGS2 re-orthogonalisation,
-// explicit restart from the Ritz vector -- same recurrence as oracle/krylov.py:lanczos_lowest).
-// x0: start vector; x_out: eigenvector (unit norm, <x0, x_out> >= 0).  x0 may alias x_out.
+// Lowest eigenpair of the symmetric operator `apply`: Lanczos with full CGS2 re-orthogonalisation and THICK
+// restarts (Krylov-Schur form, as KrylovKit's `eigsolve(.., Lanczos(krylovdim))` does): when the basis is full
+// the lowest `keep` Ritz vectors are kept, the projected matrix becomes diag(theta) plus one coupling row to the
+// residual vector, and the recurrence continues from there.  x0: start vector; x_out: eigenvector (unit norm,
+// <x0, x_out> >= 0).  x0 may alias x_out.
+// Semi-eager: the coefficients of every step are parked in device arrays and read back (one synchronisation)
+// only every LANCZOS_CHECK steps, so the launches queue up instead of paying a host round trip per step.
 int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const double* x0, double* x_out, int krylovdim,
                        double tol, int maxiter, KrylovInfo* info) {
   htn_ctx* ctx = like->ctx;
-  krylovdim = std::max(2, std::min(krylovdim, 60));
+  const int kd = std::max(2, std::min(krylovdim, 60));
+  const int keep = std::max(1, std::min(kd - 2, (3 * kd) / 5));
   const int64_t n = like->dsize;
-  int32_t rc = ensure_krylov(ctx, krylovdim + 2, n, like->nchunks);
+  int32_t rc = ensure_krylov(ctx, kd + 2 + keep, n, like->nchunks);
   if (rc) return rc;
-  double* V = ctx->kry_V;
-  double* xsave = V + (int64_t)(krylovdim + 1) * n;  // copy of x0 for the final sign convention
+  double* V = ctx->kry_V;                            // slots 0..kd: basis (+ residual)
+  double* xsave = V + (int64_t)(kd + 1) * n;         // copy of x0 for the final sign convention
+  double* S = V + (int64_t)(kd + 2) * n;             // `keep` scratch vectors for the restart rotation
   double* sc = ctx->kry_scal;
   double* sh = ctx->kry_scal_host;
   cudaStream_t st = ctx->stream;
   cudaMemcpyAsync(xsave, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(V, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
   if ((rc = t_normalize(like, V))) return rc;
-  int applies = 0;
+  constexpr int LANCZOS_CHECK = 5;
+  int applies = 0, m = 0, j0 = 0, k = 0;  // k: number of kept Ritz vectors at the head of the basis
   double theta = 0.0, res = 1e300;
   bool converged = false;
-  std::vector<double> alphas, betas, Tm, Z, ev;
-  // Semi-eager recurrence: the Lanczos coefficients of every step are parked in device arrays and read
-  // back (one synchronisation) only every LANCZOS_CHECK steps, so the launches of up to LANCZOS_CHECK
-  // steps queue up behind each other instead of paying a host round trip per step (KrylovKit's `eager`
-  // mode checks every step; the Ritz pair is the same, at most LANCZOS_CHECK - 1 applies later).
-  constexpr int LANCZOS_CHECK = 5;
-  for (int restart = 0; restart < maxiter && !converged; ++restart) {
-    alphas.clear();
-    betas.clear();
-    int m = 0;
-    std::vector<double> y;
-    for (int j = 0; j < krylovdim; ++j) {
+  std::vector<double> thetas, arrow, Hm, Z, ev, y, alphas, betas;
+  for (int cycle = 0; cycle < maxiter && !converged; ++cycle) {
+    bool full = false;
+    for (int j = j0; j < kd; ++j) {
       double* w = V + (int64_t)(j + 1) * n;
       if ((rc = apply(V + (int64_t)j * n, w))) return rc;
       ++applies;
@@ -320,7 +319,7 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       cudaMemcpyAsync(sc + S_A1 + j, sc + S_H + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(sc + S_A2 + j, sc + S_H2 + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(sc + S_B + j, sc + S_BETA, sizeof(double), cudaMemcpyDeviceToDevice, st);
-      const bool check = (j % LANCZOS_CHECK) == LANCZOS_CHECK - 1 || j == krylovdim - 1;
+      const bool check = ((j - j0) % LANCZOS_CHECK) == LANCZOS_CHECK - 1 || j == kd - 1;
       if (!check) {
         launch_scale_dev(w, sc + S_BETA, 3, w, n, st);  // next basis vector (0 on breakdown)
         continue;
@@ -330,21 +329,26 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       m = j + 1;
       alphas.assign(m, 0.0);
       betas.assign(m, 0.0);
-      for (int i = 0; i < m; ++i) {
+      for (int i = k; i < m; ++i) {
         alphas[i] = sh[S_A1 + i] + sh[S_A2 + i];
         betas[i] = std::sqrt(std::max(sh[S_B + i], 0.0));
       }
-      for (int i = 0; i < m; ++i)
+      for (int i = k; i < m; ++i)
         if (betas[i] < 1e-14) {  // invariant subspace reached at step i
           m = i + 1;
           break;
         }
-      Tm.assign((size_t)m * m, 0.0);
-      for (int i = 0; i < m; ++i) {
-        Tm[(size_t)i * m + i] = alphas[i];
-        if (i + 1 < m) Tm[(size_t)i * m + i + 1] = Tm[(size_t)(i + 1) * m + i] = betas[i];
+      // projected matrix: diag(theta_0..theta_{k-1}) + coupling row/column k + tridiagonal tail
+      Hm.assign((size_t)m * m, 0.0);
+      for (int i = 0; i < k && i < m; ++i) {
+        Hm[(size_t)i * m + i] = thetas[i];
+        if (k < m) Hm[(size_t)i * m + k] = Hm[(size_t)k * m + i] = arrow[i];
       }
-      jacobi_eigh(m, Tm, Z, ev);
+      for (int i = k; i < m; ++i) {
+        Hm[(size_t)i * m + i] = alphas[i];
+        if (i + 1 < m) Hm[(size_t)i * m + i + 1] = Hm[(size_t)(i + 1) * m + i] = betas[i];
+      }
+      jacobi_eigh(m, Hm, Z, ev);
       int lo = 0;
       for (int i = 1; i < m; ++i)
         if (ev[i] < ev[lo]) lo = i;
@@ -353,26 +357,50 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       for (int i = 0; i < m; ++i) y[i] = Z[(size_t)i * m + lo];
       const double bm = betas[m - 1];
       res = std::fabs(bm * y[m - 1]);
-      if (res < tol || bm < 1e-14 || m < j + 1 || j == krylovdim - 1) break;
+      if (res < tol || bm < 1e-14 || m < j + 1) break;
+      if (j == kd - 1) {
+        full = true;
+        break;
+      }
       launch_scale_dev(w, sc + S_BETA, 3, w, n, st);
     }
-    // Ritz vector -> V[0]  (built in the spare slot, then copied)
-    for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
-    cudaMemcpyAsync(sc + S_Y, sh + S_Y, m * sizeof(double), cudaMemcpyHostToDevice, st);
-    // slot m (the un-normalised remainder) is dead now; use it as the accumulator
-    double* acc = V + (int64_t)m * n;
-    cudaMemsetAsync(acc, 0, n * sizeof(double), st);
-    launch_multiaxpy(V, n, m, sc + S_Y, 1.0, acc, n, st);
-    if ((rc = t_normalize(like, acc))) return rc;
-    cudaMemcpyAsync(V, acc, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
-    cudaStreamSynchronize(st);  // the pinned y buffer is reused next round
-    converged = res < tol;
+    converged = res < tol || (m > 0 && m < kd && !full && res < 1e299 && betas[m - 1] < 1e-14);
+    if (converged || !full || cycle == maxiter - 1) break;
+    // ---- thick restart: keep the lowest `keep` Ritz vectors + the residual direction ----
+    std::vector<int> order(m);
+    for (int i = 0; i < m; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a2, int b2) { return ev[a2] < ev[b2]; });
+    const int kn = std::min(keep, m - 1);
+    const double bm = betas[m - 1];
+    thetas.assign(kn, 0.0);
+    arrow.assign(kn, 0.0);
+    for (int i = 0; i < kn; ++i) {
+      thetas[i] = ev[order[i]];
+      arrow[i] = bm * Z[(size_t)(m - 1) * m + order[i]];
+      for (int r = 0; r < m; ++r) sh[S_Z + i * m + r] = Z[(size_t)r * m + order[i]];
+    }
+    cudaMemcpyAsync(sc + S_Z, sh + S_Z, (size_t)kn * m * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(S, 0, (size_t)kn * n * sizeof(double), st);
+    for (int i = 0; i < kn; ++i) launch_multiaxpy(V, n, m, sc + S_Z + i * m, 1.0, S + (int64_t)i * n, n, st);
+    launch_scale_dev(V + (int64_t)m * n, sc + S_BETA, 3, V + (int64_t)kn * n, n, st);  // residual -> slot kn
+    cudaMemcpyAsync(V, S, (size_t)kn * n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "lanczos restart");
+    k = kn;
+    j0 = kn;
   }
+  // Ritz vector of the last evaluation -> V[0]
+  if (m == 0) return ctx->fail(HTN_ERR_INVALID, "lanczos: no iteration performed");
+  for (int i = 0; i < m; ++i) sh[S_Y + i] = y[i];
+  cudaMemcpyAsync(sc + S_Y, sh + S_Y, m * sizeof(double), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(S, 0, n * sizeof(double), st);
+  launch_multiaxpy(V, n, m, sc + S_Y, 1.0, S, n, st);
+  if ((rc = t_normalize(like, S))) return rc;
   // sign convention: positive overlap with the start vector
   double ov = 0.0;
-  if ((rc = t_dot_host(like, xsave, V, &ov))) return rc;
-  launch_axpby(ov < 0 ? -1.0 : 1.0, V, 0.0, x_out, n, st);
+  if ((rc = t_dot_host(like, xsave, S, &ov))) return rc;
+  launch_axpby(ov < 0 ? -1.0 : 1.0, S, 0.0, x_out, n, st);
   if ((rc = cuda_rc(ctx, "lanczos"))) return rc;
+  converged = res < tol;
   if (info) {
     info->value = theta;
     info->residual = res;

@@ -837,11 +837,11 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
     for (int i = 0; i < L; ++i) {
       KrylovInfo info;
       ApplyFn hac = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hac[i], a, b, 0xF); };
-      int32_t rc = lanczos_lowest(U.AC[i], hac, U.AC[i]->d, U.nAC[i]->d, krylovdim, tol_eig, 20, &info);
+      int32_t rc = lanczos_lowest(U.AC[i], hac, U.AC[i]->d, U.nAC[i]->d, krylovdim, tol_eig, 40, &info);
       if (rc < 0) return rc;
       napp += info.applies;
       ApplyFn hc = [&](const double* a, double* b) -> int32_t { return htn_heff_run(U.hc[i], a, b, 0xF); };
-      rc = lanczos_lowest(U.C[i], hc, U.C[i]->d, U.nC[i]->d, krylovdim, tol_eig, 20, &info);
+      rc = lanczos_lowest(U.C[i], hc, U.C[i]->d, U.nC[i]->d, krylovdim, tol_eig, 40, &info);
       if (rc < 0) return rc;
       napp += info.applies;
     }
