@@ -76,6 +76,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// producer-side wait: back off between polls so that the (mostly idle) producer warps do not compete for issue
+// slots with the DMMA warps of their SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(128);
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   unsigned ok;
   do {
@@ -306,7 +320,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
         const double* Bg = resolve(sg.b_off, sg.b_base, bases);
         const double* Ag = resolve(sg.a_off, sg.a_base, bases);
         for (int k0 = 0; k0 < K; k0 += BK) {
-          mbar_wait(&rg.empty[rg.stage], rg.phase ^ 1u);
+          mbar_wait_backoff(&rg.empty[rg.stage], rg.phase ^ 1u);
           double* as = rg.As + rg.stage * A_STAGE;
           double* bs = rg.Bs + rg.stage * B_STAGE;
           if (!(dbg & 2)) {  // timing experiment HTN_GEMM_DEBUG=2: no operand loads
