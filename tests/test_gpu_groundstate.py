@@ -1,4 +1,5 @@
-"""The reference's own ground-state tests (test/OB.jl "Dependence on parameters" :21-31 and "Tools"
+"""The reference's own ground-state tests (test/OB.jl "Dependence on parameters" :21-31, "Dependence on filling"
+:44-54 with 4-site unit cells at P/Q = 1/2 and 3/2, and "Tools"
 :94-99, test/Spin.jl :42-47), run through the product-side mirror of HubbardFunctions.jl on the GPU.
 Tolerances: the reference's own atol (1e-2 / 1e-1); like the reference's, the initial state is random
 (here seeded), and the truncated bond space the schedule lands in depends on it at the 1e-3 level.
@@ -21,8 +22,10 @@ def test_energy_matches_reference_golden(ctx, idx):
     dictionary = hf.compute_groundstate(model, ctx=ctx)
     E = dictionary["energy"]
     assert abs(E - g["E"]) < g["atol"], (g["cite"], E, g["E"])
-    exact = GOLD["lieb_wu"][str(int(g["u"][0]))]
-    assert exact - 1e-9 < E < exact + 1e-2            # variational, truncation-limited
+    if g["P"] == g["Q"]:                               # Lieb-Wu closed form: half filling only
+        exact = GOLD["lieb_wu"][str(int(g["u"][0]))]
+        assert exact - 1e-9 < E < exact + 1e-2        # variational, truncation-limited
+    assert len(dictionary["groundstate"]) == (g["Q"] if g["P"] % 2 == 0 else 2 * g["Q"])   # unit cell, HF:408-412
     # "Tools" (test/OB.jl:94-99): dim_state is a list of positive integers; filling is conserved
     psi = dictionary["groundstate"]
     D = hf.dim_state(psi)

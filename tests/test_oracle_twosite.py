@@ -47,7 +47,7 @@ def test_heff_ac2_equals_dense_and_tsvd_reconstructs(kind):
 def test_reference_schedule_reproduces_golden_energy(u):
     """IDMRG2 (Schmidt cut 1e-2 = svalue 2.0 of test/OB.jl:23,46) from the HF:917-959 initial spaces,
     then VUMPS: E/site equals the value hard-coded in the reference's tests to 1e-6 (their atol: 1e-2)."""
-    g = [r for r in GOLD["reference"] if r["u"] == [u] and not r["spin"]][0]
+    g = [r for r in GOLD["reference"] if r["u"] == [u] and not r["spin"] and r["P"] == r["Q"]][0]
     kind = S.SU2U1
     Ws, P, _ = mpo(OB_Sim(t=[1.0], u=[u]))
     sp = M.trim_spaces(kind, initial_bond_spaces(kind, [P, P], 1, 50), [P, P])

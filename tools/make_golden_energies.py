@@ -38,6 +38,8 @@ ref = [
     dict(cite="test/OB.jl:21 (U=1)", model="OB", t=[1.0], u=[1.0], P=1, Q=1, spin=False, E=grab("OB.jl", 21, "-1.037173"), atol=1e-2),
     dict(cite="test/OB.jl:21 (U=2)", model="OB", t=[1.0], u=[2.0], P=1, Q=1, spin=False, E=grab("OB.jl", 21, "-0.84163698"), atol=1e-2),
     dict(cite="test/OB.jl:44 (P/Q=1)", model="OB", t=[1.0], u=[5.0], P=1, Q=1, spin=False, E=grab("OB.jl", 44, "-0.48460447"), atol=1e-2),
+    dict(cite="test/OB.jl:44 (P/Q=1/2)", model="OB", t=[1.0], u=[5.0], P=1, Q=2, spin=False, E=grab("OB.jl", 44, "-0.73920032"), atol=1e-2),
+    dict(cite="test/OB.jl:44 (P/Q=3/2)", model="OB", t=[1.0], u=[5.0], P=3, Q=2, spin=False, E=grab("OB.jl", 44, "1.76073968"), atol=1e-2),
     dict(cite="test/Spin.jl:42", model="OB", t=[1.0], u=[8.0], P=1, Q=1, spin=True, E=grab("Spin.jl", 42, "-0.32637"), atol=1e-1),
 ]
 out = dict(
