@@ -325,8 +325,20 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
     rc = D.unit_env(HTN_SIDE_LEFT, &D.AL[i]->s0, &W[i]->Ml, 0, &D.GL[i]);
     if (rc == HTN_OK) rc = D.unit_env(HTN_SIDE_RIGHT, &D.AR[i]->s1, &W[i]->Mr, D.chi - 1, &D.GR[i]);
   }
-  for (int i = 0; i + 1 < L && rc == HTN_OK; ++i) rc = D.grow_left(i);
-  for (int i = L - 1; i > 0 && rc == HTN_OK; --i) rc = D.grow_right(i);
+  static const bool unit_start = getenv("HTN_IDMRG_UNIT_ENV") != nullptr;  // experiments: textbook iDMRG start
+  if (krylovdim > 0 && !unit_start) {
+    // MPSKit: find_groundstate(psi, H, alg::IDMRG2, envs = environments(psi, H)) -- the sweeps start from
+    // the infinite environments of the initial uniform state (oracle/twosite.py:idmrg2, init_env="infinite");
+    // empty environments let charge escape to the edges and can trap the edge bond in a one-multiplet sector
+    double el = 0, er = 0;
+    if (rc == HTN_OK) {
+      rc = htn_environments(ctx, L, D.AL.data(), D.AR.data(), D.C.data(), W, D.GL.data(), D.GR.data(), 1e-10, 30, 200, &el, &er);
+      if (rc > 0) rc = HTN_OK;  // not fully converged environments of a random state are still a valid start
+    }
+  } else {
+    for (int i = 0; i + 1 < L && rc == HTN_OK; ++i) rc = D.grow_left(i);
+    for (int i = L - 1; i > 0 && rc == HTN_OK; --i) rc = D.grow_right(i);
+  }
   if (rc < 0) return rc;
   double eps = 1e300;
   int it = 0;

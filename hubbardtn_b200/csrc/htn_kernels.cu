@@ -116,6 +116,7 @@ struct FragAddr {
   int koff[4];   // A: swizzled k offset of k4-step kk
   int b_even;    // B: krow t, swizzled column base for even 8-column atoms
   int b_odd;     //    ... for odd atoms
+  int g3;        // A: row & 3 (swizzle key)
 };
 
 template <int FLEX, bool LAYB>
@@ -147,16 +148,77 @@ __device__ __forceinline__ void mma_k4(double (&acc)[8][2][2], const double* __r
   }
 }
 
+#ifndef HTN_KUNROLL
+#define HTN_KUNROLL 4
+#endif
+
+// fragments of k4-step kk: fx = the FLEX atoms of the flex operand, ff = the two atoms of this role's strip
+template <int FLEX, bool LAYB>
+__device__ __forceinline__ void load_frags(double (&fx)[FLEX], double (&ff)[2], const double* __restrict__ as,
+                                           const double* __restrict__ bs, const FragAddr& fa, int kk) {
+  const double* ap = as + fa.a_base + (((kk ^ fa.g3) & 3) << 2) + (kk >> 2) * 16;
+  const double* bp = bs + kk * 4 * LDBS;
+  if (!LAYB) {
+#pragma unroll
+    for (int i = 0; i < FLEX; ++i) fx[i] = ap[i * 8 * LDAS];
+    ff[0] = bp[fa.b_even];
+    ff[1] = bp[fa.b_odd + 8];
+  } else {
+#pragma unroll
+    for (int j = 0; j < FLEX; ++j) fx[j] = bp[((j & 1) ? fa.b_odd : fa.b_even) + j * 8];
+    ff[0] = ap[0];
+    ff[1] = ap[8 * LDAS];
+  }
+}
+template <int FLEX, bool LAYB>
+__device__ __forceinline__ void issue_dmmas(double (&acc)[8][2][2], const double (&fx)[FLEX], const double (&ff)[2]) {
+#pragma unroll
+  for (int i = 0; i < FLEX; ++i) {
+    if (!LAYB) {
+      dmma884(acc[i][0][0], acc[i][0][1], fx[i], ff[0]);
+      dmma884(acc[i][1][0], acc[i][1][1], fx[i], ff[1]);
+    } else {
+      dmma884(acc[i][0][0], acc[i][0][1], ff[0], fx[i]);
+      dmma884(acc[i][1][0], acc[i][1][1], ff[1], fx[i]);
+    }
+  }
+}
+
 template <int FLEX, bool LAYB>
 __device__ __forceinline__ void mma_chunk(double (&acc)[8][2][2], const double* __restrict__ as,
                                           const double* __restrict__ bs, const FragAddr& fa, int nk4) {
+#if HTN_KUNROLL == 4
   if (nk4 == BK / 4) {
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) mma_k4<FLEX, LAYB>(acc, as, bs, fa, kk);
-  } else {
+  } else {  // K tail of a segment (a rolled loop here is smaller but measured 1 % slower)
     for (int kk = 0; kk < BK / 4; ++kk)
       if (kk < nk4) mma_k4<FLEX, LAYB>(acc, as, bs, fa, kk);
   }
+#else
+  // rolled K loop (small code: sixteen tile-shape specialisations share the instruction cache of an SM
+  // whose three CTAs run different ones): two k4-steps per trip, the fragments of the next step are
+  // loaded into the other register set before the DMMAs of the current one issue
+#if HTN_KUNROLL == 1
+  double fx[FLEX], ff[2];
+#pragma unroll 1
+  for (int kk = 0; kk < nk4; ++kk) {
+    load_frags<FLEX, LAYB>(fx, ff, as, bs, fa, kk);
+    issue_dmmas<FLEX, LAYB>(acc, fx, ff);
+  }
+  return;
+#endif
+  double fx0[FLEX], ff0[2], fx1[FLEX], ff1[2];
+  load_frags<FLEX, LAYB>(fx0, ff0, as, bs, fa, 0);
+#pragma unroll 1
+  for (int kk = 0; kk < nk4; kk += 2) {
+    if (kk + 1 < nk4) load_frags<FLEX, LAYB>(fx1, ff1, as, bs, fa, kk + 1);
+    issue_dmmas<FLEX, LAYB>(acc, fx0, ff0);
+    if (kk + 1 >= nk4) break;
+    if (kk + 2 < nk4) load_frags<FLEX, LAYB>(fx0, ff0, as, bs, fa, kk + 2);
+    issue_dmmas<FLEX, LAYB>(acc, fx1, ff1);
+  }
+#endif
 }
 
 struct Ring {
@@ -185,6 +247,7 @@ __device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int
   const bool active = role * 16 < (LAYB ? mt : nt);  // warp-uniform: this strip holds data
   FragAddr fa;
   fa.a_base = (LAYB ? role * 16 * LDAS : 0) + g * LDAS + t;
+  fa.g3 = g & 3;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) fa.koff[kk] = (kk ^ (g & 3)) << 2;
   {
@@ -217,29 +280,37 @@ __device__ __forceinline__ void consume_item(const GemmItem& item, Ring& rg, int
 
   if (active) {
     double* C = const_cast<double*>(resolve(item.c_off, item.c_base, bases));
-    const int ldc = item.ldc;
-    const bool beta = item.beta != 0;
+    const long long ldc = item.ldc;
+    // only the last flex atom and the strip's own edge can cross the tile extent: everything else is
+    // stored unpredicated (keeps the sixteen specialised epilogues small)
 #pragma unroll
-    for (int x = 0; x < FLEX; ++x) {
+    for (int f = 0; f < 2; ++f) {
+      const int fi = (role * 2 + f) * 8;
+      if (!LAYB) {
+        const int col = fi + 2 * t;
+        if (col < nt) {
+          const bool pair = col + 1 < nt;
+          double* p = C + g * ldc + col;
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const int ra = LAYB ? (role * 2 + f) : x;  // row atom
-        const int ca = LAYB ? x : (role * 2 + f);  // col atom
-        const int row = ra * 8 + g, col = ca * 8 + 2 * t;
-        if (row < mt && col < nt) {
-          double* p = C + (long long)row * ldc + col;
-          if (col + 1 < nt) {
-            double2 v = make_double2(acc[x][f][0], acc[x][f][1]);
-            if (beta) {
-              double2 o = *reinterpret_cast<double2*>(p);
-              v.x += o.x;
-              v.y += o.y;
+          for (int x = 0; x < FLEX; ++x) {
+            if (x < FLEX - 1 || x * 8 + g < mt) {
+              if (pair)
+                *reinterpret_cast<double2*>(p + x * 8 * ldc) = make_double2(acc[x][f][0], acc[x][f][1]);
+              else
+                p[x * 8 * ldc] = acc[x][f][0];
             }
-            *reinterpret_cast<double2*>(p) = v;
-          } else {
-            double v = acc[x][f][0];
-            if (beta) v += *p;
-            *p = v;
+          }
+        }
+      } else {
+        const int row = fi + g;
+        if (row < mt) {
+          double* p = C + row * ldc + 2 * t;
+#pragma unroll
+          for (int x = 0; x < FLEX; ++x) {
+            if (x < FLEX - 1 || x * 8 + 2 * t + 1 < nt)
+              *reinterpret_cast<double2*>(p + x * 8) = make_double2(acc[x][f][0], acc[x][f][1]);
+            else if (x * 8 + 2 * t < nt)
+              p[x * 8] = acc[x][f][0];
           }
         }
       }
@@ -313,6 +384,7 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
       const int mt = item.mt, nt = item.nt;
       GemmSeg sg{};
       if (item.seg_begin < item.seg_end) sg = segs[item.seg_begin];
+      // (padding items of the balanced schedule have mt = 0 and no segments: nothing to load)
       for (int si = item.seg_begin; si < item.seg_end; ++si) {
         GemmSeg sg_next = sg;
         if (si + 1 < item.seg_end) sg_next = segs[si + 1];
@@ -404,7 +476,9 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
       // rotate the strip a warp owns from item to item so that partially filled strips do not
       // always land on the same SM sub-partition
       const int role = (warp + it) & 3;
-      if (item.layout != 0)
+      if (item.mt == 0) {
+        // padding item of the balanced schedule
+      } else if (item.layout != 0)
         consume_dispatch<true>((item.nt + 7) >> 3, item, rg, role, lane, bases, dbg);
       else
         consume_dispatch<false>((item.mt + 7) >> 3, item, rg, role, lane, bases, dbg);

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <queue>
 
 namespace htn {
 
@@ -256,6 +258,56 @@ void Program::add_mix(std::vector<MixTaskH>& tasks, int tag) {
   if (!st.mc.empty()) stages.push_back(std::move(st));
 }
 
+// Static schedule of one GEMM stage: the kernel's CTA b walks items b, b + G, b + 2G, ...  The time a
+// tile holds its CTA is set by the flex extent (the DMMA sequence every consumer warp issues per
+// chunk) and the number of K chunks, not by its area, plus a fixed charge per chunk (ring
+// hand-over) and per item (epilogue, table reads).  Longest-processing-time-first over G CTAs with
+// that model; lists are padded to equal length with empty items (mt = 0) the kernel skips.
+static void balance_items(std::vector<GemmItem>& items, int cap) {
+  const int n = (int)items.size();
+  const int G = std::max(1, std::min(n, cap));
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("HTN_GEMM_BALANCE");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0 || n <= G) return;
+  auto cost = [](const GemmItem& it) {
+    const int flex = ((it.layout ? it.nt : it.mt) + 7) >> 3;
+    return 6.0 + (double)it.nchunks * (flex + 0.75);
+  };
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::vector<double> c(n);
+  for (int i = 0; i < n; ++i) c[i] = cost(items[i]);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c[a] > c[b]; });
+  typedef std::pair<double, int> Load;  // (load, cta)
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int b = 0; b < G; ++b) heap.push(Load(0.0, b));
+  std::vector<std::vector<int>> lists(G);
+  for (int i : order) {
+    Load l = heap.top();
+    heap.pop();
+    lists[l.second].push_back(i);
+    heap.push(Load(l.first + c[i], l.second));
+  }
+  size_t nmax = 0;
+  for (const auto& l : lists) nmax = std::max(nmax, l.size());
+  if (getenv("HTN_PLAN_DEBUG")) {
+    double tot = 0, mx = 0, mx0 = 0;
+    std::vector<double> rr(G, 0.0);
+    for (int i = 0; i < n; ++i) rr[i % G] += c[i], tot += c[i];  // the unbalanced deal (items arrive sorted by area)
+    for (int b = 0; b < G; ++b) mx0 = std::max(mx0, rr[b]);
+    while (!heap.empty()) mx = std::max(mx, heap.top().first), heap.pop();
+    fprintf(stderr, "[htn] gemm stage: %d items on %d CTAs, model load max/mean %.3f (round-robin deal %.3f), list length %zu\n",
+            n, G, mx / (tot / G), mx0 / (tot / G), nmax);
+  }
+  std::vector<GemmItem> out(nmax * (size_t)G, GemmItem{});
+  for (int b = 0; b < G; ++b)
+    for (size_t k = 0; k < lists[b].size(); ++k) out[k * G + b] = items[lists[b][k]];
+  items.swap(out);
+}
+
 int32_t Program::finalize(htn_ctx* c, int nslots_) {
   ctx = c;
   nslots = nslots_;
@@ -284,6 +336,7 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
       }
       for (GemmItem& it : st.items) fix(it.c_off, it.c_base);
       if (st.segs.empty()) st.segs.push_back(GemmSeg{});  // keep the table pointer valid
+      balance_items(st.items, cap);
       if ((rc = to_device(ctx, st.items, &st.d_items)) || (rc = to_device(ctx, st.segs, &st.d_segs))) return rc;
       st.n = (int)st.items.size();
       st.grid = std::max(1, std::min(st.n, cap));

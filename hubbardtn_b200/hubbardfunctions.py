@@ -139,24 +139,173 @@ def hamiltonian_dense(simul: OB_Sim):
     return W, levels
 
 
+@dataclass
+class MB_Sim:
+    """Multi-band Hubbard simulation parameters (HF:117-134).  `t`, `u`, `J` are B x (B + B*range) matrices:
+    the leading B x B block is the on-site part (band energies / on-band U on its diagonal), block k >= 1
+    couples band i of a cell to band j of the k-th next cell."""
+    t: np.ndarray
+    u: np.ndarray
+    J: np.ndarray = None
+    U13: np.ndarray = None
+    P: int = 1
+    Q: int = 1
+    svalue: float = 2.0
+    bond_dim: int = 50
+    kwargs: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.t = np.atleast_2d(np.asarray(self.t, float))
+        self.u = np.atleast_2d(np.asarray(self.u, float))
+        B = self.t.shape[0]
+        self.J = np.zeros((B, B)) if self.J is None else np.atleast_2d(np.asarray(self.J, float))
+        self.U13 = np.zeros((B, B)) if self.U13 is None else np.atleast_2d(np.asarray(self.U13, float))
+        if not (self.u.shape[0] == self.J.shape[0] == self.U13.shape[0] == B):
+            raise ValueError("Number of bands is incosistent.")                      # HF:826
+        for m in (self.t, self.u, self.J):
+            if m.shape[1] % B or m.shape[1] < B:
+                raise ValueError("parameter matrices must be B x (B + B*range)")
+
+    @property
+    def bands(self) -> int:
+        return self.t.shape[0]
+
+    @property
+    def spin(self) -> bool:
+        return bool(self.kwargs.get("spin", False))
+
+    @property
+    def sym(self) -> int:
+        return S.U1U1 if self.spin else S.SU2U1
+
+    @property
+    def unit_cell(self) -> int:
+        return (self.Q if self.P % 2 == 0 else 2 * self.Q) * self.bands          # HF:829-834, InfiniteStrip(B, T*B)
+
+
+def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict):
+    """Finite-state-machine MPO of  sum_p onsite[p] + sum c (c+_{p,s} c_{p+d,s} + h.c.) + sum v n_p n_{p+d}
+    on a chain with an L-site unit cell (L = len(onsite)).  hops / dens: {(p mod L, d >= 1): coefficient}.
+    A level (kind, d) means "d more sites until the term closes"; the coefficient sits on the opening
+    site, so every site shares the level list and only the dense entries differ.  Fermionic pairs carry
+    an explicit Jordan-Wigner parity string.  Returns ([W_p dense (chi,4,4,chi)], level sectors)."""
+    L = len(onsite)
+    cu, cd, par, num, dbl = _fermion_ops(sym)
+    dh = max([d for (_, d) in hops] + [0])
+    dn = max([d for (_, d) in dens] + [0])
+    levels = [(0, 0, 0)]
+    first = {}
+
+    def add(name, sectors):
+        first[name] = len(levels)
+        levels.extend(sectors)
+
+    for d in range(1, dh + 1):
+        add(("A", d), [(1, 1, Q)] if sym == S.SU2U1 else [(1, -1, Q), (1, 1, Q)])
+    for d in range(1, dh + 1):
+        add(("B", d), [(1, 1, -Q)] if sym == S.SU2U1 else [(1, -1, -Q), (1, 1, -Q)])
+    for d in range(1, dn + 1):
+        add(("N", d), [(0, 0, 0)])
+    levels.append((0, 0, 0))
+    off, acc = [], 0
+    for s in levels:
+        off.append(acc)
+        acc += S.dim(sym, s)
+    Dm, end = acc, off[-1]
+
+    def lvl(name, m):
+        return off[first[name]] + (0 if m < 0 else 1)
+
+    cdag, cann = {1: cu.T, -1: cd.T}, {1: cu, -1: cd}
+    Ws = []
+    for p in range(L):
+        W = np.zeros((Dm, 4, 4, Dm))
+        W[0, :, :, 0] = np.eye(4)
+        W[end, :, :, end] = np.eye(4)
+        W[0, :, :, end] = onsite[p]
+        for d in range(1, dh + 1):
+            for m in (-1, 1):
+                sgn = 1.0 if m > 0 else -1.0
+                a, b = lvl(("A", d), m), lvl(("B", d), m)
+                c = hops.get((p, d), 0.0)
+                if c != 0.0:
+                    W[0, :, :, a] = c * (cdag[m] @ par)                # c+_{p,s} P ... P c_{p+d,s}
+                    W[0, :, :, b] = c * sgn * (par @ cann[-m])         # h.c. through the conjugate spinor (c_dn, -c_up)
+                if d > 1:
+                    W[a, :, :, lvl(("A", d - 1), m)] = par
+                    W[b, :, :, lvl(("B", d - 1), m)] = par
+                else:
+                    W[a, :, :, end] = cann[m]
+                    W[b, :, :, end] = sgn * cdag[-m]
+        for d in range(1, dn + 1):
+            n_ = off[first[("N", d)]]
+            v = dens.get((p, d), 0.0)
+            if v != 0.0:
+                W[0, :, :, n_] = v * num
+            if d > 1:
+                W[n_, :, :, off[first[("N", d - 1)]]] = np.eye(4)
+            else:
+                W[n_, :, :, end] = num
+        Ws.append(W)
+    return Ws, levels
+
+
+def mb_terms(simul: MB_Sim):
+    """Term lists of the multi-band Hamiltonian (HF:811-910) on the chain p = band + cell * B:
+    on-band U and band energies (HF:531-551, 852-870), on-site and inter-site hopping (HF:477-519), direct
+    on-site and inter-site interactions (HF:542-561, 645-659).  Exchange, U_ijjj and the three-/four-band
+    dictionaries (HF:563-643, 662-809) are not mirrored."""
+    B, L = simul.bands, simul.unit_cell
+    if np.any(simul.J != 0) or np.any(simul.U13 != 0) or any(k in simul.kwargs for k in ("U112", "U1111", "U13_IS")):
+        raise NotImplementedError("exchange / U_ijjj / U_ijkk / U_ijkl terms (HF:563-643, 662-809) are not mirrored yet")
+    _, _, _, num, dbl = _fermion_ops(simul.sym)
+    t, u = simul.t, simul.u
+    onsite = [u[p % B, p % B] * dbl - t[p % B, p % B] * num for p in range(L)]      # OB_interaction + Chem_pot
+    hops, dens = {}, {}
+
+    def acc(dct, p, d, c):
+        if c != 0.0:
+            dct[(p % L, d)] = dct.get((p % L, d), 0.0) + c
+
+    for cell in range(L // B):
+        for bi in range(B):
+            for bf in range(bi + 1, B):
+                p = cell * B + bi
+                acc(hops, p, bf - bi, -0.5 * (t[bi, bf] + t[bf, bi]))                  # OS_Hopping (both orders of (bi,bf))
+                acc(dens, p, bf - bi, 0.5 * (u[bi, bf] + u[bf, bi]))                   # Direct_OS: U_av on the lower triangle
+        for k in range(1, t.shape[1] // B):
+            for bi in range(B):
+                for bf in range(B):
+                    acc(hops, cell * B + bi, k * B + bf - bi, -t[bi, k * B + bf])      # IS_Hopping: twosite = cdc + cdc'
+        for k in range(1, u.shape[1] // B):
+            for bi in range(B):
+                for bf in range(B):
+                    acc(dens, cell * B + bi, k * B + bf - bi, u[bi, k * B + bf])       # Direct_IS
+    return onsite, hops, dens
+
+
 class Hamiltonian:
     """`InfiniteMPOHamiltonian` stand-in: per-site reduced MPO tensors held by libhtn."""
 
-    def __init__(self, ctx, simul: OB_Sim):
+    def __init__(self, ctx, simul):
         self.simul, self.sym = simul, simul.sym
-        Wd, self.levels = hamiltonian_dense(simul)
+        if isinstance(simul, MB_Sim):
+            Wd, self.levels = fsm_mpo_dense(self.sym, simul.Q, *mb_terms(simul))
+        else:
+            W1, self.levels = hamiltonian_dense(simul)
+            Wd = [W1]
         self.phys = S.physical_space(self.sym, simul.P, simul.Q)
         self.P = dev.Legs(ctx, self.sym, self.phys)
         self.M = dev.Legs(ctx, self.sym, self.levels)
-        W = dev.Mpo.from_dense(ctx, self.M, self.P, self.M, Wd)
-        self.W = [W] * simul.unit_cell
+        mpos = [dev.Mpo.from_dense(ctx, self.M, self.P, self.M, w) for w in Wd]
+        self.W = [mpos[i % len(mpos)] for i in range(simul.unit_cell)]
         self.chi = len(self.levels)
 
     def __len__(self):
         return len(self.W)
 
 
-def hamiltonian(simul: OB_Sim, ctx=None) -> Hamiltonian:
+def hamiltonian(simul, ctx=None) -> Hamiltonian:
     return Hamiltonian(ctx, simul)
 
 
@@ -315,7 +464,11 @@ _CACHE = {}
 
 def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
     """HF:1145-1166 without the DrWatson/JLD2 disk cache (out of scope): memoised per parameter set."""
-    key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin)
+    if isinstance(simul, MB_Sim):
+        key = ("MB", simul.t.tobytes(), simul.u.tobytes(), simul.t.shape, simul.u.shape, simul.P, simul.Q, simul.svalue,
+               simul.bond_dim, simul.spin)
+    else:
+        key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin)
     if force or key not in _CACHE:
         _CACHE[key] = compute_groundstate(simul, **kw)
     return _CACHE[key]

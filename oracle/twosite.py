@@ -20,7 +20,7 @@ import numpy as np
 from . import sectors as S
 from .heff import network
 from .krylov import lanczos_lowest, vdot
-from .mps import TransferPlan, bond_norm, mul_left, mul_right, uniform_rightorth
+from .mps import Environments, TransferPlan, bond_norm, mul_left, mul_right, uniform_rightorth
 from .tensors import BondTensor, EnvTensor, Legs, MPOTensor, MPSTensor, Space
 
 
@@ -256,7 +256,8 @@ def _unit_env(side, V, M, level):
     return e
 
 
-def idmrg2(state, W_list, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol=1e-8, maxdim=None, verbose=False):
+def idmrg2(state, W_list, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol=1e-8, maxdim=None, verbose=False,
+           init_env="infinite"):
     """Two-site infinite DMRG (MPSKit `IDMRG2`): sweeps L->R, edge, R->L, edge over the unit cell
     (L >= 2), growing the environments by site transfers and the bond spaces by the truncated SVD.
     Convergence: || C_new - C_old || on the common subspace of the edge bond.  Returns
@@ -265,15 +266,24 @@ def idmrg2(state, W_list, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol
     assert L >= 2
     AL, AR, AC, C = list(state["AL"]), list(state["AR"]), list(state["AC"]), list(state["C"])
     chi = len(W_list[0].Ml)
-    GL = [_unit_env("L", AL[i].Vl, W_list[i].Ml, 0) for i in range(L)]
-    GR = [_unit_env("R", AR[i].Vr, W_list[i].Mr, chi - 1) for i in range(L)]
-    # a first pass of transfers so that the environments contain one unit cell
-    for i in range(L - 1):
-        GL[i + 1] = TransferPlan("L", W_list[i], AL[i].Vl, AL[i].P, AL[i].Vr).apply(GL[i], AL[i])
-        GL[i + 1].identity_levels = {0}
-    for i in range(L - 1, 0, -1):
-        GR[i - 1] = TransferPlan("R", W_list[i], AR[i].Vl, AR[i].P, AR[i].Vr).apply(GR[i], AR[i])
-        GR[i - 1].identity_levels = {chi - 1}
+    if init_env == "infinite":
+        # MPSKit: `find_groundstate(psi, H, alg::IDMRG2, envs = environments(psi, H))` -- the sweeps start
+        # from the infinite environments of the initial uniform state, not from empty (unit) ones
+        env0 = Environments(dict(AL=AL, AR=AR, C=C), W_list, tol=1e-10)
+        GL, GR = list(env0.GL), list(env0.GR)
+        for i in range(L):
+            GL[i].identity_levels = {0}
+            GR[i].identity_levels = {chi - 1}
+    else:
+        GL = [_unit_env("L", AL[i].Vl, W_list[i].Ml, 0) for i in range(L)]
+        GR = [_unit_env("R", AR[i].Vr, W_list[i].Mr, chi - 1) for i in range(L)]
+        # a first pass of transfers so that the environments contain one unit cell
+        for i in range(L - 1):
+            GL[i + 1] = TransferPlan("L", W_list[i], AL[i].Vl, AL[i].P, AL[i].Vr).apply(GL[i], AL[i])
+            GL[i + 1].identity_levels = {0}
+        for i in range(L - 1, 0, -1):
+            GR[i - 1] = TransferPlan("R", W_list[i], AR[i].Vl, AR[i].P, AR[i].Vr).apply(GR[i], AR[i])
+            GR[i - 1].identity_levels = {chi - 1}
     log = []
     eps = np.inf
     applies = 0

