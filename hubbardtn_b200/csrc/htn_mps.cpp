@@ -21,6 +21,8 @@ using namespace htn;
 
 extern "C" {
 bool htn_same_structure(const htn_tensor* x, const htn_tensor* y);
+int32_t htn_upload_locked(htn_tensor* t, const double* host, int64_t nelem);
+int32_t htn_download_locked(const htn_tensor* t, double* host, int64_t nelem);
 int32_t htn_heff_run(htn_plan* p, const double* x, double* y, int mask);
 int32_t htn_plan_transfer(htn_ctx* ctx, int32_t side, const htn_mpo* W, const htn_tensor* A, const htn_tensor* At,
                           const htn_tensor* env_in, const htn_tensor* env_out, htn_plan** out);
@@ -880,6 +882,256 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
   if (delta) *delta = eps;
   if (energy_per_site) *energy_per_site = 0.5 * (eL + eR) / L;
   if (iterations) *iterations = std::min(it, maxiter);
+  return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
+}
+
+// M = C^T (C C^T + delta^2)^-1 per sector, on the host (blocks are at most a few hundred wide): the
+// metric of the Grassmann gradient (MPSKit GrassmannMPS: rho_reg = regularised C C^+).
+static int32_t regularized_right_inverse(const htn_tensor* Cb, double delta, htn_tensor* M) {
+  std::vector<double> host(Cb->hsize), out(Cb->hsize, 0.0);
+  RC(htn_download_locked(Cb, host.data(), Cb->hsize));
+  for (const Block& b : Cb->blocks) {
+    const int n = b.rows;
+    const double* Cm = host.data() + b.hoff;
+    double* Mo = out.data() + b.hoff;
+    std::vector<double> K((size_t)n * n), X((size_t)n * n);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double v = (i == j) ? delta * delta : 0.0;
+        for (int k = 0; k < n; ++k) v += Cm[(size_t)i * n + k] * Cm[(size_t)j * n + k];
+        K[(size_t)i * n + j] = v;
+      }
+    // Cholesky K = G G^T (lower), then solve K X = C
+    for (int j = 0; j < n; ++j) {
+      double d = K[(size_t)j * n + j];
+      for (int k = 0; k < j; ++k) d -= K[(size_t)j * n + k] * K[(size_t)j * n + k];
+      if (!(d > 0.0)) return Cb->ctx->fail(HTN_ERR_INVALID, "gradient_grassmann: metric is not positive definite");
+      d = std::sqrt(d);
+      K[(size_t)j * n + j] = d;
+      for (int i = j + 1; i < n; ++i) {
+        double v = K[(size_t)i * n + j];
+        for (int k = 0; k < j; ++k) v -= K[(size_t)i * n + k] * K[(size_t)j * n + k];
+        K[(size_t)i * n + j] = v / d;
+      }
+    }
+    for (int c = 0; c < n; ++c) {
+      for (int i = 0; i < n; ++i) {  // forward: G y = C[:,c]
+        double v = Cm[(size_t)i * n + c];
+        for (int k = 0; k < i; ++k) v -= K[(size_t)i * n + k] * X[(size_t)k * n + c];
+        X[(size_t)i * n + c] = v / K[(size_t)i * n + i];
+      }
+      for (int i = n - 1; i >= 0; --i) {  // backward: G^T x = y
+        double v = X[(size_t)i * n + c];
+        for (int k = i + 1; k < n; ++k) v -= K[(size_t)k * n + i] * X[(size_t)k * n + c];
+        X[(size_t)i * n + c] = v / K[(size_t)i * n + i];
+      }
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Mo[(size_t)i * n + j] = X[(size_t)j * n + i];  // M = X^T
+  }
+  return htn_upload_locked(M, out.data(), M->hsize);
+}
+
+// Riemannian conjugate-gradient polish of a uniform MPS on the Grassmann manifold of its left isometries:
+// the role MPSKit's GradientGrassmann plays behind `VUMPS(...) & GradientGrassmann(...)`
+// (/root/reference/src/HubbardFunctions.jl:1025-1027).  Per site
+//   g_i = H_AC AC_i - AL_i (AL_i^T H_AC AC_i)           (tangent vector, ||g|| = Galerkin error)
+//   G_i = g_i C_i^T                                      (Euclidean gradient of the energy per cell, up to 2)
+//   d_i = g_i C_i^T (C_i C_i^T + delta^2)^-1             (gradient in the rho-weighted metric)
+// Directions are combined with Polak-Ribiere+ and moved to the new point by projection onto its
+// tangent space; the retraction is the positive QR of AL + alpha dir; the step is found by
+// backtracking on the energy of the re-gauged state (gauge fixing + environments per trial).
+// The minimiser on fixed bond spaces is the VUMPS fixed point, so converged observables agree with
+// the reference's within tol; the iteration path is not MPSKit/OptimKit's.
+// log rows of 8: galerkin error, E/site, accepted step, energy evaluations so far, beta, slope, seconds, 0.
+int32_t htn_gradient_grassmann(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR,
+                               htn_tensor* const* C, htn_tensor* const* AC, const htn_mpo* const* W,
+                               htn_tensor* const* GL, htn_tensor* const* GR, double tol, int32_t maxiter,
+                               int32_t krylovdim, double* delta, double* energy_per_site, int32_t* iterations,
+                               double* log, int32_t log_cap) {
+  if (!ctx || nsites <= 0 || !AL || !AR || !C || !AC || !W || !GL || !GR) return HTN_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  Uniform U;
+  RC(U.init_gauge(ctx, nsites, AL, AR, C, AC));
+  RC(U.refresh_ac_and_transposes());
+  RC(U.init_envs(W, GL, GR));
+  RC(U.init_heff());
+  U.eig_miniter = 2;
+  const int L = nsites;
+  cudaStream_t st = ctx->stream;
+  std::vector<htn_tensor*> AL0(L), dir(L), dirT(L), dcur(L), dold(L), Gcur(L), Gold(L), Mi(L);
+  for (int i = 0; i < L; ++i) {
+    AL0[i] = U.own.like(AL[i]);
+    dir[i] = U.own.like(AL[i]);
+    dirT[i] = U.own.like(AL[i]);
+    dcur[i] = U.own.like(AL[i]);
+    dold[i] = U.own.like(AL[i]);
+    Gcur[i] = U.own.like(AL[i]);
+    Gold[i] = U.own.like(AL[i]);
+    Mi[i] = U.own.like(C[i]);
+    if (!AL0[i] || !dir[i] || !dirT[i] || !dcur[i] || !dold[i] || !Gcur[i] || !Gold[i] || !Mi[i])
+      return ctx->fail(HTN_ERR_OOM, "gradient_grassmann: work tensor allocation failed");
+  }
+  auto now = [&]() {
+    cudaStreamSynchronize(st);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  const double t0 = now();
+  double eL = 0, eR = 0, eps = 1.0;
+  int nevals = 0;
+  // energy per cell, Galerkin error and g_i (left in U.tA[i]) of the state defined by the current AL
+  auto evaluate = [&](double* f, double* eps_out) -> int32_t {
+    const double tol_gauge = std::min(1e-10, std::max(eps * eps * 1e-2, 1e-14));
+    const double tol_env = std::min(1e-10, std::max(eps * eps * 1e-2, 1e-14));
+    RC(t_copy(U.C[L - 1], U.nC[L - 1]));
+    int32_t rc = U.rightorth(U.nC[L - 1], tol_gauge, 10000, nullptr, nullptr);
+    if (rc < 0) return rc;
+    RC(U.refresh_ac_and_transposes());
+    rc = U.environments(tol_env, krylovdim, 200, &eL, &eR, nullptr);
+    if (rc < 0) return rc;
+    *f = 0.5 * (eL + eR);
+    ++nevals;
+    return U.galerkin(eps_out);
+  };
+  // x <- x - AL_i (AL_i^T x): projection onto the tangent space at the current AL_i
+  auto project = [&](int i, htn_tensor* x) -> int32_t {
+    RC(run3(U.proj[i], U.ALt[i]->d, x->d, U.tB2[i]->d));
+    RC(run3(U.mulR[i], U.AL[i]->d, U.tB2[i]->d, U.tA2[i]->d));
+    launch_axpby(-1.0, U.tA2[i]->d, 1.0, x->d, x->dsize, st);
+    return HTN_OK;
+  };
+  auto inner = [&](const std::vector<htn_tensor*>& a, const std::vector<htn_tensor*>& b, double* out) -> int32_t {
+    double s = 0.0;
+    for (int i = 0; i < L; ++i) {
+      double v = 0.0;
+      RC(t_dot_host(a[i], a[i]->d, b[i]->d, &v));
+      s += v;
+    }
+    *out = s;
+    return HTN_OK;
+  };
+  // gradients at the current point from g_i = U.tA[i]
+  auto gradients = [&]() -> int32_t {
+    for (int i = 0; i < L; ++i) {
+      double n2 = 0.0;
+      RC(t_dot_host(U.tA[i], U.tA[i]->d, U.tA[i]->d, &n2));
+      const double dl = std::max(std::sqrt(std::max(n2, 0.0)) / 10.0, 1e-8);
+      RC(regularized_right_inverse(U.C[i], dl, Mi[i]));
+      RC(run3(U.mulR[i], U.tA[i]->d, Mi[i]->d, dcur[i]->d));
+      RC(t_transpose(U.C[i], U.tB3[i], 0));
+      RC(run3(U.mulR[i], U.tA[i]->d, U.tB3[i]->d, Gcur[i]->d));
+    }
+    return HTN_OK;
+  };
+  double f = 0.0;
+  RC(evaluate(&f, &eps));
+  RC(gradients());
+  int it = 0, done = 0;
+  double alpha = 0.25, gd_old = 0.0;
+  bool have_old = false;
+  const bool dbg = getenv("HTN_DEBUG_GG") != nullptr;
+  // state at AL0 + a dir (retracted by the positive QR): energy, Galerkin error, and the slope
+  // <G(a), P_a dir> of the energy along the transported direction
+  auto trial = [&](double a, double* fn, double* en, double* sn) -> int32_t {
+    for (int i = 0; i < L; ++i) {
+      RC(t_copy(AL0[i], U.AL[i]));
+      launch_axpby(a, dir[i]->d, 1.0, U.AL[i]->d, U.AL[i]->dsize, st);
+      RC(t_qr_inplace(U.AL[i], U.tB[i]));
+    }
+    RC(evaluate(fn, en));
+    RC(gradients());
+    for (int i = 0; i < L; ++i) {
+      RC(t_copy(dir[i], dirT[i]));
+      RC(project(i, dirT[i]));
+    }
+    return inner(Gcur, dirT, sn);
+  };
+  for (it = 1; it <= maxiter && eps >= tol; ++it) {
+    double beta = 0.0, gd = 0.0;
+    RC(inner(Gcur, dcur, &gd));
+    if (have_old && gd_old > 0.0) {
+      // Polak-Ribiere+ with the old preconditioned gradient and direction projected to the new tangent spaces
+      for (int i = 0; i < L; ++i) {
+        RC(project(i, dold[i]));
+        RC(project(i, dir[i]));
+      }
+      double gdo = 0.0;
+      RC(inner(Gcur, dold, &gdo));
+      beta = std::max(0.0, (gd - gdo) / gd_old);
+    }
+    for (int i = 0; i < L; ++i) launch_axpby(-1.0, dcur[i]->d, beta, dir[i]->d, dir[i]->dsize, st);  // dir = -d + beta dir
+    double s0 = 0.0;
+    RC(inner(Gcur, dir, &s0));
+    if (!(s0 < 0.0)) {  // not a descent direction: restart with the steepest descent
+      for (int i = 0; i < L; ++i) launch_axpby(-1.0, dcur[i]->d, 0.0, dir[i]->d, dir[i]->dsize, st);
+      s0 = -gd;
+      beta = 0.0;
+    }
+    for (int i = 0; i < L; ++i) {
+      RC(t_copy(U.AL[i], AL0[i]));
+      RC(t_copy(dcur[i], dold[i]));
+    }
+    gd_old = gd;
+    have_old = true;
+    // line search on the slope (energies differ by O(eps^2) and drown in rounding long before the gradient
+    // does): one trial step, then the secant zero of the slope; steps that raise the energy measurably are cut
+    const double noise = 1e-12 * std::max(1.0, std::fabs(f));
+    double a = alpha, fn = f, en = eps, sn = 0.0;
+    bool ok = false;
+    for (int cut = 0; cut < 10 && !ok; ++cut) {
+      RC(trial(a, &fn, &en, &sn));
+      if (dbg) fprintf(stderr, "gg it %d a %.3e f %.15f -> %.15f eps %.3e -> %.3e slope %.3e -> %.3e beta %.3f\n", it, a, f, fn, eps, en, s0, sn, beta);
+      if (fn > f + noise) {
+        a *= 0.25;
+        continue;
+      }
+      ok = true;
+      double a2 = a;
+      if (sn > 0.0)
+        a2 = a * s0 / (s0 - sn);                       // overshoot: interpolate
+      else if (sn > s0 && sn < 0.5 * s0)
+        a2 = std::min(4.0 * a, a * s0 / (s0 - sn));    // still descending steeply: extrapolate
+      else if (sn <= s0)
+        a2 = 2.0 * a;
+      if (std::fabs(a2 - a) > 0.1 * a) {
+        double f2 = fn, e2 = en, s2 = sn;
+        RC(trial(a2, &f2, &e2, &s2));
+        if (dbg) fprintf(stderr, "gg it %d   secant a %.3e f %.15f eps %.3e slope %.3e\n", it, a2, f2, e2, s2);
+        if (f2 <= fn + noise && (std::fabs(s2) < std::fabs(sn) || f2 < fn - noise)) {
+          a = a2;
+          fn = f2;
+          en = e2;
+        } else {
+          RC(trial(a, &fn, &en, &sn));                 // back to the first trial point
+        }
+      }
+    }
+    if (!ok) {  // no admissible step at this accuracy: restore the point and stop
+      for (int i = 0; i < L; ++i) RC(t_copy(AL0[i], U.AL[i]));
+      RC(evaluate(&f, &eps));
+      break;
+    }
+    f = fn;
+    eps = en;
+    alpha = a;
+    done = it;
+    if (log && it <= log_cap) {
+      double* row = log + 8 * (it - 1);
+      row[0] = eps;
+      row[1] = f / L;
+      row[2] = a;
+      row[3] = nevals;
+      row[4] = beta;
+      row[5] = s0;
+      row[6] = now() - t0;
+      row[7] = 0.0;
+    }
+  }
+  cudaStreamSynchronize(st);
+  if (delta) *delta = eps;
+  if (energy_per_site) *energy_per_site = f / L;
+  if (iterations) *iterations = done;
   return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
 }
 

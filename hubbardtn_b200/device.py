@@ -507,6 +507,18 @@ def vumps(ctx: Context, AL, AR, Cs, AC, Ws, GL, GR, tol=1e-10, maxiter=100, kryl
                 log=log[:it.value])
 
 
+def gradient_grassmann(ctx: Context, AL, AR, Cs, AC, Ws, GL, GR, tol=1e-10, maxiter=100, krylovdim=30):
+    """`find_groundstate(psi, H, GradientGrassmann(; tol, maxiter))` on fixed bond spaces (in/out tensors):
+    the polish stage of HF:1025-1027."""
+    delta, e, it = C.c_double(), C.c_double(), C.c_int32()
+    log = np.zeros((maxiter, 8))
+    rc = L.check(lib.htn_gradient_grassmann(ctx.h, len(AL), _harr(AL), _harr(AR), _harr(Cs), _harr(AC), _harr(Ws),
+                                            _harr(GL), _harr(GR), tol, maxiter, krylovdim, C.byref(delta), C.byref(e),
+                                            C.byref(it), log.ctypes.data_as(C.POINTER(C.c_double)), maxiter), ctx.h)
+    return dict(converged=rc == 0, delta=delta.value, energy_per_site=e.value, iterations=it.value,
+                log=log[:it.value])
+
+
 def idmrg2(ctx: Context, AL, AR, Cs, AC, Ws, cut=1e-2, tol=1e-6, maxiter=100, krylovdim=30, eig_tol=1e-8, maxdim=0):
     """`find_groundstate(psi, H, IDMRG2(trscheme=truncbelow(cut), tol))` (HF:1010).  The bond spaces
     change, so the tensors are REPLACED: returns new (AL, AR, C, AC) lists and an info dict."""

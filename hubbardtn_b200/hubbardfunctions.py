@@ -452,11 +452,15 @@ def compute_groundstate(simul: OB_Sim, ctx=None, tol: float = 1e-6, verbosity: i
     psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC)
     GL, GR = _make_envs(ctx, psi, H)
     info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))  # HF:1025-1027
+    info3 = None
+    if not info2["converged"]:                                             # ... & GradientGrassmann(; maxiter, tol)
+        info3 = dev.gradient_grassmann(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))
+        info2 = dict(info2, delta=info3["delta"], energy_per_site=info3["energy_per_site"], converged=info3["converged"])
     if verbosity > 0:
         print("IDMRG2: %d iterations, delta %.3e; VUMPS: %d iterations, galerkin %.3e, E/site %.10f"
               % (info1["iterations"], info1["delta"], info2["iterations"], info2["delta"], info2["energy_per_site"]))
     return {"groundstate": psi, "environments": (GL, GR), "ham": H, "delta": info2["delta"], "config": simul,
-            "energy": info2["energy_per_site"], "idmrg2": info1, "vumps": info2, "ctx": ctx}
+            "energy": info2["energy_per_site"], "idmrg2": info1, "vumps": info2, "gradient_grassmann": info3, "ctx": ctx}
 
 
 _CACHE = {}

@@ -244,6 +244,18 @@ int32_t htn_vumps(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tenso
                   htn_tensor* const* AC, const htn_mpo* const* W, htn_tensor* const* GL, htn_tensor* const* GR,
                   double tol, int32_t maxiter, int32_t krylovdim, double* delta, double* energy_per_site,
                   int32_t* iterations, double* log, int32_t log_cap);
+/* Replaces: the `GradientGrassmann(; maxiter, tol)` stage of `VUMPS(...) & GradientGrassmann(...)`
+ * (HubbardFunctions.jl:1025-1027; MPSKit GrassmannMPS + OptimKit): Riemannian conjugate-gradient descent
+ * of the energy per unit cell over the left isometries AL on fixed bond spaces (metric C C^T regularised,
+ * positive-QR retraction, Polak-Ribiere+ directions, backtracking on the energy).  In/out as htn_vumps;
+ * delta = final Galerkin error (gradient norm).  log rows of 8 doubles per iteration (galerkin error,
+ * energy per site, accepted step, energy evaluations so far, beta, slope, seconds, 0).  The converged
+ * state is the VUMPS fixed point; the iteration path is not OptimKit's.  HTN_NOT_CONVERGED at maxiter. */
+int32_t htn_gradient_grassmann(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, htn_tensor* const* AR,
+                               htn_tensor* const* C, htn_tensor* const* AC, const htn_mpo* const* W,
+                               htn_tensor* const* GL, htn_tensor* const* GR, double tol, int32_t maxiter,
+                               int32_t krylovdim, double* delta, double* energy_per_site, int32_t* iterations,
+                               double* log, int32_t log_cap);
 /* Replaces: `find_groundstate(psi, H, IDMRG2(trscheme = truncbelow(cut), tol, maxiter))`
  * (HubbardFunctions.jl:1010): two-site infinite DMRG over a unit cell of nsites >= 2 with bond spaces
  * re-defined by the truncated SVD (keep Schmidt values >= cut, at most maxdim multiplets if maxdim > 0).

@@ -72,6 +72,8 @@ def test_idmrg2_needs_two_sites_and_rejects_unmirrored_models(ctx):
     psi = hf.initialize_mps(H, 1, 50, False, ctx)
     rc = _lib.lib.htn_idmrg2(ctx.h, 1, None, None, None, None, None, 1e-2, 1e-6, 1, 30, 1e-8, 0, None, None, None, 0)
     assert rc == _lib.HTN_ERR_INVALID
+    rc = _lib.lib.htn_gradient_grassmann(ctx.h, 2, None, None, None, None, None, None, None, 1e-8, 10, 30, None, None, None, None, 0)
+    assert rc == _lib.HTN_ERR_INVALID
     assert len(psi) == 2
 
 

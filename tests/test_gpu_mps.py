@@ -239,3 +239,26 @@ def test_qrpos_is_orthogonal_on_ill_conditioned_panels(ctx):
         assert np.abs(Qr.T @ Qr - np.eye(n)).max() < 5e-13
         assert np.abs(Qr @ Rb[r] - Ar).max() < 1e-13 * np.abs(Ar).max() * 10
         assert (np.diag(Rb[r]) > 0).all()
+
+
+@pytest.mark.parametrize("kind,u,D", [(S.SU2U1, 8.0, 10), (S.U1U1, 4.0, 12)])
+def test_gradient_grassmann_reaches_the_vumps_fixed_point(ctx, kind, u, D):
+    """HF:1025-1027 `VUMPS(maxiter) & GradientGrassmann(maxiter, tol)`: VUMPS stopped early, the Riemannian
+    CG polish takes the state to the same variational minimum the oracle's converged VUMPS finds on these
+    bond spaces: energy per site within 1e-10 relative, densities within 1e-7, gradient norm below tol,
+    energy non-increasing along the accepted steps."""
+    Ws, P, spaces, st0 = _hubbard_state(kind, u=u, D=D)
+    st, envs, eps, log = M.vumps(st0, Ws, tol=1e-10, maxiter=300)
+    assert eps < 1e-10
+    du = DevUniform(ctx, kind, st0, Ws)
+    res = dev.vumps(ctx, du.AL, du.AR, du.C, du.AC, du.W, du.GL, du.GR, tol=1e-10, maxiter=3)
+    assert not res["converged"] and res["delta"] > 1e-6
+    gg = dev.gradient_grassmann(ctx, du.AL, du.AR, du.C, du.AC, du.W, du.GL, du.GR, tol=1e-8, maxiter=1500)
+    assert gg["converged"] and gg["delta"] < 1e-8, (gg["delta"], gg["iterations"])
+    E, Eo = gg["energy_per_site"], envs.energy_per_site
+    assert E < res["energy_per_site"] + 1e-12
+    assert abs(E - Eo) < 1e-10 * abs(Eo), (E, Eo)
+    assert np.all(np.diff(gg["log"][:, 1]) < 1e-11)
+    vals = [0, 2, 1] if kind == S.SU2U1 else [0, 2, 1, 1]
+    for i in range(2):
+        assert abs(dev.expval_diag(du.AC[i], vals) - M.expval_diag(st["AC"][i], vals)) < 1e-7
