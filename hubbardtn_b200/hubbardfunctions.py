@@ -4,7 +4,9 @@ Names, arguments and return conventions follow `src/HubbardFunctions.jl` of the 
 parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
 
     OB_Sim(t, u, mu, J, P, Q, svalue, bond_dim, period; kwargs...)      HF:76-93
-    hamiltonian(simul)                                                  HF:386-472 (t, u, mu terms)
+    MB_Sim(t, u, J, U13, P, Q, svalue, bond_dim; kwargs...)             HF:117-134
+    hamiltonian(simul)                                                  HF:386-472 (t, u, mu terms), HF:811-910 (hopping,
+                                                                        band energies, on-band U, direct interactions)
     initialize_mps(H, P, max_dimension, spin)                           HF:917-959
     compute_groundstate(simul; tol, verbosity, maxiter)                 HF:993-1030
     produce_groundstate(simul; force)                                   HF:1145-1166 (in-memory cache only)
@@ -15,9 +17,8 @@ parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
 The reference delegates the numerics to MPSKit; here `compute_groundstate` drives the same schedule
 (IDMRG2 with truncbelow(10^-svalue), then VUMPS) through the C ABI on the GPU.  This module contains
 host bookkeeping only (spaces, the MPO as a finite-state machine, random initial blocks); it never
-touches `oracle/`.  Not mirrored yet: exchange / U13 / staggered-field / helix terms (HF:445-469),
-one-site unit cells (the VUMPS + SvdCut bond-growing loop, HF:1011-1022) and the GradientGrassmann
-polish (HF:1026).
+touches `oracle/`.  Not mirrored yet: exchange / U13 / staggered-field / helix terms (HF:445-469, 563-643,
+662-809) and one-site unit cells (the VUMPS + SvdCut bond-growing loop, HF:1011-1022).
 """
 from __future__ import annotations
 
