@@ -213,6 +213,17 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     ++n_u;
   }
   *n_mix_t = (int)(mixU.size() + like->blocks.size());
+  // launch order of the U mixes: a T block feeds ~1.7 U blocks (other MPO levels b, other s'); walking the targets
+  // in the order of their first source puts those readers next to each other in time, so the repeat reads of T hit L2
+  if (!getenv("HTN_MIX_ORDER_BY_TARGET")) {
+    auto first_src = [](const MixTaskH& t) {
+      int64_t m = INT64_MAX;
+      for (const MixSrcH& q : t.srcs)
+        if (q.src.slot == SLOT_WS) m = std::min<int64_t>(m, q.src.off);
+      return m;
+    };
+    std::stable_sort(mixU.begin(), mixU.end(), [&](const MixTaskH& a, const MixTaskH& b) { return first_src(a) < first_src(b); });
+  }
   pg.add_mix(mixU, TAG_W);
   pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y);
   *n_u_out = n_u;

@@ -161,7 +161,12 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
   // split-K: a reduce task has few tiles but a K loop over every (level, sector) pair; cut the
   // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy of
   // the output block (summed in fixed order by the mix => deterministic, no atomics)
-  const int SPLIT_CHUNKS = 640 / GEMM_BK, SPLIT_MAX = 32;
+  static int split_k = 0;
+  if (split_k == 0) {
+    const char* e = getenv("HTN_SPLIT_K");  // tuning knob: K extent of one split-K part
+    split_k = e ? std::max(GEMM_BK, atoi(e)) : 640;
+  }
+  const int SPLIT_CHUNKS = split_k / GEMM_BK, SPLIT_MAX = 32;
   Stage st;
   st.kind = 0;
   st.tag = tag_gemm;
