@@ -176,7 +176,7 @@ struct GemmItem {
   int nchunks;  // sum over segments of ceil(K / BK)
   int beta;     // 0: overwrite, 1: accumulate
   int layout;   // 0: flex = M, strips over N ; 1: flex = N, strips over M (htn_kernels.cu)
-  int pad_;
+  int group;    // host scheduling only: items that read the same large operand block share a group (>= 0)
 };
 
 struct MixSrc {

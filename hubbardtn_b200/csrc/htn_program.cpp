@@ -5,7 +5,9 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <queue>
+#include <tuple>
 
 namespace htn {
 
@@ -108,6 +110,16 @@ int64_t Program::ws_alloc(int64_t elems) {
   return off;
 }
 
+typedef std::map<std::tuple<int, int64_t, int>, int> GroupMap;
+static int group_id(GroupMap& g, const Opnd& o, int tile_off) {
+  auto key = std::make_tuple(o.slot, o.off, tile_off);
+  auto it = g.find(key);
+  if (it != g.end()) return it->second;
+  const int id = (int)g.size();
+  g[key] = id;
+  return id;
+}
+
 static void emit_seg(Stage& st, const GemmSegH& s, const TileSpec& ts) {
   GemmSeg sg{};
   enc(s.A, sg.a_off, sg.a_base);
@@ -124,6 +136,7 @@ void Program::add_gemm(std::vector<GemmTaskH>& tasks, int tag) {
   Stage st;
   st.kind = 0;
   st.tag = tag;
+  GroupMap groups;
   for (const GemmTaskH& t : tasks) {
     for (const GemmSegH& s : t.segs) {
       flops += 2.0 * t.M * t.N * s.K;
@@ -140,8 +153,10 @@ void Program::add_gemm(std::vector<GemmTaskH>& tasks, int tag) {
       it.beta = 0;
       it.seg_begin = (int)st.segs.size();
       it.nchunks = 0;
+      it.group = -1;
       for (const GemmSegH& s : t.segs) {
         if (s.K <= 0) continue;
+        if (it.group < 0) it.group = group_id(groups, s.A, ts.mo);   // stage L: the environment block is the big shared operand
         emit_seg(st, s, ts);
         it.nchunks += (s.K + GEMM_BK - 1) / GEMM_BK;
         padded_flops += padded_tile_flops(ts.mn, ts.nn, s.K);
@@ -170,6 +185,7 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
   Stage st;
   st.kind = 0;
   st.tag = tag_gemm;
+  GroupMap groups;
   std::vector<MixTaskH> mixes;
   for (size_t ti = 0; ti < tasks.size(); ++ti) {
     const GemmTaskH& t = tasks[ti];
@@ -218,6 +234,7 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
           it.beta = 0;
           it.seg_begin = (int)st.segs.size();
           it.nchunks = 0;
+          it.group = group_id(groups, segs[cut[sp]]->B, ts.no);   // stage R: parts that start on the same GR block walk the same GR blocks
           for (int q = cut[sp]; q < cut[sp + 1]; ++q) {
             emit_seg(st, *segs[q], ts);
             it.nchunks += (segs[q]->K + GEMM_BK - 1) / GEMM_BK;
@@ -281,27 +298,62 @@ static void balance_items(std::vector<GemmItem>& items, int cap) {
     const int flex = ((it.layout ? it.nt : it.mt) + 7) >> 3;
     return 6.0 + (double)it.nchunks * (flex + 0.75);
   };
-  std::vector<int> order(n);
-  for (int i = 0; i < n; ++i) order[i] = i;
   std::vector<double> c(n);
-  for (int i = 0; i < n; ++i) c[i] = cost(items[i]);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c[a] > c[b]; });
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) total += (c[i] = cost(items[i]));
+  // units of scheduling: single items.  Experiment HTN_GEMM_BALANCE=3: the items of one group (same big operand
+  // block) stay together on one CTA, back to back, so that the repeat reads of that block hit L2 (groups heavier
+  // than a quarter of a CTA's share are cut).  Measured SLOWER (stage L +4 %, stage R +18 %): a CTA then runs
+  // look-alike tiles in a row and the three CTAs of an SM fall into the same load/DMMA/store phases.
+  std::vector<std::vector<int>> units;
+  {
+    std::map<int, std::vector<int>> by_group;
+    for (int i = 0; i < n; ++i) {
+      if (items[i].group < 0 || mode != 3)
+        units.push_back({i});
+      else
+        by_group[items[i].group].push_back(i);
+    }
+    const double cap_unit = 0.25 * total / G;
+    for (auto& kv : by_group) {
+      std::vector<int> cur;
+      double acc = 0.0;
+      for (int i : kv.second) {
+        if (!cur.empty() && acc + c[i] > cap_unit) {
+          units.push_back(cur);
+          cur.clear();
+          acc = 0.0;
+        }
+        cur.push_back(i);
+        acc += c[i];
+      }
+      if (!cur.empty()) units.push_back(cur);
+    }
+  }
+  const int nu = (int)units.size();
+  std::vector<double> uc(nu, 0.0);
+  for (int u = 0; u < nu; ++u)
+    for (int i : units[u]) uc[u] += c[i];
+  std::vector<int> order(nu);
+  for (int u = 0; u < nu; ++u) order[u] = u;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return uc[a] > uc[b]; });
   typedef std::pair<double, int> Load;  // (load, cta)
   std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
   for (int b = 0; b < G; ++b) heap.push(Load(0.0, b));
   std::vector<std::vector<int>> lists(G);
-  for (int i : order) {
+  for (int u : order) {
     Load l = heap.top();
     heap.pop();
-    lists[l.second].push_back(i);
-    heap.push(Load(l.first + c[i], l.second));
+    for (int i : units[u]) lists[l.second].push_back(i);
+    heap.push(Load(l.first + uc[u], l.second));
   }
   size_t nmax = 0;
   for (const auto& l : lists) nmax = std::max(nmax, l.size());
   if (getenv("HTN_PLAN_DEBUG")) {
     double tot = 0, mx = 0, mx0 = 0;
     std::vector<double> rr(G, 0.0);
-    for (int i = 0; i < n; ++i) rr[i % G] += c[i], tot += c[i];  // the unbalanced deal (items arrive sorted by area)
+    for (int i = 0; i < n; ++i) rr[i % G] += c[i], tot += c[i];
+    fprintf(stderr, "[htn] gemm stage: %d scheduling units\n", nu);  // the unbalanced deal (items arrive sorted by area)
     for (int b = 0; b < G; ++b) mx0 = std::max(mx0, rr[b]);
     while (!heap.empty()) mx = std::max(mx, heap.top().first), heap.pop();
     fprintf(stderr, "[htn] gemm stage: %d items on %d CTAs, model load max/mean %.3f (round-robin deal %.3f), list length %zu\n",
