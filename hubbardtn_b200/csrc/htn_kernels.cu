@@ -335,7 +335,7 @@ __device__ __forceinline__ void consume_dispatch(int flex, const GemmItem& item,
 
 __global__ void __launch_bounds__(NTHREADS, NPROD_WARPS == 1 ? 3 : 2)
 grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restrict__ segs, int nitems,
-                    const __grid_constant__ Bases bases, int dbg, int nsm) {
+                    const __grid_constant__ Bases bases, int dbg) {
   extern __shared__ __align__(16) double smem[];
   Ring rg;
   rg.As = smem;
@@ -357,21 +357,10 @@ grouped_gemm_kernel(const GemmItem* __restrict__ items, const GemmSeg* __restric
   }
   __syncthreads();
   if (blockIdx.x >= nitems) return;
-  // Item order of this CTA.  Items are sorted by cost and dealt round-robin, so every CTA owns a
-  // similar mix; the CTAs that share an SM (blockIdx = sm, sm + nsm, sm + 2 nsm) walk their lists in
-  // different orders (forward / backward / from the middle) so that their load, DMMA and store phases
-  // do not run in lockstep.
+  // CTA b walks items b, b + G, b + 2G, ...: the host lays the table out as one list per CTA (balanced by a cost
+  // model, ordered so that the CTAs sharing an SM are out of phase; htn_program.cpp:balance_items).
   const int n_mine = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int wave = (dbg & 4) ? 0 : ((int)blockIdx.x / nsm) % 3;
-  auto item_index = [&](int j) {
-    int k = j;
-    if (wave == 1) k = n_mine - 1 - j;
-    if (wave == 2) {
-      k = j + n_mine / 2;
-      if (k >= n_mine) k -= n_mine;
-    }
-    return (int)blockIdx.x + k * (int)gridDim.x;
-  };
+  auto item_index = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 
   if (warp >= NCONS_WARPS) {
     // =========================== PRODUCER (one warp) ================================
@@ -511,14 +500,7 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const B
     const char* e = getenv("HTN_GEMM_DEBUG");  // timing experiments only (results are wrong when set)
     dbg = e ? atoi(e) : 0;
   }
-  static int nsm = 0;
-  if (nsm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (nsm <= 0) nsm = 148;
-  }
-  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases, dbg, nsm);
+  grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases, dbg);
 }
 
 // ------------------------------------------------------------------------------------

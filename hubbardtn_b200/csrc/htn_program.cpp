@@ -285,7 +285,7 @@ void Program::add_mix(std::vector<MixTaskH>& tasks, int tag) {
 // chunk) and the number of K chunks, not by its area, plus a fixed charge per chunk (ring
 // hand-over) and per item (epilogue, table reads).  Longest-processing-time-first over G CTAs with
 // that model; lists are padded to equal length with empty items (mt = 0) the kernel skips.
-static void balance_items(std::vector<GemmItem>& items, int cap) {
+static void balance_items(std::vector<GemmItem>& items, int cap, int tag, int nsm) {
   const int n = (int)items.size();
   const int G = std::max(1, std::min(n, cap));
   static int mode = -1;
@@ -347,6 +347,65 @@ static void balance_items(std::vector<GemmItem>& items, int cap) {
     for (int i : units[u]) lists[l.second].push_back(i);
     heap.push(Load(l.first + uc[u], l.second));
   }
+  if (mode == 4) {  // experiment: random order inside every CTA's list (fixed seed)
+    uint64_t rs = 0x9E3779B97F4A7C15ull;
+    for (auto& l : lists)
+      for (size_t k = l.size(); k > 1; --k) {
+        rs = rs * 6364136223846793005ull + 1442695040888963407ull;
+        std::swap(l[k - 1], l[(size_t)((rs >> 33) % k)]);
+      }
+  }
+  // Order inside a CTA's list (LPT leaves it sorted by falling cost).  The three CTAs of an SM overlap best when
+  // long and short tiles alternate: 1 = zigzag (largest, smallest, 2nd largest, ...), 2 = interleave the two
+  // halves (largest, median, 2nd largest, ...), 0 = falling cost.  Stage L (many short-K tiles per CTA) gains
+  // 6 % from the zigzag; stage R (a handful of long split-K parts per CTA) loses 8 % and keeps falling cost.
+  static int order_l = -1, order_r = -1;
+  if (order_l < 0) {
+    const char* e = getenv("HTN_ORDER_L");
+    order_l = e ? atoi(e) : 1;
+    e = getenv("HTN_ORDER_R");
+    order_r = e ? atoi(e) : 0;
+  }
+  const int ord = mode == 5 ? 1 : (tag == TAG_L ? order_l : order_r);
+  if (ord == 1 || ord == 2) {
+    for (auto& l : lists) {
+      std::vector<int> z;
+      if (ord == 1) {
+        size_t lo = 0, hi = l.size();
+        while (lo < hi) {
+          z.push_back(l[lo++]);
+          if (lo < hi) z.push_back(l[--hi]);
+        }
+      } else {
+        const size_t h = (l.size() + 1) / 2;
+        for (size_t k = 0; k < h; ++k) {
+          z.push_back(l[k]);
+          if (k + h < l.size()) z.push_back(l[k + h]);
+        }
+      }
+      l.swap(z);
+    }
+  }
+  // De-phasing of the CTAs that share an SM (blockIdx = sm, sm + nsm, sm + 2 nsm): 0 = forward / backward / from
+  // the middle, 1 = cyclic shifts by thirds of the list
+  static int wave_mode = -1;
+  if (wave_mode < 0) {
+    const char* e = getenv("HTN_WAVE");
+    wave_mode = e ? atoi(e) : 0;
+  }
+  for (int b = 0; b < G; ++b) {
+    std::vector<int>& l = lists[b];
+    const int w = (b / std::max(1, nsm)) % 3, nl = (int)l.size();
+    if (w == 0 || nl < 2) continue;
+    if (wave_mode == 0) {
+      if (w == 1)
+        std::reverse(l.begin(), l.end());
+      else
+        std::rotate(l.begin(), l.begin() + nl / 2, l.end());
+    } else if (wave_mode == 1) {
+      std::rotate(l.begin(), l.begin() + (w * nl) / 3, l.end());
+    }
+  }
   size_t nmax = 0;
   for (const auto& l : lists) nmax = std::max(nmax, l.size());
   if (getenv("HTN_PLAN_DEBUG")) {
@@ -393,7 +452,7 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
       }
       for (GemmItem& it : st.items) fix(it.c_off, it.c_base);
       if (st.segs.empty()) st.segs.push_back(GemmSeg{});  // keep the table pointer valid
-      balance_items(st.items, cap);
+      balance_items(st.items, cap, st.tag, ctx->sm_count);
       if ((rc = to_device(ctx, st.items, &st.d_items)) || (rc = to_device(ctx, st.segs, &st.d_segs))) return rc;
       st.n = (int)st.items.size();
       st.grid = std::max(1, std::min(st.n, cap));
