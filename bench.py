@@ -158,9 +158,17 @@ def groundstate_leg(ctx, args):
     the same schedule on the host CPU beside it (numpy, single process; NOT MPSKit)."""
     from hubbardtn_b200 import hubbardfunctions as hf
     model = hf.OB_Sim([1.0], [8.0], 0.0, [0.0], 1, 1, 2.0)
-    hf.compute_groundstate(model, ctx=ctx, tol=1e-8)             # warm-up (plans, allocations)
+    H0 = hf.hamiltonian(model, ctx)
+    psi0 = hf.initialize_mps(H0, model.P, model.bond_dim, False, ctx)      # one seeded random start for both arms
+
+    def fresh():
+        return hf.InfiniteMPS(ctx, psi0.sym, *[[t.like_copy() for t in lst] for lst in (psi0.AL, psi0.AR, psi0.C, psi0.AC)])
+
+    hf.compute_groundstate(model, ctx=ctx, tol=1e-8, init_state=fresh())   # warm-up (plans, allocations)
+    start = fresh()
+    ctx.synchronize()
     t0 = time.perf_counter()
-    d = hf.compute_groundstate(model, ctx=ctx, tol=1e-8)
+    d = hf.compute_groundstate(model, ctx=ctx, tol=1e-8, init_state=start)
     ctx.synchronize()
     gpu_s = time.perf_counter() - t0
     out = {
@@ -173,11 +181,19 @@ def groundstate_leg(ctx, args):
         import numpy as np
         from oracle import mps as M, sectors as OS, twosite as T2
         from oracle.hubbard import OB_Sim as OSim, mpo
-        from oracle.spaces import initial_bond_spaces
-        t0 = time.perf_counter()
+        from oracle import bridge
+        from oracle.tensors import Space as OSpace
         Ws, P, _ = mpo(OSim(t=[1.0], u=[8.0]))
-        sp = M.trim_spaces(OS.SU2U1, initial_bond_spaces(OS.SU2U1, [P, P], 1, 50), [P, P])
-        st = M.random_state(OS.SU2U1, sp, [P, P], np.random.default_rng(1))
+        # the same initial state as the GPU arm: its left isometries, brought to mixed gauge by the oracle
+        L = len(psi0)
+        Vd = [psi0.C[i].space(0, psi0.sym) for i in range(L)]
+        Vo = [OSpace(OS.SU2U1, dict(zip(v.sectors, v.mult))) for v in Vd]
+        tab = lambda t: (t.labels, t.rows, t.cols, t.offsets)  # noqa: E731
+        ALo = [bridge.mps_from_packed(Vo[i - 1], P, Vo[i], tab(psi0.AL[i]), psi0.AL[i].download()) for i in range(L)]
+        C0 = bridge.bond_from_packed(Vo[L - 1], tab(psi0.C[L - 1]), psi0.C[L - 1].download())
+        t0 = time.perf_counter()
+        ARo, Co, _ = M.uniform_rightorth(ALo, C0, tol=1e-12)
+        st = dict(AL=ALo, AR=ARo, C=Co, AC=[M.mul_right(ALo[i], Co[i]) for i in range(L)])
         AL, C, AR, eps, log = T2.idmrg2(st, Ws, cut=1e-2, tol=1e-8, maxiter=200)
         st2, envs, eps2, log2 = M.vumps(T2.idmrg2_to_uniform(AR, C), Ws, tol=1e-8, maxiter=200)
         out["cpu_port_seconds"] = time.perf_counter() - t0
