@@ -101,6 +101,46 @@ def test_heff_ac_full_size_properties(ctx):
         assert rel_err(views[ky], acc) < 1e-11
 
 
+def test_heff_ac_c3_shape_u1u1(ctx):
+    """BASELINE config C3 shape: U(1)xU(1) (abelian, four one-dimensional hopping sectors, many more bond sectors),
+    D=512: full apply against the oracle's planned apply."""
+    case = synthetic.HeffCase(ctx, PS.U1U1, D=512, chi=6)
+    _apply_and_compare(case, naive=False)
+
+
+def test_heff_ac_c5_shape_properties(ctx):
+    """BASELINE config C5 shape (D=2048, chi=160 MPO levels, the largest single-GPU case: ~4 GB of workspaces):
+    the oracle needs minutes per apply here, so parity rests on size-independent properties -- linearity,
+    determinism -- plus the oracle's term list evaluated for the two smallest output blocks."""
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=2048, chi=160)
+    st = case.plan.stats
+    assert st["flops"] > 1.5e11                  # ~8x the D=1024, chi=96 apply (D^3 chi)
+    x, y = case.x, case.y
+    case.plan.apply(x, y)
+    y1 = y.download()
+    case.plan.apply(x, y)
+    assert np.array_equal(y1, y.download())
+    z = x.like().upload(synthetic.random_packed(x.nelem, 78))
+    hz = x.like()
+    case.plan.apply(z, hz)
+    comb = x.like()
+    comb.axpby(1.5, x, 0.0)
+    comb.axpby(-0.25, z, 1.0)
+    hc = x.like()
+    case.plan.apply(comb, hc)
+    assert rel_err(hc.download(), 1.5 * y1 - 0.25 * hz.download()) < 1e-12
+    ov = oracle_view(case)
+    terms = oheff.heff_ac_terms(ov["GL"], ov["W"], ov["GR"], ov["x"])
+    views = case.y.block_views(y1)
+    keys = sorted(views.keys(), key=lambda k: views[k].size)
+    for ky in keys[:2]:
+        acc = np.zeros(views[ky].shape)
+        for (k0, kgl, kx, kgr, cf) in terms:
+            if k0 == ky:
+                acc += cf * (ov["GL"].blocks[kgl] @ ov["x"].blocks[kx] @ ov["GR"].blocks[kgr])
+        assert rel_err(views[ky], acc) < 1e-11
+
+
 def test_blocktables_match_oracle_order(ctx):
     case = synthetic.HeffCase(ctx, PS.U1U1, D=40, chi=5)
     oracle_view(case)   # asserts sector order + block order + offsets inside
