@@ -528,3 +528,20 @@ def density_state(psi: InfiniteMPS):
     """<n_i> per site (HF:1495-1542; `expectation_value(psi, i => n)` HF:1507)."""
     vals = [0.0, 2.0, 1.0] if psi.sym == S.SU2U1 else [0.0, 2.0, 1.0, 1.0]
     return [dev.expval_diag(psi.AC[i], vals) for i in range(len(psi))]
+
+
+def density_spin(psi: InfiniteMPS):
+    """(<n_up>_i, <n_down>_i) per site for a U(1)xU(1) state (HF:1413-1454): n_up is 1 on the doubly occupied and
+    the up multiplet, n_down on the doubly occupied and the down multiplet."""
+    if psi.sym != S.U1U1:
+        raise ValueError("This system is spin independent.")                  # HF:1424
+    up = [dev.expval_diag(psi.AC[i], [0.0, 1.0, 1.0, 0.0]) for i in range(len(psi))]
+    down = [dev.expval_diag(psi.AC[i], [0.0, 1.0, 0.0, 1.0]) for i in range(len(psi))]
+    return up, down
+
+
+def calc_ms(psi: InfiniteMPS):
+    """Staggered magnetisation |<n_up> - <n_down>| of the first site (HF:1461-1468)."""
+    up, down = density_spin(psi)
+    mag = [u - d for u, d in zip(up, down)]
+    return abs(mag[0])

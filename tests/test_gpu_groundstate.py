@@ -85,3 +85,24 @@ def test_multiband_coupled_model_converges(ctx):
     n = hf.density_state(d["groundstate"])
     assert abs(sum(n) / len(n) - 1.0) < 1e-8
     assert d["ham"].chi == 2 + 2 * 3 + 2                                 # hop distance <= 3 (A and B strings), n.n distance <= 2
+
+
+def test_multiband_spin_model_and_spin_densities(ctx):
+    """test/Spin.jl:20-30,49-53 (two-band model with spin=true, U(1)xU(1): E_norm2 = -0.63093, atol 1e-1) and the
+    "Tools" block :78-86: the spin-resolved densities add up to the total density; an SU(2) state refuses them."""
+    import numpy as np
+    g = GOLD["reference_mb"][1]
+    assert g["spin"]
+    model = hf.MB_Sim(np.array(g["t"]), np.array(g["u"]), None, None, g["P"], g["Q"], 2.0, g["bond_dim"], kwargs={"spin": True})
+    d = hf.compute_groundstate(model, ctx=ctx)
+    assert abs(d["energy"] - g["E"]) < g["atol"], (d["energy"], g["E"])
+    assert GOLD["lieb_wu"]["3"] - 1e-9 < d["energy"]
+    psi = d["groundstate"]
+    N = hf.density_state(psi)
+    up, down = hf.density_spin(psi)
+    assert abs(sum(N) - sum(up) - sum(down)) < 1e-9                      # Spin.jl:80,85
+    assert all(abs(n - u - dn) < 1e-9 for n, u, dn in zip(N, up, down))
+    assert hf.calc_ms(psi) < 0.5 + 1e-9
+    d1 = hf.compute_groundstate(hf.OB_Sim([1.0], [8.0], 0.0, [0.0], 1, 1, 2.0), ctx=ctx)
+    with pytest.raises(ValueError):
+        hf.density_spin(d1["groundstate"])

@@ -47,6 +47,10 @@ ref_mb = [
     dict(cite="test/MB.jl:59", model="MB", t=[[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]],
          u=[[3.0, 0.0, 0.0, 0.0], [0.0, 3.0, 0.0, 0.0]], P=1, Q=1, spin=False, bond_dim=20,
          E=grab("MB.jl", 59, "-0.630375296"), atol=1e-1),
+    # test/Spin.jl:20-30,49: the same two-band model with spin=true (U(1)xU(1)); atol = tol = 1e-1 (Spin.jl:12)
+    dict(cite="test/Spin.jl:49", model="MB", t=[[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]],
+         u=[[3.0, 0.0, 0.0, 0.0], [0.0, 3.0, 0.0, 0.0]], P=1, Q=1, spin=True, bond_dim=20,
+         E=grab("Spin.jl", 49, "-0.63093"), atol=1e-1),
 ]
 out = dict(
     note="reference: values hard-coded in DaanVrancken/HubbardTN tests (truncation-limited, loose atol); "
