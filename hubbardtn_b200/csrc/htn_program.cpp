@@ -367,10 +367,18 @@ static void balance_items(std::vector<GemmItem>& items, int cap, int tag, int ns
     order_r = e ? atoi(e) : 0;
   }
   const int ord = mode == 5 ? 1 : (tag == TAG_L ? order_l : order_r);
-  if (ord == 1 || ord == 2) {
+  if (ord == 3 || ord == 4) {  // experiments: zigzag over the K length (3) or the flex extent (4) instead of the cost
+    for (auto& l : lists)
+      std::stable_sort(l.begin(), l.end(), [&](int a, int b) {
+        if (ord == 3) return items[a].nchunks > items[b].nchunks;
+        const int fa = items[a].layout ? items[a].nt : items[a].mt, fb = items[b].layout ? items[b].nt : items[b].mt;
+        return fa > fb;
+      });
+  }
+  if (ord >= 1 && ord <= 4) {
     for (auto& l : lists) {
       std::vector<int> z;
-      if (ord == 1) {
+      if (ord != 2) {
         size_t lo = 0, hi = l.size();
         while (lo < hi) {
           z.push_back(l[lo++]);
