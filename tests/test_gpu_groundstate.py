@@ -106,3 +106,18 @@ def test_multiband_spin_model_and_spin_densities(ctx):
     d1 = hf.compute_groundstate(hf.OB_Sim([1.0], [8.0], 0.0, [0.0], 1, 1, 2.0), ctx=ctx)
     with pytest.raises(ValueError):
         hf.density_spin(d1["groundstate"])
+
+
+def test_gradient_grassmann_stage_runs_after_unconverged_vumps(ctx):
+    """HF:1025-1027 with a small `maxiter`: VUMPS stops early, the GradientGrassmann stage takes over on the 4-site
+    two-band cell (site-dependent MPO) and does not raise the energy; with the default maxiter it is never entered."""
+    import numpy as np
+    g = GOLD["reference_mb"][0]
+    model = hf.MB_Sim(np.array(g["t"]), np.array(g["u"]), None, None, g["P"], g["Q"], 2.0, g["bond_dim"])
+    d = hf.compute_groundstate(model, ctx=ctx, tol=1e-9, maxiter=6)
+    gg = d["gradient_grassmann"]
+    assert gg is not None and gg["iterations"] >= 1
+    assert gg["energy_per_site"] <= d["vumps"]["log"][-1, 1] + 1e-12
+    assert np.all(np.diff(gg["log"][:, 1]) < 1e-11) and gg["delta"] < d["vumps"]["log"][-1, 0] * 1.5
+    full = hf.compute_groundstate(model, ctx=ctx)
+    assert full["gradient_grassmann"] is None and full["delta"] < 1e-6
