@@ -17,8 +17,10 @@ parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
 The reference delegates the numerics to MPSKit; here `compute_groundstate` drives the same schedule
 (IDMRG2 with truncbelow(10^-svalue), then VUMPS) through the C ABI on the GPU.  This module contains
 host bookkeeping only (spaces, the MPO as a finite-state machine, random initial blocks); it never
-touches `oracle/`.  Not mirrored yet: exchange / U13 / staggered-field / helix terms (HF:445-469, 563-643,
-662-809) and one-site unit cells (the VUMPS + SvdCut bond-growing loop, HF:1011-1022).
+touches `oracle/`.  The helix (`period`) and staggered-field (`JMs`) variants of the one-band model (HF:458-465)
+go through the same site-dependent finite-state-machine builder as `MB_Sim`.  Not mirrored yet: exchange / U13 /
+U_ijkk / U_ijkl terms (HF:445-457, 563-643, 662-809) and one-site unit cells (the VUMPS + SvdCut bond-growing
+loop, HF:1011-1022).
 """
 from __future__ import annotations
 
@@ -81,8 +83,9 @@ def hamiltonian_dense(simul: OB_Sim):
     """H = sum_i [u1 n_up n_dn - mu n]_i - sum_r t_r sum_i,s (c+_{i,s} c_{i+r,s} + h.c.) + sum_{r>=2} u_r n_i n_{i+r-1}
     (HF:424-444) as an upper-triangular MPO W[a, s', s, b] with explicit Jordan-Wigner strings.
     Returns (W dense, level sectors)."""
-    if simul.period != 0 or any(k in simul.kwargs for k in ("U13", "JMs")) or any(abs(j) > 0 for j in simul.J):
-        raise NotImplementedError("exchange / U13 / staggered-field / helix terms (HF:445-469) are not mirrored yet")
+    if simul.period != 0 or "U13" in simul.kwargs or any(abs(j) > 0 for j in simul.J):
+        raise NotImplementedError("exchange / U13 terms (HF:445-457) are not mirrored yet; helix and staggered field go "
+                                  "through ob_extended_terms")
     sym, Q = simul.sym, simul.Q
     cu, cd, par, num, dbl = _fermion_ops(sym)
     t, u = list(simul.t), list(simul.u)
@@ -285,6 +288,39 @@ def mb_terms(simul: MB_Sim):
     return onsite, hops, dens
 
 
+def ob_extended_terms(simul: OB_Sim):
+    """Term lists of the one-band variants that go beyond `hamiltonian_dense`: the helix of circumference `period`
+    (HF:463-465: -t (c+_i c_{i+1} + c+_i c_{i+period} + h.c.), on-site U only) and the staggered field
+    J_inter Ms (-1)^i S^z_i of `JMs` (HF:458-462, U(1)xU(1) only; i = 1..T as `enumerate` counts)."""
+    L = simul.unit_cell
+    cu, cd, par, num, dbl = _fermion_ops(simul.sym)
+    t, u = list(simul.t), list(simul.u)
+    JMs = simul.kwargs.get("JMs", (0.0, 0.0))
+    if any(abs(j) > 0 for j in simul.J) or "U13" in simul.kwargs:
+        raise NotImplementedError("exchange / U13 terms (HF:445-457) are not mirrored yet")
+    onsite = [(u[0] if u else 0.0) * dbl - simul.mu * num for _ in range(L)]
+    hops, dens = {}, {}
+    if simul.period != 0:
+        if len(t) != 1 or len(u) != 1:
+            raise ValueError("Extended models in 2D not implemented.")            # HF:467
+        for p in range(L):
+            for d in (1, simul.period):
+                hops[(p, d)] = hops.get((p, d), 0.0) - t[0]
+    else:
+        for p in range(L):
+            for r, tr in enumerate(t, start=1):
+                if tr != 0.0:
+                    hops[(p, r)] = -tr
+            for r, ur in enumerate(u[1:], start=1):
+                if ur != 0.0:
+                    dens[(p, r)] = ur
+    if JMs[1] != 0.0 and simul.spin:
+        sz = 0.5 * (cu.T @ cu - cd.T @ cd)
+        for p in range(L):
+            onsite[p] = onsite[p] + JMs[0] * JMs[1] * (-1.0) ** (p + 1) * sz
+    return onsite, hops, dens
+
+
 class Hamiltonian:
     """`InfiniteMPOHamiltonian` stand-in: per-site reduced MPO tensors held by libhtn."""
 
@@ -292,6 +328,8 @@ class Hamiltonian:
         self.simul, self.sym = simul, simul.sym
         if isinstance(simul, MB_Sim):
             Wd, self.levels = fsm_mpo_dense(self.sym, simul.Q, *mb_terms(simul))
+        elif simul.period != 0 or (simul.kwargs.get("JMs", (0.0, 0.0))[1] != 0.0 and simul.spin):
+            Wd, self.levels = fsm_mpo_dense(self.sym, simul.Q, *ob_extended_terms(simul))
         else:
             W1, self.levels = hamiltonian_dense(simul)
             Wd = [W1]
@@ -473,7 +511,8 @@ def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
         key = ("MB", simul.t.tobytes(), simul.u.tobytes(), simul.t.shape, simul.u.shape, simul.P, simul.Q, simul.svalue,
                simul.bond_dim, simul.spin)
     else:
-        key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin)
+        key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin,
+               simul.period, tuple(simul.kwargs.get("JMs", (0.0, 0.0))))
     if force or key not in _CACHE:
         _CACHE[key] = compute_groundstate(simul, **kw)
     return _CACHE[key]

@@ -121,3 +121,21 @@ def test_gradient_grassmann_stage_runs_after_unconverged_vumps(ctx):
     assert np.all(np.diff(gg["log"][:, 1]) < 1e-11) and gg["delta"] < d["vumps"]["log"][-1, 0] * 1.5
     full = hf.compute_groundstate(model, ctx=ctx)
     assert full["gradient_grassmann"] is None and full["delta"] < 1e-6
+
+
+def test_helix_and_staggered_field_ground_states(ctx):
+    """HF:458-465 variants of the one-band model through the site-dependent MPO path: a helix of circumference 3
+    (extra hop at distance 3) lowers the kinetic energy below the chain's; a staggered field J_inter Ms (-1)^i S^z_i
+    on the spin-resolved model induces a staggered magnetisation of the sign the field selects."""
+    chain = hf.compute_groundstate(hf.OB_Sim([1.0], [4.0], 0.0, [0.0], 1, 1, 2.0), ctx=ctx)
+    helix = hf.compute_groundstate(hf.OB_Sim([1.0], [4.0], 0.0, [0.0], 1, 1, 2.0, 50, 3), ctx=ctx)
+    assert helix["delta"] < 1e-5 and helix["ham"].chi == 2 + 2 * 3
+    n = hf.density_state(helix["groundstate"])
+    assert abs(sum(n) / len(n) - 1.0) < 1e-8
+    assert helix["energy"] < chain["energy"] - 1e-3
+    stag = hf.compute_groundstate(hf.OB_Sim([1.0], [6.0], 0.0, [0.0], 1, 1, 2.0, 50, 0,
+                                            kwargs={"spin": True, "JMs": (1.0, 0.5)}), ctx=ctx)
+    up, down = hf.density_spin(stag["groundstate"])
+    m = [u - d for u, d in zip(up, down)]
+    assert m[0] > 0.05 and m[1] < -0.05 and abs(m[0] + m[1]) < 1e-6      # site 1 carries (-1)^1 = -1: the field lowers the energy of up there
+    assert hf.calc_ms(stag["groundstate"]) > 0.05

@@ -109,3 +109,38 @@ def test_unmirrored_terms_raise():
         hf.mb_terms(hf.MB_Sim(t, u, np.array([[0.0, 0.5], [0.5, 0.0]])))
     with pytest.raises(ValueError):
         hf.MB_Sim(t, np.eye(3))
+
+
+def _ob_direct(sim, N, hop_dists, field=None):
+    c = jw_ops(sim.sym, N)
+    H = np.zeros((4 ** N, 4 ** N))
+    for p in range(N):
+        nu, nd = c[p][0].T @ c[p][0], c[p][1].T @ c[p][1]
+        H += sim.u[0] * nu @ nd - sim.mu * (nu + nd)
+        if field is not None:
+            H += field * (-1.0) ** ((p % sim.unit_cell) + 1) * 0.5 * (nu - nd)
+        for d in hop_dists:
+            if p + d < N:
+                for s in (0, 1):
+                    H += -sim.t[0] * (c[p][s].T @ c[p + d][s] + c[p + d][s].T @ c[p][s])
+    return H
+
+
+def test_helix_and_staggered_field_variants():
+    """HF:463-465 (helix of circumference `period`: hops at distance 1 and period) and HF:458-462 (staggered field
+    J_inter Ms (-1)^i S^z_i, spin-resolved symmetry only) against the directly written Hamiltonians."""
+    N = 5
+    helix = hf.OB_Sim([1.3], [4.0], 0.2, [0.0], 1, 1, 2.0, 50, 3)
+    Ws, _ = hf.fsm_mpo_dense(helix.sym, helix.Q, *hf.ob_extended_terms(helix))
+    assert np.abs(chain_from_mpo(Ws, N) - _ob_direct(helix, N, (1, 3))).max() < 1e-12
+    with pytest.raises(ValueError):
+        hf.ob_extended_terms(hf.OB_Sim([1.0, 0.5], [4.0], 0.0, [0.0], 1, 1, 2.0, 50, 3))     # HF:467
+    stag = hf.OB_Sim([1.0], [6.0], 0.0, [0.0], 1, 1, 2.0, 50, 0, kwargs={"spin": True, "JMs": (0.7, 0.4)})
+    Ws, _ = hf.fsm_mpo_dense(stag.sym, stag.Q, *hf.ob_extended_terms(stag))
+    assert len(Ws) == 2 and np.abs(Ws[0] - Ws[1]).max() > 0.1                                 # site-dependent
+    assert np.abs(chain_from_mpo(Ws, N) - _ob_direct(stag, N, (1,), field=0.7 * 0.4)).max() < 1e-12
+    # without spin resolution the field is ignored, as in the reference (HF:458 `&& spin`)
+    plain = hf.OB_Sim([1.0], [6.0], 0.0, [0.0], 1, 1, 2.0, 50, 0, kwargs={"JMs": (0.7, 0.4)})
+    W1, _ = hf.hamiltonian_dense(plain)
+    W0, _ = hf.hamiltonian_dense(hf.OB_Sim([1.0], [6.0], 0.0, [0.0], 1, 1, 2.0))
+    assert np.array_equal(W1, W0)
