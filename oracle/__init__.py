@@ -17,7 +17,10 @@ Pinning status (see DESIGN.md "Oracle"):
   * every block-sparse contraction is checked against its dense (symmetry-free)
     expansion, and the MPO against an exact-diagonalisation Hamiltonian;
   * end-to-end energies are checked against the reference's golden vectors and the
-    Lieb-Wu Bethe-ansatz values;
+    Lieb-Wu Bethe-ansatz values: the full HF:993-1030 schedule reproduces the printed
+    digits of test/OB.jl:21,44 (one-band, 2- and 4-site cells) and of test/MB.jl:59
+    (-0.630375296, two-band 4-site cell, which also pins that IDMRG2 starts from the
+    infinite environments of the initial state as MPSKit does);
   * intermediate quantities (block tables, single applies) are unpinned by the
     reference (it has no such tests): parity for those is "oracle-defined".
 
