@@ -547,6 +547,18 @@ def TruncState(simul: OB_Sim, trunc_dim: int, trunc_scheme: int = 1, **kw):
     return best
 
 
+def produce_TruncState(simul, trunc_dim: int, trunc_scheme: int = 1, force: bool = False, **kw):
+    """HF:1378-1387 without the disk cache: {"ψ_trunc": state, "envs_trunc": (GL, GR)} as `TruncState` returns in
+    the reference (HF:1366); the environments are those of the truncated state."""
+    if force:
+        produce_groundstate(simul, force=True, **kw)
+    psi = TruncState(simul, trunc_dim, trunc_scheme, **kw)
+    d = produce_groundstate(simul, **kw)
+    GL, GR = _make_envs(d["ctx"], psi, d["ham"])
+    dev.environments(d["ctx"], psi.AL, psi.AR, psi.C, d["ham"].W, GL, GR, tol=1e-10)
+    return {"ψ_trunc": psi, "psi_trunc": psi, "envs_trunc": (GL, GR)}
+
+
 def dim_state(psi: InfiniteMPS):
     """Full (quantum-dimension weighted) bond dimension of every site's left bond (HF:1399-1405)."""
     out = []

@@ -139,3 +139,22 @@ def test_helix_and_staggered_field_ground_states(ctx):
     m = [u - d for u, d in zip(up, down)]
     assert m[0] > 0.05 and m[1] < -0.05 and abs(m[0] + m[1]) < 1e-6      # site 1 carries (-1)^1 = -1: the field lowers the energy of up there
     assert hf.calc_ms(stag["groundstate"]) > 0.05
+
+
+def test_multiband_tools_block(ctx):
+    """test/MB.jl:94-107 "Tools": produce_TruncState(model, 5; trunc_scheme=1), dim_state, density_state."""
+    import numpy as np
+    g = GOLD["reference_mb"][0]
+    model = hf.MB_Sim(np.array(g["t"]), np.array(g["u"]), None, None, g["P"], g["Q"], 2.0, g["bond_dim"])
+    dictionary = hf.produce_groundstate(model, ctx=ctx, force=True)
+    trunc_dim = 5
+    dict_trunc = hf.produce_TruncState(model, trunc_dim, trunc_scheme=1, ctx=ctx)
+    D = hf.dim_state(dictionary["groundstate"])
+    assert all(isinstance(x, int) and x > 0 for x in D)                          # MB.jl:98-100
+    D_trunc = hf.dim_state(dict_trunc["ψ_trunc"])
+    assert sum(D_trunc) / 4 <= trunc_dim and max(D) > trunc_dim                  # MB.jl:102-103
+    electron_number = hf.density_state(dictionary["groundstate"])
+    assert abs(sum(electron_number) / 4 - g["P"] / g["Q"]) < 1e-8                # MB.jl:105-106
+    assert len(dict_trunc["envs_trunc"][0]) == 4
+    with pytest.raises(NotImplementedError):
+        hf.TruncState(model, trunc_dim, trunc_scheme=0, ctx=ctx)                 # VUMPSSvdCut: not mirrored
