@@ -103,6 +103,7 @@ SIGNATURES = {
                          _pd, _i32]),
     "htn_gradient_grassmann": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, _pp, _pp, C.c_double, _i32, _i32, _pd, _pd,
                                       _pi32, _pd, _i32]),
+    "htn_mul_bond": (_i32, [_p, _p, _i32, C.POINTER(C.c_void_p)]),
     "htn_expval_diag": (_i32, [_p, _pd, _i32, _pd]),
     "htn_entanglement_spectrum": (_i32, [_p, _pd, _i64]),
     "htn_idmrg2": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, C.c_double, C.c_double, _i32, _i32, C.c_double, _i32, _pd,

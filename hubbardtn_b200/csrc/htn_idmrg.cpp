@@ -442,6 +442,22 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
   return eps < tol ? HTN_OK : HTN_NOT_CONVERGED;
 }
 
+// out = A . C (right) or C . A (left): the AC = AL C = C AR products of MPSKit (`_mul_tail` / `_mul_front`)
+int32_t htn_mul_bond(const htn_tensor* A, const htn_tensor* Cb, int32_t right, htn_tensor** out) {
+  if (!A || !Cb || !out) return HTN_ERR_INVALID;
+  htn_ctx* ctx = A->ctx;
+  *out = nullptr;
+  if (A->kind != HTN_T_MPS || Cb->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "mul_bond: needs an MPS and a bond tensor");
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  int32_t rc = mul_bond(ctx, A, Cb, right != 0, out);
+  if (rc != HTN_OK && *out) {
+    htn_tensor_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
 // Gauge-fix site tensors into a consistent uniform MPS in mixed gauge (MPSKit `InfiniteMPS(A...)`).
 //   from_right = 0: AL[i] hold (approximate) left isometries: AL <- Q(AL), then AR, C by the iterated LQ;
 //   from_right = 1: AR[i] hold (approximate) right isometries -- the list whose bond spaces chain after

@@ -550,6 +550,69 @@ def changebonds_svdcut(ctx: Context, AL, AR, Cs, AC, Ws, cut=0.0, maxdim=0, sym=
     return uniform_from_right(ctx, AR, Cs[-1], sym)
 
 
+def mul_bond(A: Tensor, Cb: Tensor, right: bool = True) -> Tensor:
+    """A . C (right) or C . A (left) as a new MPS tensor (MPSKit `_mul_tail` / `_mul_front`)."""
+    h = C.c_void_p()
+    L.check(lib.htn_mul_bond(A.h, Cb.h, 1 if right else 0, C.byref(h)), A.ctx.h)
+    return Tensor(A.ctx, h)
+
+
+def _identity_bond(ctx: Context, V: Space) -> Tensor:
+    t = Tensor.bond(ctx, V)
+    g = np.zeros(t.nelem)
+    for blk in t.block_views(g).values():
+        blk[...] = np.eye(blk.shape[0])
+    return t.upload(g)
+
+
+def changebonds_vumpssvdcut(ctx: Context, AL, AR, Cs, AC, Ws, P: Legs, sym: int = 0, cut: float = 0.0, maxdim: int = 0,
+                            krylovdim: int = 30, eig_tol: float = 1e-10, tol_gauge: float = 1e-12):
+    """`changebonds(psi, H, VUMPSSvdCut(; trscheme))` for unit cells of two or more sites (MPSKit `changebonds_n`;
+    HF:1016, 1363): for every site loc the two-site tensor AC[loc] AR[loc+1] is replaced by the lowest eigenvector of
+    H_AC2, the bond matrix C[loc+1] by that of H_C, the two-site tensor is split by a truncated SVD (AL1, S V), the
+    second site is regauged as in VUMPS (AL2 = Q(S V) Q(C)^T), and the state and its environments are rebuilt from the
+    new left isometries before the next site.  Difference to MPSKit: the bonds are first brought to the cap by SvdCut
+    (see below).  Inputs are left untouched; returns new (AL, AR, C, AC, GL, GR)."""
+    n = len(AL)
+    if n < 2:
+        raise NotImplementedError("VUMPSSvdCut on a one-site unit cell (MPSKit changebonds_1) is not mirrored")
+    AL, AR, Cs, AC = [[t.like_copy() for t in lst] for lst in (AL, AR, Cs, AC)]
+    if maxdim > 0 or cut > 0.0:
+        # MPSKit rebuilds the state with InfiniteMPS(...) after every site, which shrinks the neighbouring bonds to
+        # full rank; the positive QR used here needs that up front, so all bonds are first cut to the same cap by
+        # SvdCut and the sweep below re-optimises and re-cuts them at that size.
+        AL, AR, Cs, AC = changebonds_svdcut(ctx, AL, AR, Cs, AC, Ws, cut=cut, maxdim=maxdim, sym=sym)
+    chi = len(Ws[0].Ml)
+
+    def envs():
+        V = [Cs[i].space(0, sym) for i in range(n)]
+        GL = [Tensor.env(ctx, 0, V[i - 1], Ws[i].Ml, identity_level=0) for i in range(n)]
+        GR = [Tensor.env(ctx, 1, V[i], Ws[i].Mr, identity_level=chi - 1) for i in range(n)]
+        environments(ctx, AL, AR, Cs, Ws, GL, GR, tol=1e-10)
+        return GL, GR
+
+    GL, GR = envs()
+    for loc in range(n):
+        nxt, nn = (loc + 1) % n, (loc + 2) % n
+        x2 = Tensor.mps2(ctx, AC[loc].space(0, sym), P, P, AR[nxt].space(1, sym))
+        contract_two_site(AC[loc], AR[nxt], x2)
+        y2 = x2.like()
+        HeffAC2(ctx, GL[loc], Ws[loc], Ws[nxt], GR[nxt], x2).eigsolve(x2, y2, krylovdim, eig_tol)
+        nC = Cs[nxt].like()
+        HeffC(ctx, GL[nn], GR[nxt], Cs[nxt]).eigsolve(Cs[nxt], nC, krylovdim, eig_tol)
+        _, AL1, S, V, _ = tsvd(y2, cut, maxdim, sym)
+        ACn = mul_bond(V, S, right=False)
+        AL2 = ACn.like()
+        regauge(ACn, nC, AL2)
+        AL[loc], AL[nxt] = AL1, AL2
+        AR = [a.like() for a in AL]
+        AC = [a.like() for a in AL]
+        Cs = [Tensor.bond(ctx, AL[i].space(1, sym)) for i in range(n)]
+        mixed_gauge(ctx, AL, _identity_bond(ctx, AL[n - 1].space(1, sym)), AR, Cs, AC, tol=tol_gauge)
+        GL, GR = envs()
+    return AL, AR, Cs, AC, GL, GR
+
+
 def mixed_gauge(ctx: Context, AL, C_guess: Tensor, AR, Cs, AC, tol=1e-12, maxiter=10000, from_right=False):
     """`InfiniteMPS(A...)` gauge fixing.  from_right=False: AL holds left isometries (in/out), AR, C, AC are
     outputs.  from_right=True: AR holds right isometries (MPSKit `InfiniteMPS(psi.AR)` after IDMRG2); AL, C, AC

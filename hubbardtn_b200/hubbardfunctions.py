@@ -10,7 +10,7 @@ parity tests read like the reference's own tests (test/OB.jl, test/Spin.jl):
     initialize_mps(H, P, max_dimension, spin)                           HF:917-959
     compute_groundstate(simul; tol, verbosity, maxiter)                 HF:993-1030
     produce_groundstate(simul; force)                                   HF:1145-1166 (in-memory cache only)
-    TruncState(simul, trunc_dim; trunc_scheme=1)                        HF:1351-1387 (SvdCut scheme)
+    TruncState(simul, trunc_dim; trunc_scheme=0)                        HF:1351-1387 (VUMPSSvdCut / SvdCut)
     dim_state(psi)                                                      HF:1399-1405
     density_state(psi)                                                  HF:1475-1542
 
@@ -518,26 +518,35 @@ def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
     return _CACHE[key]
 
 
-def TruncState(simul: OB_Sim, trunc_dim: int, trunc_scheme: int = 1, **kw):
+def TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, **kw):
     """HF:1351-1366: ground state truncated to (full) bond dimension `trunc_dim` with
-    `changebonds(psi, SvdCut(trscheme = truncdim(trunc_dim)))` (trunc_scheme 1; the VUMPSSvdCut variant,
-    scheme 0, is not mirrored).  The cap is applied to the number of kept multiplets such that the full
-    dimension sum_c dim(c) n_c stays <= trunc_dim (TensorKit's truncdim counts the full dimension)."""
-    if trunc_scheme != 1:
-        raise NotImplementedError("VUMPSSvdCut truncation (HF:1363) is not mirrored yet")
+    `changebonds(psi, H, VUMPSSvdCut(trscheme = truncdim(trunc_dim)))` (trunc_scheme 0, the reference's default) or
+    `changebonds(psi, SvdCut(trscheme = truncdim(trunc_dim)))` (trunc_scheme 1).  The cap is applied to the number of
+    kept multiplets such that the full dimension sum_c dim(c) n_c stays <= trunc_dim (TensorKit's truncdim counts the
+    full dimension)."""
     if trunc_dim <= 0:
         raise ValueError("trunc_dim should be a positive integer.")           # HF:1353
+    if trunc_scheme not in (0, 1):
+        raise ValueError("trunc_scheme should be either 0 (VUMPSSvdCut) or 1 (SvdCut).")   # HF:1356
     d = produce_groundstate(simul, **kw)
     psi, H, ctx = d["groundstate"], d["ham"], d["ctx"]
+
+    def truncated(cap):
+        if trunc_scheme == 1:
+            AL, AR, C, AC = dev.changebonds_svdcut(ctx, [t.like_copy() for t in psi.AL], [t.like_copy() for t in psi.AR],
+                                                   [t.like_copy() for t in psi.C], [t.like_copy() for t in psi.AC], H.W,
+                                                   maxdim=cap, sym=psi.sym)
+        else:
+            AL, AR, C, AC, _, _ = dev.changebonds_vumpssvdcut(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, H.P, psi.sym,
+                                                              maxdim=cap)
+        return InfiniteMPS(ctx, psi.sym, AL, AR, C, AC)
+
     # multiplets are kept largest-first; find the largest multiplet count whose full dimension fits
     best = None
     lo, hi = 1, max(sum(sp.values()) for sp in (psi.bond_space(i) for i in range(len(psi))))
     while lo <= hi:
         mid = (lo + hi) // 2
-        AL, AR, C, AC = dev.changebonds_svdcut(ctx, [t.like_copy() for t in psi.AL], [t.like_copy() for t in psi.AR],
-                                               [t.like_copy() for t in psi.C], [t.like_copy() for t in psi.AC], H.W,
-                                               maxdim=mid, sym=psi.sym)
-        cand = InfiniteMPS(ctx, psi.sym, AL, AR, C, AC)
+        cand = truncated(mid)
         if max(dim_state(cand)) <= trunc_dim:
             best, lo = cand, mid + 1
         else:
@@ -547,7 +556,7 @@ def TruncState(simul: OB_Sim, trunc_dim: int, trunc_scheme: int = 1, **kw):
     return best
 
 
-def produce_TruncState(simul, trunc_dim: int, trunc_scheme: int = 1, force: bool = False, **kw):
+def produce_TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, force: bool = False, **kw):
     """HF:1378-1387 without the disk cache: {"ψ_trunc": state, "envs_trunc": (GL, GR)} as `TruncState` returns in
     the reference (HF:1366); the environments are those of the truncated state."""
     if force:

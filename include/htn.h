@@ -205,6 +205,10 @@ int32_t htn_qrpos(const htn_tensor* A, htn_tensor* Q, htn_tensor* R);
 int32_t htn_lqpos(const htn_tensor* A, htn_tensor* L, htn_tensor* Q);
 /* Replaces: MPSKit `regauge!`: AL = Q(AC) Q(C)^T. */
 int32_t htn_regauge(const htn_tensor* AC, const htn_tensor* C, htn_tensor* AL);
+/* Replaces: the bond products MPSKit writes as `A * C` / `C * A` (`_mul_tail`, `_mul_front`; AC = AL C = C AR):
+ * right != 0: out[l,s,r] = A[l,s,r] . C[r];  right == 0: out[l,s,r] = C[l] . A[l,s,r].  A new MPS tensor with the
+ * structure of A is created (caller destroys it). */
+int32_t htn_mul_bond(const htn_tensor* A, const htn_tensor* C, int32_t right, htn_tensor** out);
 /* Replaces: MPSKit `uniform_rightorth!` (entered through InfiniteMPS(...), HubbardFunctions.jl:958,990
  * and VUMPS's gauge step): from left-orthonormal AL[0..n) and a guess for C[n-1] compute AR[i], C[i]
  * (C[i] on the bond right of site i, unit norm) with AL[i] C[i] = C[i-1] AR[i]. */

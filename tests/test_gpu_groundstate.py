@@ -43,7 +43,7 @@ def test_truncstate_tools(ctx):
     psi = d["groundstate"]
     full = max(hf.dim_state(psi))
     target = max(4, full // 2)
-    cut = hf.TruncState(model, target, ctx=ctx)
+    cut = hf.TruncState(model, target, trunc_scheme=1, ctx=ctx)
     assert max(hf.dim_state(cut)) <= target < full
     n = hf.density_state(cut)
     assert abs(sum(n) / len(n) - 1.0) < 1e-8
@@ -156,5 +156,34 @@ def test_multiband_tools_block(ctx):
     electron_number = hf.density_state(dictionary["groundstate"])
     assert abs(sum(electron_number) / 4 - g["P"] / g["Q"]) < 1e-8                # MB.jl:105-106
     assert len(dict_trunc["envs_trunc"][0]) == 4
-    with pytest.raises(NotImplementedError):
-        hf.TruncState(model, trunc_dim, trunc_scheme=0, ctx=ctx)                 # VUMPSSvdCut: not mirrored
+    with pytest.raises(ValueError):
+        hf.TruncState(model, trunc_dim, trunc_scheme=2, ctx=ctx)                 # HF:1356
+    cut0 = hf.TruncState(model, 8, ctx=ctx)                                      # default scheme 0 (VUMPSSvdCut), 4-site cell
+    assert max(hf.dim_state(cut0)) <= 8 < max(D)
+    n0 = hf.density_state(cut0)
+    assert abs(sum(n0) / 4 - 1.0) < 1e-8
+
+
+def test_truncstate_vumpssvdcut_scheme(ctx):
+    """HF:1363 `changebonds(psi, H, VUMPSSvdCut(trscheme = truncdim(D)))` (the reference's default trunc_scheme 0):
+    the truncated state respects the cap and the filling, its energy is variational, and -- the two-site tensors
+    are re-optimised before they are cut -- not worse than the plain SvdCut truncation at the same cap."""
+    from hubbardtn_b200 import device as dev
+    model = hf.OB_Sim([1.0], [5.0], 0.0, [0.0], 1, 1, 2.5)
+    d = hf.produce_groundstate(model, ctx=ctx, force=True)
+    full = max(hf.dim_state(d["groundstate"]))
+    target = max(4, full // 2)
+
+    def energy(psi):
+        GL, GR = hf._make_envs(ctx, psi, d["ham"])
+        e = dev.environments(ctx, psi.AL, psi.AR, psi.C, d["ham"].W, GL, GR, tol=1e-12)
+        return 0.5 * (e["energy_cell_left"] + e["energy_cell_right"]) / len(psi)
+
+    cut0 = hf.TruncState(model, target, ctx=ctx)                     # scheme 0
+    cut1 = hf.TruncState(model, target, trunc_scheme=1, ctx=ctx)
+    assert max(hf.dim_state(cut0)) <= target < full
+    n = hf.density_state(cut0)
+    assert abs(sum(n) / len(n) - 1.0) < 1e-8
+    E0, E1 = energy(cut0), energy(cut1)
+    assert d["energy"] - 1e-10 < E0 < d["energy"] + 0.05
+    assert E0 < E1 + 1e-6, (E0, E1)
