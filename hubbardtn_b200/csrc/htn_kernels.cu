@@ -508,14 +508,17 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const B
 // target; chunk sizes shrink with the number of sources so that every CTA streams a similar
 // number of bytes; source descriptors are staged in shared memory; loads are unrolled x4.
 // ------------------------------------------------------------------------------------
+// Occupancy is what this kernel lives on: at 42 registers (5 CTAs/SM) it streamed 4.1 TB/s, capped at 32 registers
+// (8 CTAs/SM = 64 warps) 4.9 TB/s; a grid of 32 CTAs per SM walking the chunk list adds another 2 %.
 constexpr int MIX_MAX_SRC_SMEM = 128;
 
-__global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ tg, const MixSrc* __restrict__ src,
-                                                  const MixChunk* __restrict__ chunks,
+__global__ void __launch_bounds__(256, 8) mix_kernel(const MixTarget* __restrict__ tg, const MixSrc* __restrict__ src,
+                                                  const MixChunk* __restrict__ chunks, int nchunks,
                                                   const __grid_constant__ Bases bases) {
   __shared__ const double* sptr[MIX_MAX_SRC_SMEM];
   __shared__ double scoef[MIX_MAX_SRC_SMEM];
-  const MixChunk ch = chunks[blockIdx.x];
+  for (int cidx = blockIdx.x; cidx < nchunks; cidx += gridDim.x) {
+  const MixChunk ch = chunks[cidx];
   const MixTarget T = tg[ch.target];
   double* dst = const_cast<double*>(resolve(T.off, T.base, bases));
   const int nsrc = T.src_end - T.src_begin;
@@ -556,12 +559,22 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixTarget* __restrict__ 
     }
     if (nsrc == 0) break;
   }
+  }
 }
 
 void launch_mix(const MixTarget* tg, const MixSrc* src, const MixChunk* chunks, int nchunks, const Bases& bases,
                 cudaStream_t st) {
   if (nchunks <= 0) return;
-  mix_kernel<<<nchunks, 256, 0, st>>>(tg, src, chunks, bases);
+  static int grid_cap = 0;
+  if (grid_cap == 0) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("HTN_MIX_CTAS_PER_SM");  // 0 = one CTA per chunk
+    const int per = e ? atoi(e) : 32;
+    grid_cap = per > 0 ? per * nsm : 1 << 30;
+  }
+  mix_kernel<<<std::min(nchunks, grid_cap), 256, 0, st>>>(tg, src, chunks, nchunks, bases);
 }
 
 // ------------------------------------------------------------------------------------
