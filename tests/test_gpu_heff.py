@@ -3,6 +3,8 @@
 Tolerance: FP64, relative 1e-12 per apply on O(1) data (north star: observables to 1e-10
 relative; a single apply must sit well below that).  Block tables must agree exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -17,17 +19,22 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _apply_and_compare(case, naive=True):
+def _apply_and_compare(case, naive=True, threads=1):
     ov = oracle_view(case)
     case.plan.apply(case.x, case.y)
     y_gpu = case.y.download()
     if naive:
         y_ref = oheff.heff_ac_apply_naive(ov["GL"], ov["W"], ov["GR"], ov["x"])
     else:
-        y_ref = oheff.HeffACPlan(ov["GL"], ov["W"], ov["GR"], ov["x"]).apply(ov["x"])
+        y_ref = oheff.HeffACPlan(ov["GL"], ov["W"], ov["GR"], ov["x"]).apply(ov["x"], threads=threads)
     ref = bridge.mps_to_packed(y_ref, table(case.y))
     assert np.abs(ref).max() > 1e-3
     assert rel_err(y_gpu, ref) < TOL
+    # every output block on its own scale (a small block must not hide behind the largest one)
+    vg, vr = case.y.block_views(y_gpu), case.y.block_views(ref)
+    for k in vr:
+        if vr[k].size:
+            assert rel_err(vg[k], vr[k]) < 10 * TOL, k
     return ov, y_gpu, ref
 
 
@@ -87,18 +94,11 @@ def test_heff_ac_full_size_properties(ctx):
     hc = x.like()
     case.plan.apply(comb, hc)
     assert rel_err(hc.download(), 0.5 * y1 - 2.0 * y2) < 1e-12
-    # oracle check on a subset of output blocks (terms restricted to those blocks)
-    ov = oracle_view(case)
-    terms = oheff.heff_ac_terms(ov["GL"], ov["W"], ov["GR"], ov["x"])
-    views = case.y.block_views(y1)
-    keys = sorted(views.keys(), key=lambda k: views[k].size)
-    pick = [keys[0], keys[len(keys) // 2], keys[-1]]
-    for ky in pick:
-        acc = np.zeros(views[ky].shape)
-        for (k0, kgl, kx, kgr, cf) in terms:
-            if k0 == ky:
-                acc += cf * (ov["GL"].blocks[kgl] @ ov["x"].blocks[kx] @ ov["GR"].blocks[kgr])
-        assert rel_err(views[ky], acc) < 1e-11
+    # FULL output against the oracle's planned apply: all 90 blocks, <= 1e-12 (and <= 1e-11 block by block)
+    ov, y_gpu, ref = _apply_and_compare(case, naive=False, threads=os.cpu_count() or 1)
+    assert len(case.y.block_views(ref)) == 90
+    # the checksum bench.py prints for its e2e leg (same seeded inputs) is pinned on the oracle's value
+    assert abs(y_gpu.sum() - ref.sum()) < 1e-9 * np.abs(ref).sum()
 
 
 def test_heff_ac_c3_shape_u1u1(ctx):
@@ -110,8 +110,8 @@ def test_heff_ac_c3_shape_u1u1(ctx):
 
 def test_heff_ac_c5_shape_properties(ctx):
     """BASELINE config C5 shape (D=2048, chi=160 MPO levels, the largest single-GPU case: ~4 GB of workspaces):
-    the oracle needs minutes per apply here, so parity rests on size-independent properties -- linearity,
-    determinism -- plus the oracle's term list evaluated for the two smallest output blocks."""
+    size-independent properties (linearity, determinism) plus the FULL output against the oracle's planned apply
+    (226 GF: ~10 s on the box's host cores with one worker thread per core)."""
     case = synthetic.HeffCase(ctx, PS.SU2U1, D=2048, chi=160)
     st = case.plan.stats
     assert st["flops"] > 1.5e11                  # ~8x the D=1024, chi=96 apply (D^3 chi)
@@ -129,16 +129,7 @@ def test_heff_ac_c5_shape_properties(ctx):
     hc = x.like()
     case.plan.apply(comb, hc)
     assert rel_err(hc.download(), 1.5 * y1 - 0.25 * hz.download()) < 1e-12
-    ov = oracle_view(case)
-    terms = oheff.heff_ac_terms(ov["GL"], ov["W"], ov["GR"], ov["x"])
-    views = case.y.block_views(y1)
-    keys = sorted(views.keys(), key=lambda k: views[k].size)
-    for ky in keys[:2]:
-        acc = np.zeros(views[ky].shape)
-        for (k0, kgl, kx, kgr, cf) in terms:
-            if k0 == ky:
-                acc += cf * (ov["GL"].blocks[kgl] @ ov["x"].blocks[kx] @ ov["GR"].blocks[kgr])
-        assert rel_err(views[ky], acc) < 1e-11
+    _apply_and_compare(case, naive=False, threads=os.cpu_count() or 1)
 
 
 def test_blocktables_match_oracle_order(ctx):
