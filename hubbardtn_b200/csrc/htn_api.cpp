@@ -1,4 +1,6 @@
 // C-ABI entry points: context, spaces, tensors, MPO, vector algebra (see include/htn.h).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -174,22 +176,75 @@ int32_t htn_legs_destroy(htn_legs* l) {
 }
 
 // ---- tensors --------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libhtn links no driver library)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 static int32_t finalize_tensor(htn_tensor* t) {
   htn_ctx* ctx = t->ctx;
   // Blocks of one coupled sector (MPS: same r; transposed MPS: same l) are laid out back to back
   // so that they form ONE row-major panel -- the matrix TensorKit stores per coupled sector and
   // the unit the QR / LQ gauge kernels work on in place.  Panels start 128-byte aligned.
   int64_t off = 0, hoff = 0;
+  const bool env = t->kind == HTN_T_ENVL || t->kind == HTN_T_ENVR;
+  if (env) {
+    // stacked panels (htn_internal.hpp): device order (lab[2]; identity level last; lab[1]; level), table order kept
+    const int nv = (int)t->s0.sec.size();
+    std::vector<int> order(t->blocks.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    const int idl = t->identity_level;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      const Block &a = t->blocks[x], &b = t->blocks[y];
+      const int ia = a.lab[0] == idl, ib = b.lab[0] == idl;
+      return std::make_tuple(a.lab[2], ia, a.lab[1], a.lab[0]) < std::make_tuple(b.lab[2], ib, b.lab[1], b.lab[0]);
+    });
+    t->panels.assign(nv, htn_tensor::Panel{0, 0, 0, 0, 0});
+    t->block_prow.assign(t->blocks.size(), 0);
+    int prev = -1;
+    for (int i : order) {
+      Block& b = t->blocks[i];
+      b.ld = even_up(b.cols);
+      const int g = b.lab[2];
+      if (g != prev) {
+        off = align_up(off, 16);
+        t->panels[g].off = off;
+        t->panels[g].cols = b.cols;
+        t->panels[g].ld = b.ld;
+        prev = g;
+      }
+      b.off = off;
+      t->block_prow[i] = t->panels[g].rows;
+      t->panels[g].rows += b.rows;
+      if (b.lab[0] != idl) t->panels[g].rows_active += b.rows;
+      off += (int64_t)b.rows * b.ld;
+    }
+  }
   int prev_group = -1;
   for (size_t i = 0; i < t->blocks.size(); ++i) {
     Block& b = t->blocks[i];
-    b.ld = even_up(b.cols);
-    const int group = t->kind == HTN_T_MPS ? b.lab[2] : (t->kind == HTN_T_MPST ? b.lab[0] : -2 - (int)i);
-    if (group != prev_group) off = align_up(off, 16);
-    prev_group = group;
-    b.off = off;
+    if (!env) {
+      b.ld = even_up(b.cols);
+      const int group = t->kind == HTN_T_MPS ? b.lab[2] : (t->kind == HTN_T_MPST ? b.lab[0] : -2 - (int)i);
+      if (group != prev_group) off = align_up(off, 16);
+      prev_group = group;
+      b.off = off;
+      off += (int64_t)b.rows * b.ld;
+    }
     b.hoff = hoff;
-    off += (int64_t)b.rows * b.ld;
     hoff += (int64_t)b.rows * b.cols;
     if (t->kind == HTN_T_MPS2)
       t->index5[std::array<int, 5>{b.lab[0], b.lab[1], b.lab[2], b.lab[3], b.lab[4]}] = (int)i;
@@ -202,6 +257,29 @@ static int32_t finalize_tensor(htn_tensor* t) {
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaMalloc(&t->d, t->dsize * sizeof(double)));
   CU(ctx, cudaMemsetAsync(t->d, 0, t->dsize * sizeof(double), ctx->stream));
+  if (env && !t->panels.empty() && tensor_map_encoder()) {
+    // one 2-D tensor map per panel: dims (cols, rows), row pitch ld * 8 B, box 16 x 64, 128-byte swizzle; columns
+    // beyond `cols` (K tails, the pad column) and rows beyond the panel read as zeros
+    std::vector<CUtensorMap> maps(t->panels.size());
+    bool ok = true;
+    for (size_t g = 0; g < t->panels.size() && ok; ++g) {
+      const htn_tensor::Panel& pn = t->panels[g];
+      memset(&maps[g], 0, sizeof(CUtensorMap));
+      if (pn.rows == 0 || pn.cols == 0) continue;
+      cuuint64_t dims[2] = {(cuuint64_t)pn.cols, (cuuint64_t)pn.rows};
+      cuuint64_t strides[1] = {(cuuint64_t)pn.ld * 8};
+      cuuint32_t box[2] = {16, 64};
+      cuuint32_t es[2] = {1, 1};
+      ok = tensor_map_encoder()(&maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, t->d + pn.off, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok) {
+      CU(ctx, cudaMalloc(&t->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+      CU(ctx, cudaMemcpyAsync(t->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   // device block table + row-chunk table
   std::vector<DevBlock> db(t->blocks.size());
   std::vector<int> chunks;
@@ -504,6 +582,7 @@ int32_t htn_tensor_destroy(htn_tensor* t) {
   if (t->d) cudaFree(t->d);
   if (t->dblocks) cudaFree(t->dblocks);
   if (t->dchunks) cudaFree(t->dchunks);
+  if (t->d_tmaps) cudaFree(t->d_tmaps);
   for (auto& kv : t->devtables) cudaFree(kv.second.first);
   delete t;
   return HTN_OK;

@@ -119,6 +119,17 @@ struct htn_tensor {
   // row-chunk table for pack/unpack/dot kernels: (block, row0, nrows)
   int* dchunks = nullptr;
   int nchunks = 0;
+  // Environment tensors are stored as STACKED PANELS: all blocks with the same last label (ENVL: the contracted
+  // sector l of GL[a,l',l]; ENVR: the output sector r' of GR[b,r,r']) lie back to back as one row-major matrix
+  // (ENVL rows ordered (l', a), ENVR rows ordered (r, b); blocks of the identity level last), so that a GEMM over
+  // the panel sees one tall operand (csrc/htn_stackl.cuh).  The block table / host order is unaffected.
+  struct Panel {
+    int64_t off;  // device offset of the panel
+    int rows, rows_active, cols, ld;  // total rows, rows before the identity-level blocks, columns, leading dimension
+  };
+  std::vector<Panel> panels;      // by sector index lab[2] (empty for non-environment kinds)
+  std::vector<int> block_prow;    // first row of block i inside its panel
+  unsigned char* d_tmaps = nullptr;  // ENVL/ENVR: one CUtensorMap (128 B) per panel: box 16 (cols) x 64 (rows), SWIZZLE_128B
   // cached device tables (transpose tiles, level fills, QR panels) keyed by (partner, mode)
   std::map<std::pair<const void*, int>, std::pair<void*, int>> devtables;
   int find5(int l, int s1, int m, int s2, int r) const {
@@ -179,6 +190,21 @@ struct GemmItem {
   int group;    // host scheduling only: items that read the same large operand block share a group (>= 0)
 };
 
+// one job of the stacked stage-L GEMM (htn_stackl.cuh):  C[M x nt] = A[M x K] . B[K x nt], B resident in shared memory
+struct StackJob {
+  long long a_off, b_off, c_off;
+  int a_base, b_base, c_base;
+  int lda, ldb, ldc;
+  int K;    // contraction length (multiplicity of the contracted sector)
+  int nt;   // valid output columns (<= 64)
+  int nb;   // doubles copied per slab row: even, >= nt, <= 8 ceil(nt / 8)
+  int M;    // rows of the run (tiles of 64)
+  int tmap; // >= 0: A is read through the 2-D tensor map tmaps[tmap] (TMA), rows arow .. arow + M of that panel
+  int arow;
+  int wave; // host scheduling only
+};
+constexpr int STACK_SLAB_ELEMS = 10080;
+inline bool stack_job_fits(int K, int nt) { return ((K + 3) & ~3) * (((nt + 7) & ~7) + 4) <= STACK_SLAB_ELEMS && nt <= 64; }
 struct MixSrc {
   long long off;
   int base, pad_;
@@ -193,8 +219,28 @@ struct MixTarget {
 };
 
 struct MixChunk {
-  int target, elem0, nelem, pad_;
+  int target, elem0, nelem, pad_;  // pad_: wave the chunk waits for in the fused stage (-1: none)
 };
+
+// Arguments of the fused stage L + W launch.  Counters (64-bit, never reset: `epoch` = 1-based launch number):
+//   ctr[0] job ticket, ctr[1] mix ticket, ctr[2] watchdog flag, ctr[4 + w] consumer-warp arrivals of wave w.
+struct StackArgs {
+  const StackJob* jobs;
+  int njobs;
+  const unsigned char* tmaps;
+  const MixTarget* mt;
+  const MixSrc* ms;
+  const MixChunk* mc;  // sorted by wave; pad_ = wave the chunk waits for (-1: none)
+  int nmix;
+  const int* wave_need;  // arrivals that complete wave w (= SL_NCONS * jobs of the wave)
+  unsigned long long* ctr;
+  unsigned long long epoch;
+  int dbg;
+};
+
+void launch_stack_gemm(const StackArgs& args, const Bases& bases, int grid, cudaStream_t st);
+
+int stack_gemm_ctas_per_sm();
 
 void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const Bases& bases, int grid,
                  cudaStream_t st);

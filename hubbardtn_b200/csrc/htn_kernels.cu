@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "htn_internal.hpp"
+#include "htn_stackl.cuh"
 
 namespace htn {
 
@@ -501,6 +502,28 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const B
     dbg = e ? atoi(e) : 0;
   }
   grouped_gemm_kernel<<<grid, NTHREADS, GEMM_SMEM_BYTES, st>>>(items, segs, nitems, bases, dbg);
+}
+
+// ------------------------------------------------------------------------------------
+// stacked stage L with the mix riding along (htn_stackl.cuh)
+// ------------------------------------------------------------------------------------
+int stack_gemm_ctas_per_sm() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaFuncSetAttribute(stack_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES);
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stack_gemm_kernel, SL_THREADS, SL_SMEM_BYTES);
+  cached = n > 0 ? n : 1;
+  return cached;
+}
+
+void launch_stack_gemm(const StackArgs& args, const Bases& bases, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stack_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES);
+    attr = true;
+  }
+  stack_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, st>>>(args, bases);
 }
 
 // ------------------------------------------------------------------------------------

@@ -66,21 +66,193 @@ struct HTerm {
 
 // Front end shared by H_AC, H_AC2 and T_L: stage L (T = GL . X, once per (a,lp,l,xi)) and the mix
 // sources of every U block (b, yi, r).
+//
+// Stage L comes in two forms.  Classic: one grouped-GEMM task per T block.  Stacked (H_AC / H_AC2 with a real
+// environment tensor, contracted multiplicity small enough for the shared-memory slab): for every x block all T
+// blocks {T[a,lp,l,xi]}_(lp,a) are rows of ONE tall array that the stacked kernel (htn_stackl.cuh) fills from the GL
+// panel of sector l; the left sectors lp are grouped into waves and the mix targets of a wave are formed by the
+// mixer warps of the same launch as soon as the wave's jobs are done.
 struct LeftFront {
   std::vector<std::tuple<int, int, int>> ukeys;  // (b, yi, r)
   std::vector<WsBlock> ub;
   std::vector<std::vector<Src>> usrc;
   int n_t = 0;
+  bool stacked = false;
+  std::vector<StackJobH> jobs;
+  std::vector<int> wave_of_lp;
+  int nwaves = 0;
 };
 
+static int stack_max_atoms(int K) {
+  const int k4 = (K + 3) & ~3;
+  int at = (STACK_SLAB_ELEMS / std::max(k4, 4) - 4) / 8;
+  return std::min(at, 7);
+}
+
 static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView& GL,
-                             const std::map<HTerm, double>& terms, int slot_x, int slot_gl) {
+                             const std::map<HTerm, double>& terms, int slot_x, int slot_gl, bool allow_stack = false) {
   LeftFront F;
   const int idL = GL.identity_level();
-  std::map<std::tuple<int, int, int, int>, int> tindex;  // (a,lp,l,xi)
-  std::map<std::tuple<int, int, int>, int> uindex;
+  typedef std::tuple<int, int, int, int> TKey;  // (a,lp,l,xi)
+  std::map<TKey, int> tindex;
+  std::vector<TKey> tkeys;
+  for (auto& kv : terms) {
+    if (kv.second == 0.0) continue;
+    const HTerm& t = kv.first;
+    if (t.a == idL) continue;
+    TKey key(t.a, t.lp, t.l, t.xi);
+    if (!tindex.count(key)) {
+      tindex[key] = (int)tkeys.size();
+      tkeys.push_back(key);
+    }
+  }
+  static int stack_env = -1;
+  if (stack_env < 0) {
+    const char* e = getenv("HTN_STACK");  // 0: classic stage L everywhere (A/B experiments)
+    stack_env = e ? atoi(e) : 1;
+  }
+  const htn_tensor* G = GL.t;
+  const bool can_stack = allow_stack && stack_env && G->kind == HTN_T_ENVL && !G->panels.empty();
+  std::vector<WsBlock> tb(tkeys.size());
+  std::vector<char> is_stacked(tkeys.size(), 0);
   std::vector<GemmTaskH> tasksL;
-  std::vector<WsBlock> tb;
+  // ---- which T blocks go through the stacked kernel: contracted multiplicity must leave >= 4 column atoms ----
+  std::map<int, std::vector<int>> by_xi;  // xi -> T indices (stacked ones)
+  for (size_t ti = 0; ti < tkeys.size(); ++ti) {
+    int a, lp, l, xi;
+    std::tie(a, lp, l, xi) = tkeys[ti];
+    const Block& xb = like->blocks[xi];
+    const Block& yb_rows = G->blocks[GL.find(a, lp, l)];
+    tb[ti] = WsBlock{yb_rows.rows, xb.cols, even_up(xb.cols), 0};
+    if (can_stack && stack_max_atoms(yb_rows.cols) >= std::min(4, (xb.cols + 7) / 8) && yb_rows.cols >= 1) {
+      is_stacked[ti] = 1;
+      by_xi[xi].push_back((int)ti);
+    }
+  }
+  // ---- waves over the left sectors lp, by the bytes of stacked T they own (heavy sectors first) ----
+  const int nlp = (int)like->s0.sec.size();
+  F.wave_of_lp.assign(nlp, -1);
+  if (!by_xi.empty()) {
+    std::vector<double> bytes(nlp, 0.0);
+    double total = 0.0;
+    for (size_t ti = 0; ti < tkeys.size(); ++ti)
+      if (is_stacked[ti]) {
+        const double b = 8.0 * tb[ti].rows * tb[ti].ld;
+        bytes[std::get<1>(tkeys[ti])] += b;
+        total += b;
+      }
+    static double wave_mb = -1.0;
+    if (wave_mb < 0) {
+      const char* e = getenv("HTN_WAVE_MB");
+      wave_mb = e ? atof(e) : 32.0;
+    }
+    std::vector<int> order;
+    for (int lp = 0; lp < nlp; ++lp)
+      if (bytes[lp] > 0) order.push_back(lp);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bytes[x] > bytes[y]; });
+    double acc = 0.0;
+    int w = 0;
+    for (int lp : order) {
+      if (acc > 0 && acc + bytes[lp] > wave_mb * 1e6) {
+        ++w;
+        acc = 0.0;
+      }
+      F.wave_of_lp[lp] = w;
+      acc += bytes[lp];
+    }
+    F.nwaves = w + 1;
+    F.stacked = true;
+  }
+  // ---- stacked T arrays and jobs ----
+  for (auto& kv : by_xi) {
+    const int xi = kv.first;
+    const Block& xb = like->blocks[xi];
+    const int l = std::get<2>(tkeys[kv.second[0]]);
+    const htn_tensor::Panel& pn = G->panels[l];
+    struct Row {
+      int prow, rows, lp, ti;
+    };
+    std::vector<Row> rows;
+    for (int ti : kv.second) {
+      int a, lp, l2, x2;
+      std::tie(a, lp, l2, x2) = tkeys[ti];
+      rows.push_back(Row{G->block_prow[GL.find(a, lp, l2)], tb[ti].rows, lp, ti});
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row& x, const Row& y) { return x.prow < y.prow; });
+    const int span0 = rows.front().prow, span1 = rows.back().prow + rows.back().rows;
+    const int ldT = even_up(xb.cols);
+    const int64_t tarr = pg.ws_alloc((int64_t)(span1 - span0) * ldT);
+    for (const Row& r : rows) tb[r.ti].off = tarr + (int64_t)(r.prow - span0) * ldT;
+    // column pieces: the 8-column atoms split evenly into pieces of <= maxat atoms
+    const int atoms = (xb.cols + 7) / 8, maxat = std::max(1, stack_max_atoms(pn.cols));
+    const int npieces = (atoms + maxat - 1) / maxat;
+    // row runs: consecutive needed blocks of one wave (gaps of < 32 unneeded rows are computed along)
+    size_t i = 0;
+    while (i < rows.size()) {
+      size_t j = i;
+      int r0 = rows[i].prow, r1 = rows[i].prow + rows[i].rows;
+      const int wave = F.wave_of_lp[rows[i].lp];
+      while (j + 1 < rows.size() && F.wave_of_lp[rows[j + 1].lp] == wave && rows[j + 1].prow - r1 < 32) {
+        ++j;
+        r1 = rows[j].prow + rows[j].rows;
+      }
+      int c0 = 0;
+      for (int pc = 0; pc < npieces; ++pc) {
+        const int at = atoms / npieces + (pc < atoms % npieces ? 1 : 0);
+        const int nt = std::min(at * 8, xb.cols - c0);
+        // jobs of falling size: 12-tile jobs first, the last third of the run in ever smaller ones (the ticket order
+        // inside a wave is by falling cost, so the small jobs even out the end of the wave)
+        int m0 = r0;
+        while (m0 < r1) {
+          const int rem_tiles = (r1 - m0 + 63) / 64;
+          const int tiles = std::max(1, std::min(12, (rem_tiles + 2) / 3));
+          const int M = std::min(tiles * 64, r1 - m0);
+          StackJobH jb{};
+          jb.A = Opnd{slot_gl, pn.off + (int64_t)m0 * pn.ld};
+          jb.lda = pn.ld;
+          jb.B = Opnd{slot_x, xb.off + c0};
+          jb.ldb = xb.ld;
+          jb.C = Opnd{SLOT_WS, tarr + (int64_t)(m0 - span0) * ldT + c0};
+          jb.ldc = ldT;
+          jb.K = pn.cols;
+          jb.nt = nt;
+          jb.nb = std::min(even_up(nt), xb.ld - c0);
+          jb.M = M;
+          jb.tmap = G->d_tmaps ? l : -1;
+          jb.arow = m0;
+          jb.wave = wave;
+          F.jobs.push_back(jb);
+          m0 += M;
+        }
+        c0 += nt;
+      }
+      i = j + 1;
+    }
+  }
+  // ---- classic tasks for the rest; algorithmic flops of all T blocks ----
+  for (size_t ti = 0; ti < tkeys.size(); ++ti) {
+    int a, lp, l, xi;
+    std::tie(a, lp, l, xi) = tkeys[ti];
+    const Block& xb = like->blocks[xi];
+    const Block& gl = G->blocks[GL.find(a, lp, l)];
+    if (is_stacked[ti]) {
+      const double f = 2.0 * tb[ti].rows * tb[ti].cols * gl.cols;
+      pg.flops += f;
+      pg.flops_tag[TAG_L] += f;
+      continue;
+    }
+    WsBlock& w = tb[ti];
+    w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
+    GemmTaskH g;
+    g.C = Opnd{SLOT_WS, w.off};
+    g.ldc = w.ld;
+    g.M = w.rows;
+    g.N = w.cols;
+    g.segs.push_back(GemmSegH{Opnd{slot_gl, gl.off}, gl.ld, Opnd{slot_x, xb.off}, xb.ld, gl.cols});
+    tasksL.push_back(std::move(g));
+  }
+  // ---- mix sources of every U block ----
+  std::map<std::tuple<int, int, int>, int> uindex;
   for (auto& kv : terms) {
     if (kv.second == 0.0) continue;
     const HTerm& t = kv.first;
@@ -92,26 +264,7 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
       if (t.lp != t.l) continue;  // identity level is trivial
       src.o = Opnd{slot_x, xb.off};
     } else {
-      auto key = std::make_tuple(t.a, t.lp, t.l, t.xi);
-      auto it = tindex.find(key);
-      int ti;
-      if (it == tindex.end()) {
-        ti = (int)tb.size();
-        tindex[key] = ti;
-        WsBlock w{yb.rows, xb.cols, even_up(xb.cols), 0};
-        w.off = pg.ws_alloc((int64_t)w.rows * w.ld);
-        tb.push_back(w);
-        const Block& gl = GL.t->blocks[GL.find(t.a, t.lp, t.l)];
-        GemmTaskH g;
-        g.C = Opnd{SLOT_WS, w.off};
-        g.ldc = w.ld;
-        g.M = w.rows;
-        g.N = w.cols;
-        g.segs.push_back(GemmSegH{Opnd{slot_gl, gl.off}, gl.ld, Opnd{slot_x, xb.off}, xb.ld, gl.cols});
-        tasksL.push_back(std::move(g));
-      } else
-        ti = it->second;
-      src.o = Opnd{SLOT_WS, tb[ti].off};
+      src.o = Opnd{SLOT_WS, tb[tindex[TKey(t.a, t.lp, t.l, t.xi)]].off};
     }
     auto key = std::make_tuple(t.b, t.yi, t.r);
     auto it = uindex.find(key);
@@ -192,12 +345,19 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
   std::vector<int> order(F.ukeys.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
   std::sort(order.begin(), order.end(), [&](int i, int j) { return F.ukeys[i] < F.ukeys[j]; });
+  std::map<int, MixTaskH> y0;  // stacked front: direct (identity right level) contributions, formed by the mixer warps
   for (int ui : order) {
     int b, yi, r;
     std::tie(b, yi, r) = F.ukeys[ui];
     n_mix_s += (int)F.usrc[ui].size();
+    const int lp = like->blocks[yi].lab[0];
     if (b == idR) {
-      for (const Src& s : F.usrc[ui]) yextra[yi].push_back(MixSrcH{s.o, s.coef});
+      if (!F.stacked) {
+        for (const Src& s : F.usrc[ui]) yextra[yi].push_back(MixSrcH{s.o, s.coef});
+      } else {
+        MixTaskH& t = y0[yi];
+        for (const Src& s : F.usrc[ui]) t.srcs.push_back(MixSrcH{s.o, s.coef});
+      }
       continue;
     }
     WsBlock& w = F.ub[ui];
@@ -205,6 +365,7 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     MixTaskH mt;
     mt.dst = Opnd{SLOT_WS, w.off};
     mt.nelem = w.rows * w.ld;
+    mt.wave = F.stacked ? F.wave_of_lp[lp] : -1;
     for (const Src& s : F.usrc[ui]) mt.srcs.push_back(MixSrcH{s.o, s.coef});
     mixU.push_back(std::move(mt));
     const int rp = like->kind == HTN_T_MPS ? like->blocks[yi].lab[2] : like->blocks[yi].lab[4];
@@ -212,19 +373,33 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     tasksR[yi].segs.push_back(GemmSegH{Opnd{SLOT_WS, w.off}, w.ld, Opnd{3, gr.off}, gr.ld, gr.rows});
     ++n_u;
   }
-  *n_mix_t = (int)(mixU.size() + like->blocks.size());
-  // launch order of the U mixes: a T block feeds ~1.7 U blocks (other MPO levels b, other s'); walking the targets
-  // in the order of their first source puts those readers next to each other in time, so the repeat reads of T hit L2
-  if (!getenv("HTN_MIX_ORDER_BY_TARGET")) {
-    auto first_src = [](const MixTaskH& t) {
-      int64_t m = INT64_MAX;
-      for (const MixSrcH& q : t.srcs)
-        if (q.src.slot == SLOT_WS) m = std::min<int64_t>(m, q.src.off);
-      return m;
-    };
-    std::stable_sort(mixU.begin(), mixU.end(), [&](const MixTaskH& a, const MixTaskH& b) { return first_src(a) < first_src(b); });
+  for (auto& kv : y0) {
+    const Block& yb = like->blocks[kv.first];
+    MixTaskH& t = kv.second;
+    const int64_t off = pg.ws_alloc((int64_t)yb.rows * yb.ld);
+    t.dst = Opnd{SLOT_WS, off};
+    t.nelem = yb.rows * yb.ld;
+    t.wave = F.wave_of_lp[yb.lab[0]];
+    yextra[kv.first].push_back(MixSrcH{t.dst, 1.0});
+    mixU.push_back(std::move(t));
   }
-  pg.add_mix(mixU, TAG_W);
+  *n_mix_t = (int)(mixU.size() + like->blocks.size());
+  if (F.stacked) {
+    pg.add_stack(F.jobs, mixU, F.nwaves, 2, TAG_L);
+  } else {
+    // launch order of the U mixes: a T block feeds ~1.7 U blocks (other MPO levels b, other s'); walking the targets
+    // in the order of their first source puts those readers next to each other in time, so the repeat reads of T hit L2
+    if (!getenv("HTN_MIX_ORDER_BY_TARGET")) {
+      auto first_src = [](const MixTaskH& t) {
+        int64_t m = INT64_MAX;
+        for (const MixSrcH& q : t.srcs)
+          if (q.src.slot == SLOT_WS) m = std::min<int64_t>(m, q.src.off);
+        return m;
+      };
+      std::stable_sort(mixU.begin(), mixU.end(), [&](const MixTaskH& a, const MixTaskH& b) { return first_src(a) < first_src(b); });
+    }
+    pg.add_mix(mixU, TAG_W);
+  }
   pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y);
   *n_u_out = n_u;
   *n_mix_s_out = n_mix_s;
@@ -295,7 +470,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     Program& pg = p->prog;
     EnvView gl{GL};
     auto terms = one_site_terms(sym, like, gl, W, [&](int b, int r, int rp) { return GR->find(b, r, rp) >= 0; });
-    LeftFront F = build_front(pg, like, gl, terms, 0, 2);
+    LeftFront F = build_front(pg, like, gl, terms, 0, 2, true);
     int n_u = 0, n_mix_t = 0, n_mix_s = 0;
     build_heff_backend(pg, like, GR, F, &n_u, &n_mix_t, &n_mix_s);
     if ((rc = pg.finalize(ctx, 4))) {
@@ -394,7 +569,7 @@ int32_t htn_plan_heff_ac2(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W1,
         }
       }
     }
-    LeftFront F = build_front(pg, like, gl, terms, 0, 2);
+    LeftFront F = build_front(pg, like, gl, terms, 0, 2, true);
     int n_u = 0, n_mix_t = 0, n_mix_s = 0;
     build_heff_backend(pg, like, GR, F, &n_u, &n_mix_t, &n_mix_s);
     if ((rc = pg.finalize(ctx, 4))) {
@@ -759,7 +934,9 @@ static int32_t check_xy(htn_plan* p, const htn_tensor* x, const htn_tensor* y) {
 
 int32_t htn_heff_run(htn_plan* p, const double* x, double* y, int mask) {
   const double* slots[4] = {x, y, p->bound[2] ? p->bound[2]->d : nullptr, p->bound[3] ? p->bound[3]->d : nullptr};
-  return p->prog.run(slots, mask);
+  const unsigned char* tmaps[4] = {nullptr, nullptr, p->bound[2] ? p->bound[2]->d_tmaps : nullptr,
+                                   p->bound[3] ? p->bound[3]->d_tmaps : nullptr};
+  return p->prog.run(slots, mask, tmaps);
 }
 
 int32_t htn_heff_apply(htn_plan* p, const htn_tensor* x, htn_tensor* y) {

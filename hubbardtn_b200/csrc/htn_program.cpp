@@ -253,10 +253,57 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
   add_mix(mixes, tag_mix);
 }
 
+static void fill_mix_tables(Stage& st, const std::vector<MixTaskH>& tasks);
+
 void Program::add_mix(std::vector<MixTaskH>& tasks, int tag) {
   Stage st;
   st.kind = 1;
   st.tag = tag;
+  fill_mix_tables(st, tasks);
+  if (!st.mc.empty()) stages.push_back(std::move(st));
+}
+
+void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mixes, int nwaves, int tmap_slot, int tag) {
+  Stage st;
+  st.kind = 2;
+  st.tag = tag;
+  st.nwaves = std::max(nwaves, 0);
+  st.tmap_slot = tmap_slot;
+  st.wave_need.assign(std::max(nwaves, 1), 0);
+  // table order = ticket order: wave by wave, heavy jobs first
+  auto cost = [](const StackJobH& j) {
+    return (double)((j.M + 63) / 64) * (((j.K + 15) / 16) * (((j.nt + 7) / 8) + 0.75) + 6.0) + 20.0;
+  };
+  std::stable_sort(jobs.begin(), jobs.end(), [&](const StackJobH& a, const StackJobH& b) {
+    if (a.wave != b.wave) return a.wave < b.wave;
+    return cost(a) > cost(b);
+  });
+  for (const StackJobH& j : jobs) {
+    StackJob d{};
+    enc(j.A, d.a_off, d.a_base);
+    enc(j.B, d.b_off, d.b_base);
+    enc(j.C, d.c_off, d.c_base);
+    d.lda = j.lda;
+    d.ldb = j.ldb;
+    d.ldc = j.ldc;
+    d.K = j.K;
+    d.nt = j.nt;
+    d.nb = j.nb;
+    d.M = j.M;
+    d.tmap = j.tmap;
+    d.arow = j.arow;
+    d.wave = j.wave;
+    st.sjobs.push_back(d);
+    if (j.wave >= 0 && j.wave < (int)st.wave_need.size()) st.wave_need[j.wave] += 4;  // SL_NCONS consumer warps signal per job
+    padded_flops += 2.0 * ((j.M + 7) / 8 * 8) * ((j.nt + 7) / 8 * 8) * ((j.K + 3) / 4 * 4.0);
+  }
+  std::stable_sort(mixes.begin(), mixes.end(), [](const MixTaskH& a, const MixTaskH& b) { return a.wave < b.wave; });
+  fill_mix_tables(st, mixes);
+  n_gemm_tiles_tag[TAG_L] += (int)st.sjobs.size();
+  if (!st.sjobs.empty() || !st.mc.empty()) stages.push_back(std::move(st));
+}
+
+static void fill_mix_tables(Stage& st, const std::vector<MixTaskH>& tasks) {
   for (const MixTaskH& t : tasks) {
     if (t.nelem <= 0) continue;
     MixTarget mt{};
@@ -275,9 +322,8 @@ void Program::add_mix(std::vector<MixTaskH>& tasks, int tag) {
     // ~16k element-sources per CTA, chunk a multiple of 512 elements (256 threads x double2)
     int per = 16384 / std::max<int>(1, (int)t.srcs.size());
     per = std::max(512, std::min(8192, per / 512 * 512));
-    for (int e = 0; e < t.nelem; e += per) st.mc.push_back(MixChunk{ti, e, std::min(per, t.nelem - e), 0});
+    for (int e = 0; e < t.nelem; e += per) st.mc.push_back(MixChunk{ti, e, std::min(per, t.nelem - e), t.wave});
   }
-  if (!st.mc.empty()) stages.push_back(std::move(st));
 }
 
 // Static schedule of one GEMM stage: the kernel's CTA b walks items b, b + G, b + 2G, ...  The time a
@@ -468,10 +514,32 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
       for (MixTarget& t : st.mt) fix(t.off, t.base);
       for (MixSrc& s : st.ms) fix(s.off, s.base);
       if (st.ms.empty()) st.ms.push_back(MixSrc{});
+      if (st.kind == 2) {
+        if (st.mt.empty()) st.mt.push_back(MixTarget{});
+        if (st.mc.empty()) st.mc.push_back(MixChunk{});
+        st.n = (int)st.mc.size();
+        if (st.mc.size() == 1 && st.mc[0].nelem == 0) st.n = 0;
+      }
       if ((rc = to_device(ctx, st.mt, &st.d_mt)) || (rc = to_device(ctx, st.ms, &st.d_ms)) ||
           (rc = to_device(ctx, st.mc, &st.d_mc)))
         return rc;
-      st.n = (int)st.mc.size();
+      if (st.kind == 1) st.n = (int)st.mc.size();
+      if (st.kind == 2) {
+        for (StackJob& j : st.sjobs) {
+          fix(j.a_off, j.a_base);
+          fix(j.b_off, j.b_base);
+          fix(j.c_off, j.c_base);
+        }
+        st.n_sjobs = (int)st.sjobs.size();
+        if (st.sjobs.empty()) st.sjobs.push_back(StackJob{});
+        if ((rc = to_device(ctx, st.sjobs, &st.d_sjobs)) || (rc = to_device(ctx, st.wave_need, &st.d_wave_need))) return rc;
+        const size_t nctr = 4 + st.wave_need.size();
+        if (cudaMalloc(&st.d_ctr, nctr * sizeof(unsigned long long)) != cudaSuccess)
+          return ctx->fail(HTN_ERR_OOM, "program counters allocation failed");
+        cudaMemsetAsync(st.d_ctr, 0, nctr * sizeof(unsigned long long), ctx->stream);
+        st.grid = ctx->sm_count * stack_gemm_ctas_per_sm();
+        std::vector<StackJob>().swap(st.sjobs);
+      }
     }
     // host tables are no longer needed
     std::vector<GemmItem>().swap(st.items);
@@ -484,15 +552,36 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
   return HTN_OK;
 }
 
-int32_t Program::run(const double* const* slots, int mask) const {
+int32_t Program::run(const double* const* slots, int mask, const unsigned char* const* slot_tmaps) const {
   Bases bs;
   for (int i = 0; i < MAX_SLOTS; ++i) bs.p[i] = i < nslots ? slots[i] : nullptr;
+  static int stack_dbg = -1;
+  if (stack_dbg < 0) {
+    const char* e = getenv("HTN_STACK_DEBUG");  // timing experiments only (results are wrong when set)
+    stack_dbg = e ? atoi(e) : 0;
+  }
   for (const Stage& st : stages) {
     if (!(st.tag & mask)) continue;
     if (st.kind == 0)
       launch_gemm(st.d_items, st.d_segs, st.n, bs, st.grid, ctx->stream);
-    else
+    else if (st.kind == 1)
       launch_mix(st.d_mt, st.d_ms, st.d_mc, st.n, bs, ctx->stream);
+    else {
+      StackArgs a{};
+      a.jobs = st.d_sjobs;
+      a.njobs = st.n_sjobs;
+      a.tmaps = (st.tmap_slot >= 0 && slot_tmaps) ? slot_tmaps[st.tmap_slot] : nullptr;
+      if (st.tmap_slot >= 0 && !a.tmaps) return ctx->fail(HTN_ERR_INVALID, "program: the stacked stage needs the tensor maps of its environment operand");
+      a.mt = st.d_mt;
+      a.ms = st.d_ms;
+      a.mc = st.d_mc;
+      a.nmix = st.n;
+      a.wave_need = st.d_wave_need;
+      a.ctr = st.d_ctr;
+      a.epoch = ++st.epoch;
+      a.dbg = stack_dbg;
+      launch_stack_gemm(a, bs, st.grid, ctx->stream);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ctx->fail(HTN_ERR_CUDA, std::string("program launch: ") + cudaGetErrorString(e));
@@ -513,6 +602,9 @@ void Program::destroy() {
     cudaFree(st.d_mt);
     cudaFree(st.d_ms);
     cudaFree(st.d_mc);
+    cudaFree(st.d_sjobs);
+    cudaFree(st.d_wave_need);
+    cudaFree(st.d_ctr);
   }
   stages.clear();
   cudaFree(ws);

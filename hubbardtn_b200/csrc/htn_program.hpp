@@ -41,12 +41,25 @@ struct MixTaskH {
   Opnd dst;
   int nelem;
   std::vector<MixSrcH> srcs;
+  int wave = -1;  // fused stage only: wave of stack jobs whose T blocks this target reads
+};
+// one job of the stacked stage L (htn_stackl.cuh): C[M x nt] = A[M x K] . B[K x nt]
+struct StackJobH {
+  Opnd A;
+  int lda;
+  Opnd B;
+  int ldb;
+  Opnd C;
+  int ldc;
+  int K, nt, nb, M;
+  int tmap, arow;  // tensor map index / first row inside that panel (tmap < 0: plain pointer path)
+  int wave;
 };
 
 enum StageTag { TAG_L = 1, TAG_W = 2, TAG_R = 4, TAG_Y = 8 };
 
 struct Stage {
-  int kind;  // 0 gemm, 1 mix
+  int kind;  // 0 gemm, 1 mix, 2 stacked gemm with the mix riding along (htn_stackl.cuh)
   int tag;
   // host tables (kept until finalize)
   std::vector<GemmItem> items;
@@ -62,6 +75,15 @@ struct Stage {
   MixChunk* d_mc = nullptr;
   int n = 0;  // items or chunks
   int grid = 0;
+  // kind 2
+  std::vector<StackJob> sjobs;
+  std::vector<int> wave_need;
+  StackJob* d_sjobs = nullptr;
+  int* d_wave_need = nullptr;
+  unsigned long long* d_ctr = nullptr;
+  int n_sjobs = 0, nwaves = 0;
+  int tmap_slot = -1;  // slot whose tensor supplies the tensor maps at launch (-1: none needed)
+  mutable unsigned long long epoch = 0;
 };
 
 struct Program {
@@ -85,9 +107,11 @@ struct Program {
   void add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::vector<MixSrcH>>& extra, int tag_gemm,
                        int tag_mix);
   void add_mix(std::vector<MixTaskH>& tasks, int tag);
+  // fused stage: stack jobs (ordered by wave) + the mix targets that consume their outputs
+  void add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mixes, int nwaves, int tmap_slot, int tag);
   int32_t finalize(htn_ctx* ctx, int nslots);
   // ---- running ----
-  int32_t run(const double* const* slots, int mask = 0xF) const;
+  int32_t run(const double* const* slots, int mask = 0xF, const unsigned char* const* slot_tmaps = nullptr) const;
   int launches(int mask = 0xF) const;
   void destroy();
 };
