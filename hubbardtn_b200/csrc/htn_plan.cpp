@@ -129,29 +129,27 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
       by_xi[xi].push_back((int)ti);
     }
   }
-  // ---- waves over the left sectors lp, by the bytes of stacked T they own (heavy sectors first) ----
+  // ---- waves.  Wave 0: the jobs of the LIGHT panels (contracted multiplicity <= 16: hardly any flops or bytes, but
+  // many rows) -- one run per x block, every mix target waits for it.  Waves 1..: the left sectors lp grouped by the
+  // bytes of heavy T they own (heavy sectors first); a target of sector lp waits for wave_of_lp[lp] (and wave 0).
   const int nlp = (int)like->s0.sec.size();
-  F.wave_of_lp.assign(nlp, -1);
+  F.wave_of_lp.assign(nlp, 0);
+  auto light_panel = [&](int l) { return G->panels[l].cols <= 16; };
   if (!by_xi.empty()) {
     std::vector<double> bytes(nlp, 0.0);
-    double total = 0.0;
     for (size_t ti = 0; ti < tkeys.size(); ++ti)
-      if (is_stacked[ti]) {
-        const double b = 8.0 * tb[ti].rows * tb[ti].ld;
-        bytes[std::get<1>(tkeys[ti])] += b;
-        total += b;
-      }
+      if (is_stacked[ti] && !light_panel(std::get<2>(tkeys[ti]))) bytes[std::get<1>(tkeys[ti])] += 8.0 * tb[ti].rows * tb[ti].ld;
     static double wave_mb = -1.0;
     if (wave_mb < 0) {
       const char* e = getenv("HTN_WAVE_MB");
-      wave_mb = e ? atof(e) : 32.0;
+      wave_mb = e ? atof(e) : 48.0;
     }
     std::vector<int> order;
     for (int lp = 0; lp < nlp; ++lp)
       if (bytes[lp] > 0) order.push_back(lp);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bytes[x] > bytes[y]; });
     double acc = 0.0;
-    int w = 0;
+    int w = 1;
     for (int lp : order) {
       if (acc > 0 && acc + bytes[lp] > wave_mb * 1e6) {
         ++w;
@@ -191,8 +189,9 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
     while (i < rows.size()) {
       size_t j = i;
       int r0 = rows[i].prow, r1 = rows[i].prow + rows[i].rows;
-      const int wave = F.wave_of_lp[rows[i].lp];
-      while (j + 1 < rows.size() && F.wave_of_lp[rows[j + 1].lp] == wave && rows[j + 1].prow - r1 < 32) {
+      const bool light = light_panel(l);
+      const int wave = light ? 0 : F.wave_of_lp[rows[i].lp];
+      while (j + 1 < rows.size() && (light || (F.wave_of_lp[rows[j + 1].lp] == wave && rows[j + 1].prow - r1 < 32))) {
         ++j;
         r1 = rows[j].prow + rows[j].rows;
       }
@@ -200,12 +199,19 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
       for (int pc = 0; pc < npieces; ++pc) {
         const int at = atoms / npieces + (pc < atoms % npieces ? 1 : 0);
         const int nt = std::min(at * 8, xb.cols - c0);
-        // jobs of falling size: 12-tile jobs first, the last third of the run in ever smaller ones (the ticket order
-        // inside a wave is by falling cost, so the small jobs even out the end of the wave)
+        // jobs of 6 tiles (measured best of 2..24: larger jobs delay the completion of their wave and with it the
+        // mixers, smaller ones pay a slab reload each; HTN_STACK_FALL=1 cuts the end of every run finer)
         int m0 = r0;
         while (m0 < r1) {
+          static int tpj = -1, fall = -1;
+          if (tpj < 0) {
+            const char* e = getenv("HTN_STACK_TPJ");  // tiles per job (tuning)
+            tpj = e ? std::max(1, atoi(e)) : 6;
+            e = getenv("HTN_STACK_FALL");
+            fall = e ? atoi(e) : 0;
+          }
           const int rem_tiles = (r1 - m0 + 63) / 64;
-          const int tiles = std::max(1, std::min(12, (rem_tiles + 2) / 3));
+          const int tiles = fall ? std::max(1, std::min(tpj, (rem_tiles + 2) / 3)) : tpj;
           const int M = std::min(tiles * 64, r1 - m0);
           StackJobH jb{};
           jb.A = Opnd{slot_gl, pn.off + (int64_t)m0 * pn.ld};
@@ -365,7 +371,7 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     MixTaskH mt;
     mt.dst = Opnd{SLOT_WS, w.off};
     mt.nelem = w.rows * w.ld;
-    mt.wave = F.stacked ? F.wave_of_lp[lp] : -1;
+    mt.wave = F.stacked ? F.wave_of_lp[lp] : -1;  // (wave 0 = light panels only: the mixers always wait for it too)
     for (const Src& s : F.usrc[ui]) mt.srcs.push_back(MixSrcH{s.o, s.coef});
     mixU.push_back(std::move(mt));
     const int rp = like->kind == HTN_T_MPS ? like->blocks[yi].lab[2] : like->blocks[yi].lab[4];

@@ -300,6 +300,18 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
   std::stable_sort(mixes.begin(), mixes.end(), [](const MixTaskH& a, const MixTaskH& b) { return a.wave < b.wave; });
   fill_mix_tables(st, mixes);
   n_gemm_tiles_tag[TAG_L] += (int)st.sjobs.size();
+  if (getenv("HTN_PLAN_DEBUG")) {
+    long long tiles = 0;
+    std::vector<int> per_wave(st.wave_need.size(), 0);
+    for (const StackJob& j : st.sjobs) {
+      tiles += (j.M + 63) / 64;
+      if (j.wave >= 0) per_wave[j.wave]++;
+    }
+    fprintf(stderr, "[htn] stacked stage: %zu jobs, %lld tiles, %d waves, %zu mix targets, %zu mix chunks; jobs per wave:", st.sjobs.size(),
+            tiles, st.nwaves, st.mt.size(), st.mc.size());
+    for (int v : per_wave) fprintf(stderr, " %d", v);
+    fprintf(stderr, "\n");
+  }
   if (!st.sjobs.empty() || !st.mc.empty()) stages.push_back(std::move(st));
 }
 
@@ -575,12 +587,13 @@ int32_t Program::run(const double* const* slots, int mask, const unsigned char* 
       a.mt = st.d_mt;
       a.ms = st.d_ms;
       a.mc = st.d_mc;
-      a.nmix = st.n;
+      a.nmix = (stack_dbg & 16) ? 0 : st.n;  // experiment 16: the mix as a separate launch
       a.wave_need = st.d_wave_need;
       a.ctr = st.d_ctr;
       a.epoch = ++st.epoch;
       a.dbg = stack_dbg;
       launch_stack_gemm(a, bs, st.grid, ctx->stream);
+      if ((stack_dbg & 16) && st.n > 0) launch_mix(st.d_mt, st.d_ms, st.d_mc, st.n, bs, ctx->stream);
     }
   }
   cudaError_t e = cudaGetLastError();

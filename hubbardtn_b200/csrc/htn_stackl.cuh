@@ -44,8 +44,10 @@ constexpr int SL_NMIX = 3;                     // mixer warps (stage W), warps S
 constexpr int SL_THREADS = (SL_NCONS + 1 + SL_NMIX) * 32;
 constexpr int SL_JOBWORDS = (int)(sizeof(StackJob) / 4);
 constexpr int SL_MIXSRC = 32;                  // source descriptors staged per mixer warp
-constexpr int SL_SMEM_BYTES = (SL_STAGES * SL_STAGE_ELEMS + SL_SLAB) * 8 + (2 * SL_STAGES + 4) * 8 + 2 * SL_JOBWORDS * 4 + 16 +
-                              SL_NMIX * SL_MIXSRC * 16;
+// 2 CTAs per SM need 2 x (this + 1 KB) <= 228 KB: the slab leaves no room for per-warp staging of the mix sources
+// (they travel through warp shuffles instead)
+constexpr int SL_SMEM_BYTES = (SL_STAGES * SL_STAGE_ELEMS + SL_SLAB) * 8 + (2 * SL_STAGES + 4) * 8 + 2 * SL_JOBWORDS * 4 + 16;
+static_assert(2 * (SL_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
 
 __device__ __forceinline__ unsigned sl_smem(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void sl_mbar_init(uint64_t* bar, int count) {
@@ -199,46 +201,74 @@ __device__ __forceinline__ unsigned long long sl_ld_acquire(const unsigned long 
 }
 
 // one mix chunk by one warp: dst[e] = sum_s coef_s src_s[e] over a flat element range (identical padded layouts)
-__device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk& ch, const Bases& bases, const double** sptr,
-                                             double* scoef, int lane) {
+// weak 16-byte global load that does not allocate in L1 (the data was written by other SMs earlier in this launch and is
+// read exactly once here; weak loads keep all 2 U requests of a trip in flight -- ld.global.cg compiles to ordered
+// LDG.STRONG.GPU and was 5x slower)
+__device__ __forceinline__ double2 sl_ld_stream(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// one mix chunk by one warp: dst[e] = sum_s coef_s src_s[e] over a flat element range (identical padded layouts)
+template <int U>
+__device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk& ch, const Bases& bases, int lane) {
   const MixTarget T = a.mt[ch.target];
   double* dst = const_cast<double*>(resolve(T.off, T.base, bases));
   const int nsrc = T.src_end - T.src_begin;
-  const int end = ch.elem0 + ch.nelem;
+  const int end = ch.elem0 + ch.nelem;  // even, >= 2
   for (int s0 = 0; s0 < nsrc || s0 == 0; s0 += SL_MIXSRC) {
     const int ns = min(SL_MIXSRC, nsrc - s0);
-    __syncwarp();
+    // lane s holds source s of this batch; the trip loop below broadcasts them by shuffle
+    unsigned long long my_ptr = 0;
+    double my_coef = 0.0;
     if (lane < ns) {
       const MixSrc S = a.ms[T.src_begin + s0 + lane];
-      sptr[lane] = resolve(S.off, S.base, bases);
-      scoef[lane] = S.coef;
+      my_ptr = reinterpret_cast<unsigned long long>(resolve(S.off, S.base, bases));
+      my_coef = S.coef;
     }
-    __syncwarp();
-    // 4 positions (double2 each) per lane and trip: 256 elements per warp trip
-    for (int e0 = ch.elem0 + 2 * lane; e0 < end; e0 += 256) {
-      double2 acc[4];
+    // U positions (double2 each) per lane and trip: 64 U elements per warp trip; positions beyond the chunk are
+    // clamped to its last pair (loaded, never stored) so that the loads of a trip are straight-line code
+    for (int eb = ch.elem0; eb < end; eb += 64 * U) {  // warp-uniform trip count (the shuffles below need all lanes)
+      const int e0 = eb + 2 * lane;
+      int eu[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + 64 * u;
-        acc[u] = (s0 == 0 || e >= end) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(dst + e);
-      }
-      for (int s = 0; s < ns; ++s) {
-        const double* sp = sptr[s];
-        const double cf = scoef[s];
-        double2 v[4];
+      for (int u = 0; u < U; ++u) eu[u] = min(e0 + 64 * u, end - 2);
+      double2 acc[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + 64 * u;
-          v[u] = e < end ? __ldcg(reinterpret_cast<const double2*>(sp + e)) : make_double2(0.0, 0.0);
+      for (int u = 0; u < U; ++u) acc[u] = s0 == 0 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(dst + eu[u]);
+      int s = 0;
+      for (; s + 2 <= ns; s += 2) {  // two sources at a time: 2 U independent loads in flight per lane
+        const double* sp0 = reinterpret_cast<const double*>(__shfl_sync(0xffffffffu, my_ptr, s));
+        const double* sp1 = reinterpret_cast<const double*>(__shfl_sync(0xffffffffu, my_ptr, s + 1));
+        const double cf0 = __shfl_sync(0xffffffffu, my_coef, s), cf1 = __shfl_sync(0xffffffffu, my_coef, s + 1);
+        double2 v0[U], v1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v0[u] = sl_ld_stream(sp0 + eu[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) v1[u] = sl_ld_stream(sp1 + eu[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[u].x = fma(cf0, v0[u].x, acc[u].x);
+          acc[u].y = fma(cf0, v0[u].y, acc[u].y);
+          acc[u].x = fma(cf1, v1[u].x, acc[u].x);
+          acc[u].y = fma(cf1, v1[u].y, acc[u].y);
         }
+      }
+      if (s < ns) {
+        const double* sp = reinterpret_cast<const double*>(__shfl_sync(0xffffffffu, my_ptr, s));
+        const double cf = __shfl_sync(0xffffffffu, my_coef, s);
+        double2 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) v[u] = sl_ld_stream(sp + eu[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
           acc[u].x = fma(cf, v[u].x, acc[u].x);
           acc[u].y = fma(cf, v[u].y, acc[u].y);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int e = e0 + 64 * u;
         if (e < end) *reinterpret_cast<double2*>(dst + e) = acc[u];
       }
@@ -247,11 +277,44 @@ __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk&
   }
 }
 
+// mixer loop: mix chunks by ticket, each after the wave of stack jobs it reads from is complete
+template <int U>
+__device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
+  const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
+  while (true) {
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= (unsigned long long)a.nmix) break;
+    const MixChunk ch = a.mc[tk];
+    if (ch.pad_ >= 0) {
+      if (lane == 0) {
+        // wave 0 holds the jobs of the light panels (every left sector reads from them), wave pad_ the heavy ones
+        for (int w = ch.pad_;; w = 0) {
+          const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[w];
+          unsigned spins = 0;
+          while (sl_ld_acquire(a.ctr + 4 + w) < need) {
+            __nanosleep(256);
+            if (++spins > (1u << 22)) {  // ~1 s: something is wrong; flag it and go on (results are then invalid)
+              atomicAdd(a.ctr + 2, 1ull);
+              break;
+            }
+          }
+          if (w == 0) break;
+        }
+      }
+      __syncwarp();
+    }
+    if (!(a.dbg & 4)) sl_mix_chunk<U>(a, ch, bases, lane);
+  }
+}
+
 // Roles: warps 0 .. SL_NCONS-1 = consumers (DMMA; they also load the slab of a job themselves, all 128 threads,
 // while the A chunks the producer has already queued wait in the ring: a job switch costs one slab latency);
 // warp SL_NCONS = producer (job tickets, job records, the A ring); warps SL_NCONS+1 .. = mixers (stage W).
-// Register budget: the CTA is launched with 128 registers per thread; the consumer warp group grows to 184, the
-// other warp group shrinks to 72 (setmaxnreg).
+// Register budget: launched with 128 per thread (2 CTAs x 256 threads); the consumer warp group grows to 168 (with 124
+// the DMMA loops lose a third of their speed: fewer fragment loads in flight), the other warp group shrinks to 88,
+// enough for 12 independent 16-byte loads per mixer lane.
 constexpr int SL_JOBQ = 2;
 __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_constant__ StackArgs a,
                                                                     const __grid_constant__ Bases bases) {
@@ -264,8 +327,6 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
   uint64_t* jfull = rg.empty + SL_STAGES;
   uint64_t* jempty = jfull + SL_JOBQ;
   int* job_slot = reinterpret_cast<int*>(jempty + SL_JOBQ);  // SL_JOBQ records
-  double* mix_sm = reinterpret_cast<double*>(job_slot + SL_JOBQ * SL_JOBWORDS + 2);
-  mix_sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(mix_sm) + 15) & ~uintptr_t(15));
   rg.stage = 0;
   rg.phase = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -290,7 +351,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
 
   if (warp < SL_NCONS) {
     // =========================== CONSUMERS ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;\n");
     while (true) {
       sl_mbar_wait(&jfull[jq], jphase);
       StackJob job;
@@ -345,8 +406,10 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
         jphase ^= 1u;
       }
     }
+    // no stack jobs left: help with the mix (the last wave's targets are still to be formed)
+    if (a.nmix > 0) sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;\n");
     if (warp == SL_NCONS) {
       // =========================== PRODUCER ===========================
       const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.njobs + (int)gridDim.x);
@@ -418,34 +481,10 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
           }
         }
       }
+      if (a.nmix > 0) sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
     } else if (a.nmix > 0) {
       // =========================== MIXERS (stage W) ===========================
-      const int mw = warp - SL_NCONS - 1;
-      const double** sptr = reinterpret_cast<const double**>(mix_sm + mw * SL_MIXSRC * 2);
-      double* scoef = mix_sm + mw * SL_MIXSRC * 2 + SL_MIXSRC;
-      const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + (int)gridDim.x * SL_NMIX);
-      while (true) {
-        unsigned long long tk = 0;
-        if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= (unsigned long long)a.nmix) break;
-        const MixChunk ch = a.mc[tk];
-        if (ch.pad_ >= 0) {
-          if (lane == 0) {
-            const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[ch.pad_];
-            unsigned spins = 0;
-            while (sl_ld_acquire(a.ctr + 4 + ch.pad_) < need) {
-              __nanosleep(256);
-              if (++spins > (1u << 22)) {  // ~1 s: something is wrong; flag it and go on (results are then invalid)
-                atomicAdd(a.ctr + 2, 1ull);
-                break;
-              }
-            }
-          }
-          __syncwarp();
-        }
-        if (!(dbg & 4)) sl_mix_chunk(a, ch, bases, sptr, scoef, lane);
-      }
+      sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
     }
   }
 }
