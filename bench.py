@@ -42,10 +42,11 @@ def parse():
     ap.add_argument("--sym", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-groundstate", action="store_true", help="skip the C1 time-to-converge leg")
-    ap.add_argument("--shard", default="site", choices=["site", "mpo"],
-                    help="N>1: 'site' = independent per-site replicas (default, no collective); 'mpo' = ONE apply "
-                         "sharded over MPO levels with an NCCL allreduce of y per apply (strong scaling)")
+    ap.add_argument("--no-groundstate", action="store_true", help="skip the time-to-converge leg")
+    ap.add_argument("--shard", default="sector", choices=["sector", "site"],
+                    help="N>1: 'sector' (default) = ONE apply sharded over the left symmetry sectors / MPO levels inside "
+                         "libhtn (htn_plan_heff_ac_sharded) with an NCCL allreduce of y per apply, strong scaling; "
+                         "'site' = independent per-site replicas, no collective, weak scaling")
     return ap.parse_args()
 
 
@@ -55,7 +56,6 @@ def workload_config(args, extra=None):
                     "d=3 multiplets, unit cell 4 (SURVEY.md 8(d))" % (args.D, args.chi),
         "D_red": args.D, "chi": args.chi, "symmetry": "fZ2xSU2xU1" if args.sym == 0 else "fZ2xU1xU1",
         "cache": "inputs larger than L2 (GL+GR+workspaces ~1.2 GB per apply vs 126 MB L2), no flush",
-        "parallelism": "site-parallel replicas (rank r -> unit-cell site r mod 4), no collective",
     }
     if extra:
         cfg.update(extra)
@@ -63,84 +63,111 @@ def workload_config(args, extra=None):
 
 
 # ----------------------------------------------------------------------------------------
-# CPU baseline (oracle port) — also the body of --impl reference
+# CPU side: the oracle's H_AC on EXACTLY the inputs the GPU arm uploads -- cpu_baseline leg and --impl reference.
+# Nothing here touches libhtn.so: the two pure-python input builders of the package are imported without running
+# the package's __init__ (which dlopens the library).
 # ----------------------------------------------------------------------------------------
-def cpu_case(args, chi_sample):
-    """Oracle-side construction of the same synthetic model restricted to the first
-    `chi_sample` MPO levels (bounded sample); pure numpy, no GPU involved."""
+def _pure_modules():
+    import importlib
+    import types
+    if "hubbardtn_b200" not in sys.modules:
+        pkg = types.ModuleType("hubbardtn_b200")
+        pkg.__path__ = [os.path.join(ROOT, "hubbardtn_b200")]
+        sys.modules["hubbardtn_b200"] = pkg          # stub: submodules resolve, __init__.py does not run
+    return importlib.import_module("hubbardtn_b200.sectors"), importlib.import_module("hubbardtn_b200.synthetic")
+
+
+def host_case(args, site=0):
+    """Oracle tensors holding the data of hubbardtn_b200.synthetic.HeffCase(sym, D, chi, site) (same Philox streams,
+    same canonical block order = packed host layout; tests/util.py:oracle_view checks that equality on the GPU)."""
+    import math
     import numpy as np
-    from hubbardtn_b200 import sectors as PS, synthetic
-    from oracle import sectors as OS  # noqa: F401
+    PS, synthetic = _pure_modules()
     from oracle.heff import HeffACPlan
     from oracle.tensors import EnvTensor, Legs, MPOTensor, MPSTensor, Space
 
-    sym, D = args.sym, args.D
+    sym, D, chi = args.sym, args.D, args.chi
     phys = PS.physical_space(sym, 1, 1)
-    levels = synthetic.mpo_levels(sym, chi_sample)
-    entries = synthetic.mpo_entries(sym, levels, phys, 4, synthetic.SEED)
-    Vl, Vr = Space(sym, synthetic.bond_space(sym, D, 0)), Space(sym, synthetic.bond_space(sym, D, 1))
+    levels = synthetic.mpo_levels(sym, chi)
+    entries = synthetic.mpo_entries(sym, levels, phys, 4, synthetic.SEED + site)
+    Vl = Space(sym, synthetic.bond_space(sym, D, site & 1))
+    Vr = Space(sym, synthetic.bond_space(sym, D, 1 - (site & 1)))
     P, M = Legs(sym, phys), Legs(sym, levels)
-    rng = np.random.default_rng(synthetic.SEED)
-    GL = EnvTensor("L", Vl, M, identity_levels=[0]).randomize(rng)
-    GR = EnvTensor("R", Vr, M, identity_levels=[chi_sample - 1]).randomize(rng)
+
+    def fill(t, shapes, stream, scale, identity=None):
+        n = int(sum(r * c for r, c in shapes))
+        data = synthetic.random_packed(n, stream + 10 * site, synthetic.SEED) * scale
+        off = 0
+        for k, (r, c) in zip(t.keys, shapes):
+            blk = data[off:off + r * c].reshape(r, c)
+            t.blocks[k] = np.eye(r) if (identity is not None and k[0] == identity) else np.array(blk)
+            off += r * c
+        return t
+
+    GL = EnvTensor("L", Vl, M, identity_levels=[0])
+    GR = EnvTensor("R", Vr, M, identity_levels=[chi - 1])
+    x = MPSTensor(Vl, P, Vr)
+    fill(GL, [GL.shape(k) for k in GL.keys], 1, 1.0 / math.sqrt(max(D, 1)), identity=0)
+    fill(GR, [GR.shape(k) for k in GR.keys], 2, 1.0 / math.sqrt(max(D, 1)), identity=chi - 1)
+    fill(x, [x.blocks[k].shape for k in x.keys], 3, 1.0)
     W = MPOTensor(M, P, M, {k: v for k, v in entries.items()})
-    x = MPSTensor(Vl, P, Vr).randomize(rng)
     return HeffACPlan(GL, W, GR, x), x
 
 
-def run_cpu_baseline(args, threads, budget_s):
-    """Times oracle applies on the host cores: BLAS threads = 1, `threads` workers over sector
-    blocks (the reference's policy, HubbardFunctions.jl:29,37).  Returns applies/s of the FULL
-    workload, extrapolated by algorithmic flops from a bounded sample of MPO levels."""
+def cpu_apply_timing(args, threads, budget_s, max_reps=20):
+    """Times FULL oracle applies on the host cores: BLAS threads = 1, `threads` workers over sector blocks (the
+    reference's policy, HubbardFunctions.jl:29,37).  Returns (flops, seconds per apply, reps, checksum of y)."""
+    import numpy as np
     from threadpoolctl import threadpool_limits
-    chi_sample = min(args.chi, 16)
     with threadpool_limits(limits=1):
-        plan, x = cpu_case(args, chi_sample)
+        plan, x = host_case(args)
         t0 = time.perf_counter()
-        plan.apply(x, threads=threads)             # warm-up + duration estimate
+        y = plan.apply(x, threads=threads)             # warm-up + duration estimate
         one = time.perf_counter() - t0
-        n = max(1, min(20, int(budget_s / max(one, 1e-3))))
+        n = max(1, min(max_reps, int(budget_s / max(one, 1e-3))))
         t0 = time.perf_counter()
         for _ in range(n):
-            plan.apply(x, threads=threads)
+            y = plan.apply(x, threads=threads)
         dt = (time.perf_counter() - t0) / n
-    return plan.flops, dt, chi_sample, n
-
-
-def full_flops_from_sample(args, sample_flops, chi_sample, full_flops=None):
-    if full_flops is not None:
-        return full_flops
-    # levels are statistically alike: scale by the number of active (non-identity) levels
-    return sample_flops * (args.chi - 1.0) / (chi_sample - 1.0)
+    checksum = float(sum(np.sum(y.blocks[k]) for k in x.keys))
+    return plan.flops, dt, n, checksum
 
 
 def reference_main(args):
+    """--impl reference: the reference's CPU path for this metric.  Julia / MPSKit are not in the image, so
+    this is the oracle port: the SAME workload (all chi MPO levels, same seeded inputs, same config dict) on all host
+    cores; each step = one full apply."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from threadpoolctl import threadpool_limits
     threads = os.cpu_count() or 1
-    per_step = []
-    flops = chi_s = None
-    total = max(1, min(args.steps, 5))
-    for i in range(args.warmup if args.warmup < 2 else 1):
-        run_cpu_baseline(args, threads, 2.0)
-    for i in range(total):
-        flops, dt, chi_s, n = run_cpu_baseline(args, threads, max(2.0, args.cpu_seconds / total))
-        per_step.append(dt)
-    dt = sum(per_step) / len(per_step)
-    full = full_flops_from_sample(args, flops, chi_s)
-    value = 1.0 / (dt * full / flops)
-    sample = ("oracle HeffACPlan (numpy/OpenBLAS, BLAS threads=1, %d worker threads over blocks) on the same D=%d "
-              "spaces restricted to the first %d of %d MPO levels; applies/s scaled by algorithmic flops "
-              "(%.3g of %.3g)" % (threads, args.D, chi_s, args.chi, flops, full))
+    with threadpool_limits(limits=1):
+        plan, x = host_case(args)
+        W = max(1, min(args.warmup, 3))
+        K = max(1, min(args.steps, 20))                 # bounded sample: each step is a full apply (~0.5 s)
+        for _ in range(W):
+            plan.apply(x, threads=threads)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            y = plan.apply(x, threads=threads)
+        dt = (time.perf_counter() - t0) / K
+    import numpy as np
+    value = 1.0 / dt
+    sample = ("oracle HeffACPlan (numpy/OpenBLAS dgemm per block, BLAS threads=1, %d worker threads over blocks): %d full "
+              "applies of the same workload (all %d MPO levels, the GPU arm's seeded inputs); %.1f GFLOP/s = %.2f GFLOP/s "
+              "per core" % (threads, K, args.chi, plan.flops / dt / 1e9, plan.flops / dt / 1e9 / threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, {"algorithmic_gflop_per_apply": plan.flops / 1e9}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = CPU restatement (oracle port), NOT MPSKit: Julia is not in the image (DESIGN.md)",
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "checksum": float(sum(np.sum(y.blocks[k]) for k in x.keys))},
+        "gflops_per_core": plan.flops / dt / 1e9 / threads,
+        "note": "reference = CPU restatement (oracle port), NOT MPSKit: Julia is not in the image (DESIGN.md); "
+                "baseline/run_reference.jl times the unmodified reference where Julia exists",
     }
     print(json.dumps(line))
     return 0
@@ -261,62 +288,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-def mpo_sharded_main(args, ctx, case, plan, x, y, y_t, full_flops, rank, world, local):
-    """Strong-scaling mode: one H_AC apply split over MPO level pairs, NCCL allreduce of y per apply."""
-    import torch
-    import torch.distributed as dist
-
-    def step():
-        plan.apply(x, y)
-        ctx.synchronize()                  # library stream -> torch's stream hand-over
-        dist.all_reduce(y_t, op=dist.ReduceOp.SUM)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_max = float(t.item())
-    checksum = float(y_t.sum().item())     # of the reduced y (before the shard-only timing below overwrites it)
-    shard_ms = plan.time(x, y, min(args.steps, 50)) / min(args.steps, 50)
-    tt = torch.tensor([shard_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        value = args.steps / wall_max
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, {"parallelism": "ONE apply sharded over MPO level pairs by left level (hubbardtn_b200/sharding.py "
-                                             "partition_rows; the synthetic level graph is one connected component, so the "
-                                             "chain-preserving partition cannot split it), NCCL allreduce(sum) of y (%d B) per apply"
-                                             % (y_t.numel() * 8),
-                                             "algorithmic_gflop_per_apply": full_flops / 1e9,
-                                             "this_rank_gflop": plan.stats["flops"] / 1e9}),
-            "tflops_fp64": value * full_flops / 1e12,
-            "slowest_shard_apply_ms": float(tt.item()), "allreduce_bytes": int(y_t.numel() * 8),
-            "timing": "host wall clock around apply + stream sync + NCCL allreduce, max over ranks",
-            "gpu_launches": int(plan.stats["launches_per_apply"]) * args.steps, "checksum": checksum}))
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0
-
-
-# ----------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
-        return reference_main(args)
+        rc = reference_main(args)
+        assert "hubbardtn_b200._lib" not in sys.modules, "the reference arm must not load libhtn.so"
+        return rc
 
     import numpy as np
     import torch
@@ -330,24 +307,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from hubbardtn_b200 import device, synthetic
-    ctx = device.Context(local)
     from hubbardtn_b200 import sharding
-    mpo_sharded = args.shard == "mpo" and world > 1
-    if mpo_sharded:
-        # every rank holds the SAME site problem but only its share of the MPO level pairs; y is the
-        # allreduce(sum) of the partial applies (SURVEY.md 8(e) axis 2)
-        case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=0)
-        full_flops = case.plan.stats["flops"]
-        mine = sharding.shard_mpo_entries(case.w_entries, args.chi, world, rank, mode="rows")
-        Wr = device.Mpo(ctx, case.M, case.P, case.M, mine)
-        case.plan = device.HeffAC(ctx, case.GL, Wr, case.GR, case.x)
-        y_t = torch.as_tensor(case.y.device_array(), device="cuda")
-    else:
-        case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=sharding.site_for_rank(rank, 4))
+    ctx = device.Context(local)
+    strong = world > 1 and args.shard == "sector"
+    # strong scaling: every rank holds the SAME site-0 problem and owns a shard of its terms (left symmetry sectors,
+    # heavy ones split by MPO level: htn_plan_heff_ac_sharded); y = NCCL allreduce(sum) of the partial applies,
+    # enqueued on the library's stream right behind the apply (no host synchronisation in between).
+    # replicas ('--shard site'): rank r applies H_AC of unit-cell site r mod 4, no collective.
+    case = synthetic.HeffCase(ctx, args.sym, D=args.D, chi=args.chi, site=0 if (strong or world == 1) else sharding.site_for_rank(rank, 4))
+    full_stats = case.plan.stats
+    if strong:
+        case.plan = device.HeffAC(ctx, case.GL, case.W, case.GR, case.x, nshards=world, shard=rank)
     plan, x, y = case.plan, case.x, case.y
     st = plan.stats
-    if mpo_sharded:
-        return mpo_sharded_main(args, ctx, case, plan, x, y, y_t, full_flops, rank, world, local)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
+    y_t = torch.as_tensor(y.device_array(), device="cuda")
 
     def barrier():
         ctx.synchronize()
@@ -356,38 +330,52 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(k):
+        """k steps on the library stream; returns device ms (CUDA events on that stream)."""
+        if not strong:
+            return plan.time(x, y, k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lib_stream):
+            e0.record(lib_stream)
+            for _ in range(k):
+                plan.apply(x, y)                              # library stream
+                dist.all_reduce(y_t, op=dist.ReduceOp.SUM)    # ordered behind it (torch: current stream = library stream)
+            e1.record(lib_stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
     # ---- warm-up (>=3) -------------------------------------------------------------------
     W = max(args.warmup, 3)
-    plan.time(x, y, W)
-    # ---- FP64 peak of this GPU (roofline denominator; not in MEASURED_PEAKS.json) -----------
+    run_steps(W)
+    # ---- FP64 peak of this GPU (roofline denominator; not in MEASURED_PEAKS.json; profiles/fp64_peak.json) ----
     dmma_peak = ctx.probe_fp64_peak(0)
     dfma_peak = ctx.probe_fp64_peak(1)
-    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-    b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     torch.matmul(a, b)
     best = 0.0
-    for _ in range(5):
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         torch.matmul(a, b)
         e1.record()
         torch.cuda.synchronize()
-        best = max(best, 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     cublas_peak = best
     del a, b
     peak = max(dmma_peak, dfma_peak, cublas_peak)
 
-    # ---- timed region: exactly K applies, device time, max over ranks ----------------------
+    # ---- timed region: exactly K steps, device time on the launching stream, max over ranks -----------------
     sampler = ClockSampler(local)
     sampler.start()
-    plan.time(x, y, max(W, 200))          # sampler start-up happens under load, outside the timed region
+    run_steps(max(W, 200))          # sampler start-up happens under load, outside the timed region
     barrier()
     t_lo = time.time()
-    ms = plan.time(x, y, args.steps)
+    ms = run_steps(args.steps)
     barrier()
     t_hi = time.time()
     reps_more = int(1.0 / max(ms / args.steps * 1e-3, 1e-6))   # ~1 s more of the same loop for the clock samples
-    plan.time(x, y, max(1, reps_more))
+    run_steps(max(1, reps_more))
     t_end = time.time()
     sampler.window, sampler.timed = (t_lo, t_end), (t_lo, t_hi)
     clocks = sampler.stop()
@@ -395,94 +383,140 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * args.steps / (ms_max * 1e-3)
+    value = (1 if strong else world) * args.steps / (ms_max * 1e-3)
+    checksum_dev = float(y_t.sum().item())                     # of the (reduced) y left by the timed loop
 
-    # ---- per-stage times (dominant kernel = grouped_gemm_kernel, stages L and R) -----------
+    # ---- per-stage times of this rank's plan ------------------------------------------------------------
     prof = plan.profile(x, y, reps=max(5, min(args.steps, 100)))
     gemm_ms = prof["stage_L_ms"] + prof["stage_R_ms"]
     achieved = st["flops"] / (gemm_ms * 1e-3) / 1e12
+    shard_ms = plan.time(x, y, min(args.steps, 100)) / min(args.steps, 100)
+    per_rank = torch.tensor([shard_ms, st["flops"]], dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gathered, per_rank)
+    else:
+        gathered = [per_rank]
+    shard_table = [[float(g[0]), float(g[1]) / 1e9] for g in gathered]
 
     # ---- e2e: host buffers through the C ABI (pinned), H2D + D2H inside the timed region ----
     xh = torch.from_numpy(case.x_host.copy()).pin_memory()
     yh = torch.empty_like(xh).pin_memory()
+    yh_t = None
     n = x.nelem
-    for _ in range(3):
-        plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)   # returns after the D2H copy completed
-    e2e_s = time.perf_counter() - t0
+    if strong:
+        # sharded e2e: every rank uploads x, applies its shard, the partial y is allreduced on the device and
+        # downloaded (the call sequence a Julia host would issue per Krylov step)
+        def e2e_step():
+            x.upload_ptr(xh.data_ptr(), n)
+            with torch.cuda.stream(lib_stream):
+                plan.apply(x, y)
+                dist.all_reduce(y_t, op=dist.ReduceOp.SUM)
+            y.download_ptr(yh.data_ptr(), n)                  # library stream: ordered behind the allreduce
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_s = time.perf_counter() - t0
+        checksum = float(yh.numpy().sum())
+    else:
+        for _ in range(3):
+            plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            plan.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), n)   # returns after the D2H copy completed
+        e2e_s = time.perf_counter() - t0
+        checksum = float(yh.numpy().sum())
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(te.item())
-    checksum = float(yh.numpy().sum())
+    e2e_value = (1 if strong else world) * args.steps / float(te.item())
 
-    # ---- ncu-measured DRAM traffic of the dominant kernel (committed capture; per launch) --------
+    # ---- ncu-measured DRAM traffic of the dominant kernels (committed capture; per apply) --------
     traffic = None
+    traffic_note = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_roofline_inputs.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")) as f:
             ri = json.load(f)
         if args.D == 1024 and args.chi == 96 and args.sym == 0:
-            traffic = ri["grouped_gemm_traffic_bytes_per_launch"]
+            traffic = ri["gemm_traffic_bytes_per_launch"]
+            traffic_note = ri.get("note")
     except Exception:
         traffic = None
 
     # ---- Krylov vector kernels against the HBM roofline (north star: "HBM GB/s for the Krylov kernels") ----
     kry = None
-    try:
-        kry = device.probe_krylov(x, nvec=30, reps=20)
-        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") if os.path.exists(
-            os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-        kry["hbm_peak_GBs"] = hbm
-        kry["note"] = ("30 basis vectors of len(AC) = %.1f MB: the whole basis (%.0f MB) fits the 126 MB L2, so rates above "
-                       "the HBM peak are L2 hits" % (kry["vector_bytes"] / 1e6, 31 * kry["vector_bytes"] / 1e6))
-    except Exception as e:          # keep the headline line alive
-        kry = {"error": str(e)}
+    if rank == 0:
+        try:
+            kry = device.probe_krylov(x, nvec=30, reps=20)
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+            kry["hbm_peak_GBs"] = hbm
+            kry["note"] = ("30 basis vectors of len(AC) = %.1f MB: the whole basis (%.0f MB) fits the 126 MB L2, so rates above "
+                           "the HBM peak are L2 hits" % (kry["vector_bytes"] / 1e6, 31 * kry["vector_bytes"] / 1e6))
+        except Exception as e:          # keep the headline line alive
+            kry = {"error": str(e)}
 
-    # ---- ground-state time-to-converge (BASELINE metric part 2) on config C1, rank 0 only ----------
+    # ---- ground-state time-to-converge (BASELINE metric part 2), rank 0 of a single-GPU run only ----------
     gs = None
-    if rank == 0 and not args.no_groundstate:
+    if rank == 0 and world == 1 and not args.no_groundstate:
         gs = groundstate_leg(ctx, args)
 
     line = None
     if rank == 0:
+        par = ("one GPU" if world == 1 else
+               ("ONE apply sharded over the left symmetry sectors (heavy sectors split by MPO level) inside libhtn "
+                "(htn_plan_heff_ac_sharded): GL/T/U rows and stage L are partitioned, NCCL allreduce(sum) of y (%d B) per "
+                "apply on the library stream" % (y_t.numel() * 8) if strong else
+                "site-parallel replicas (rank r -> unit-cell site r mod 4), no collective"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, {"x_elems": n, "algorithmic_gflop_per_apply": st["flops"] / 1e9,
-                                             "executed_gflop_per_apply_padded": st["padded_flops"] / 1e9,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if (strong or world == 1) else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"parallelism": par, "x_elems": n,
+                                             "algorithmic_gflop_per_apply": full_stats["flops"] / 1e9,
+                                             "executed_gflop_per_apply_padded": full_stats["padded_flops"] / 1e9,
                                              "workspace_MB": st["workspace_bytes"] / 1e6}),
-            "tflops_fp64": value * st["flops"] / 1e12,
+            "tflops_fp64": value * full_stats["flops"] / 1e12,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                     "checksum": checksum},
             "gpu_launches": int(st["launches_per_apply"]) * args.steps,
             "stages_ms": prof,
             "roofline": {
-                "bound": "tensor", "kernel": "grouped_gemm_kernel (stage L + stage R launches)",
+                "bound": "tensor", "kernel": "stack_gemm_kernel (stage L, the stage-W mix rides along) + grouped_gemm_kernel (stage R)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "bytes per launch (mean of the stage-L and stage-R launches), ncu dram__bytes_read+write, "
-                                "profiles/r1_roofline_inputs.json",
+                "traffic_note": traffic_note,
                 "algorithmic_flop_per_launch": st["flops"] / 2.0,
-                "peak_source": "measured live on this GPU: max(DMMA.8x8x4 issue loop %.2f, DFMA loop %.2f, cuBLAS "
-                               "DGEMM 4096^3 %.2f) TFLOP/s; MEASURED_PEAKS.json has no FP64 entry"
-                               % (dmma_peak, dfma_peak, cublas_peak),
-                "whole_apply_frac": (value / world) * st["flops"] / 1e12 / peak,
+                "peak_source": "peak measured by this repo's probe, live on this GPU: max(DMMA.8x8x4 issue loop %.2f, DFMA loop "
+                               "%.2f, cuBLAS DGEMM 8192^3 %.2f) TFLOP/s; MEASURED_PEAKS.json has no FP64 entry "
+                               "(profiles/fp64_peak.json holds the committed probe run)" % (dmma_peak, dfma_peak, cublas_peak),
+                "whole_apply_frac": value * full_stats["flops"] / 1e12 / peak / (world if strong else 1) if strong
+                else (value / world) * st["flops"] / 1e12 / peak,
             },
         }
-    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -----------------------
+        if world > 1:
+            line["shards"] = {"per_rank_apply_ms_and_gflop": shard_table,
+                              "collective": "NCCL allreduce(sum, f64) of y, %d bytes, stream-ordered behind the apply" % (y_t.numel() * 8)
+                              if strong else "none",
+                              "checksum_of_reduced_y": checksum_dev}
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) + checksum pin ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        flops_s, dt, chi_s, nrep = run_cpu_baseline(args, threads, args.cpu_seconds)
-        cpu_value = 1.0 / (dt * st["flops"] / flops_s)
+        flops_c, dt, nrep, cpu_checksum = cpu_apply_timing(args, threads, args.cpu_seconds)
         line["cpu_baseline"] = {
-            "value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "oracle HeffACPlan (numpy/OpenBLAS, BLAS threads=1, %d worker threads over blocks), same "
-                      "D=%d spaces, first %d of %d MPO levels, %d applies; scaled by algorithmic flops (%.3g of %.3g)"
-                      % (threads, args.D, chi_s, args.chi, nrep, flops_s, st["flops"])}
+            "value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle HeffACPlan (numpy/OpenBLAS dgemm per block, BLAS threads=1, %d worker threads over blocks): %d full "
+                      "applies of the same workload (all %d MPO levels, same seeded inputs); %.1f GFLOP/s = %.2f GFLOP/s per core"
+                      % (threads, nrep, args.chi, flops_c / dt / 1e9, flops_c / dt / 1e9 / threads)}
+        # the e2e result of the GPU arm is pinned on the oracle's value for the same inputs
+        rel = abs(checksum - cpu_checksum) / max(abs(cpu_checksum), 1e-300)
+        line["e2e"]["oracle_checksum"] = cpu_checksum
+        line["e2e"]["checksum_rel_err"] = rel
+        assert rel < 1e-9, "GPU e2e checksum %r differs from the oracle's %r" % (checksum, cpu_checksum)
     if rank == 0:
         if gs is not None:
             line["groundstate"] = gs

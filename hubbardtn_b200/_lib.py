@@ -60,6 +60,7 @@ SIGNATURES = {
     "htn_last_error_string": (C.c_char_p, [_p]),
     "htn_version": (_i32, []),
     "htn_ctx_synchronize": (_i32, [_p]),
+    "htn_ctx_stream": (_i32, [_p, _pp]),
     "htn_space_create": (_i32, [_p, _i32, _i32, _pi32, _pi32, _pp]),
     "htn_space_destroy": (_i32, [_p]),
     "htn_space_info": (_i32, [_p, _pi32, _pi32, _pi32]),
@@ -89,6 +90,7 @@ SIGNATURES = {
     "htn_mpo_entries": (_i32, [_p, _pi32, _pi32, _pi32, _pd]),
     "htn_mpo_destroy": (_i32, [_p]),
     "htn_plan_heff_ac": (_i32, [_p, _p, _p, _p, _p, _pp]),
+    "htn_plan_heff_ac_sharded": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _pp]),
     "htn_plan_heff_c": (_i32, [_p, _p, _p, _p, _pp]),
     "htn_plan_destroy": (_i32, [_p]),
     "htn_plan_transfer": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _pp]),

@@ -101,6 +101,12 @@ int32_t htn_ctx_destroy(htn_ctx* ctx) {
 
 const char* htn_last_error_string(htn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
+int32_t htn_ctx_stream(htn_ctx* ctx, void** stream) {
+  if (!ctx || !stream) return HTN_ERR_INVALID;
+  *stream = reinterpret_cast<void*>(ctx->stream);
+  return HTN_OK;
+}
+
 int32_t htn_ctx_synchronize(htn_ctx* ctx) {
   if (!ctx) return HTN_ERR_INVALID;
   CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -332,6 +332,84 @@ static std::map<HTerm, double> one_site_terms(int sym, const htn_tensor* like, c
   return terms;
 }
 
+// Multi-GPU sharding of ONE effective-Hamiltonian application: the apply is a sum of independent
+// terms, so any partition of the term list gives partial results y_k with y = sum_k y_k (one allreduce).  Units of
+// the partition are the LEFT SECTORS lp of the output: all three stages of a sector (GL rows, T, U, y blocks) stay on
+// one device, nothing is computed twice, and a device only touches the GL panels rows of its sectors.  A sector that
+// is heavier than a fair share (at D=1024 four sectors hold 80 % of the work) is split further by MPO level a of
+// its GL blocks; stage R of such a sector then runs on each of its owners (on their partial U).
+static void shard_terms(std::map<HTerm, double>& terms, const htn_tensor* like, int idL, int nshards, int shard) {
+  if (nshards <= 1) return;
+  const auto& Vl = like->s0;
+  const auto& Vr = like->s1;
+  const int nlp = (int)Vl.sec.size();
+  auto rdim = [&](int yi) { return like->kind == HTN_T_MPS ? like->blocks[yi].lab[2] : like->blocks[yi].lab[4]; };
+  std::map<std::tuple<int, int, int, int>, char> tseen;  // (a,lp,l,xi)
+  std::map<std::tuple<int, int, int>, char> useen;       // (b,yi,r)
+  std::vector<double> costR(nlp, 0.0), costL(nlp, 0.0);
+  std::map<std::pair<int, int>, double> costLa;  // (lp,a)
+  for (auto& kv : terms) {
+    if (kv.second == 0.0) continue;
+    const HTerm& t = kv.first;
+    const double nlpv = Vl.mult[t.lp];
+    if (t.a != idL && !tseen.count({t.a, t.lp, t.l, t.xi})) {
+      tseen[{t.a, t.lp, t.l, t.xi}] = 1;
+      const double c = nlpv * Vl.mult[t.l] * like->blocks[t.xi].cols;
+      costL[t.lp] += c;
+      costLa[{t.lp, t.a}] += c;
+    }
+    if (!useen.count({t.b, t.yi, t.r})) {
+      useen[{t.b, t.yi, t.r}] = 1;
+      costR[t.lp] += nlpv * like->blocks[t.xi].cols * Vr.mult[rdim(t.yi)];
+    }
+  }
+  double total = 0.0;
+  for (int lp = 0; lp < nlp; ++lp) total += costL[lp] + costR[lp];
+  const double fair = total / nshards;
+  struct Unit {
+    int lp, part, nparts;
+    double cost;
+  };
+  std::vector<Unit> units;
+  std::map<std::pair<int, int>, int> part_of;  // (lp,a) -> part
+  for (int lp = 0; lp < nlp; ++lp) {
+    const double c = costL[lp] + costR[lp];
+    if (c <= 0) continue;
+    int k = c > 1.15 * fair ? (int)std::ceil(c / fair) : 1;
+    std::vector<std::pair<double, int>> la;  // levels of this sector by falling cost
+    for (auto& kv : costLa)
+      if (kv.first.first == lp) la.push_back({kv.second, kv.first.second});
+    k = std::max(1, std::min<int>(k, (int)la.size()));
+    std::sort(la.begin(), la.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+    std::vector<double> load(k, 0.0);
+    for (auto& pr : la) {
+      const int i = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[i] += pr.first;
+      part_of[{lp, pr.second}] = i;
+    }
+    for (int i = 0; i < k; ++i) units.push_back(Unit{lp, i, k, load[i] + costR[lp]});
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.cost > y.cost; });
+  std::vector<double> sload(nshards, 0.0);
+  std::map<std::pair<int, int>, int> owner;  // (lp,part) -> shard
+  for (const Unit& u : units) {
+    const int i = (int)(std::min_element(sload.begin(), sload.end()) - sload.begin());
+    sload[i] += u.cost;
+    owner[{u.lp, u.part}] = i;
+  }
+  for (auto it = terms.begin(); it != terms.end();) {
+    const HTerm& t = it->first;
+    auto pit = part_of.find({t.lp, t.a});
+    const int part = pit == part_of.end() ? 0 : pit->second;  // identity-level terms ride with part 0
+    auto oit = owner.find({t.lp, part});
+    const int own = oit == owner.end() ? 0 : oit->second;
+    if (own != shard)
+      it = terms.erase(it);
+    else
+      ++it;
+  }
+}
+
 // Back end shared by H_AC and H_AC2: U blocks (stage W), stage R with split-K, final mix into y.
 // slots: 0 = x, 1 = y, 2 = GL, 3 = GR
 static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_tensor* GR, LeftFront& F, int* n_u_out,
@@ -447,8 +525,15 @@ static void fill_stats(htn_plan* p, int n_t, int n_u, int n_mix_t, int n_mix_s) 
 // slots: 0 = x, 1 = y, 2 = GL, 3 = GR
 int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
                          const htn_tensor* like, htn_plan** out) {
+  return htn_plan_heff_ac_sharded(ctx, GL, W, GR, like, 1, 0, out);
+}
+
+// shard `shard` of `nshards`: this plan computes a partial y; the sum over the shards (one allreduce) is H_AC x
+int32_t htn_plan_heff_ac_sharded(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
+                                 const htn_tensor* like, int32_t nshards, int32_t shard, htn_plan** out) {
   if (!ctx || !GL || !W || !GR || !like || !out) return HTN_ERR_INVALID;
   *out = nullptr;
+  if (nshards < 1 || shard < 0 || shard >= nshards) return ctx->fail(HTN_ERR_INVALID, "plan_heff_ac: shard index out of range");
   if (GL->kind != HTN_T_ENVL || GR->kind != HTN_T_ENVR || like->kind != HTN_T_MPS)
     return ctx->fail(HTN_ERR_INVALID, "plan_heff_ac: wrong tensor kinds");
   const int sym = like->sym;
@@ -476,6 +561,7 @@ int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, c
     Program& pg = p->prog;
     EnvView gl{GL};
     auto terms = one_site_terms(sym, like, gl, W, [&](int b, int r, int rp) { return GR->find(b, r, rp) >= 0; });
+    shard_terms(terms, like, gl.identity_level(), nshards, shard);
     LeftFront F = build_front(pg, like, gl, terms, 0, 2, true);
     int n_u = 0, n_mix_t = 0, n_mix_s = 0;
     build_heff_backend(pg, like, GR, F, &n_u, &n_mix_t, &n_mix_s);

@@ -35,6 +35,13 @@ class Context:
     def synchronize(self):
         L.check(lib.htn_ctx_synchronize(self.h), self.h)
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the library (for stream-ordered collectives of the caller)."""
+        p = C.c_void_p()
+        L.check(lib.htn_ctx_stream(self.h, C.byref(p)), self.h)
+        return int(p.value or 0)
+
     def probe_fp64_peak(self, which: int = 0) -> float:
         out = C.c_double()
         L.check(lib.htn_probe_fp64_peak(self.h, which, C.byref(out)), self.h)
@@ -209,6 +216,14 @@ class Tensor:
         L.check(lib.htn_tensor_upload(self.h, packed.ctypes.data, packed.size), self.ctx.h)
         return self
 
+    def upload_ptr(self, ptr: int, nelem: int):
+        """Upload from a raw host pointer (e.g. pinned memory)."""
+        L.check(lib.htn_tensor_upload(self.h, ptr, nelem), self.ctx.h)
+        return self
+
+    def download_ptr(self, ptr: int, nelem: int):
+        L.check(lib.htn_tensor_download(self.h, ptr, nelem), self.ctx.h)
+
     def download(self) -> np.ndarray:
         out = np.empty(self.nelem, dtype=np.float64)
         L.check(lib.htn_tensor_download(self.h, out.ctypes.data, out.size), self.ctx.h)
@@ -322,10 +337,11 @@ class _Heff:
 class HeffAC(_Heff):
     """y = H_AC x  (MPSKit `AC_hamiltonian`): plan over fixed GL, W, GR."""
 
-    def __init__(self, ctx: Context, GL: Tensor, W: Mpo, GR: Tensor, like: Tensor):
+    def __init__(self, ctx: Context, GL: Tensor, W: Mpo, GR: Tensor, like: Tensor, nshards: int = 1, shard: int = 0):
+        """`nshards` > 1: this plan computes shard `shard`'s PARTIAL y (sum over the shards = H_AC x)."""
         self.ctx, self.GL, self.W, self.GR = ctx, GL, W, GR   # keep GL/GR alive
         h = C.c_void_p()
-        L.check(lib.htn_plan_heff_ac(ctx.h, GL.h, W.h, GR.h, like.h, C.byref(h)), ctx.h)
+        L.check(lib.htn_plan_heff_ac_sharded(ctx.h, GL.h, W.h, GR.h, like.h, nshards, shard, C.byref(h)), ctx.h)
         self.h = h
         self._finish(like)
 

@@ -69,6 +69,9 @@ int32_t htn_ctx_destroy(htn_ctx* ctx);
 const char* htn_last_error_string(htn_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL */
 int32_t htn_version(void);
 int32_t htn_ctx_synchronize(htn_ctx* ctx);
+/* the library's CUDA stream (cudaStream_t) of this context: collectives of the caller (NCCL allreduce of a sharded y)
+   are enqueued on it so that they are ordered after the apply without a host synchronisation */
+int32_t htn_ctx_stream(htn_ctx* ctx, void** stream);
 
 /* ---- spaces ------------------------------------------------------------------------- */
 /* Replaces: Vect[I](sector => multiplicity ...) (HubbardFunctions.jl:248,251,261,282,343).
@@ -148,6 +151,12 @@ int32_t htn_mpo_destroy(htn_mpo* w);
  * copied; they must outlive the plan) and copies W. `like` fixes the block structure of x,y. */
 int32_t htn_plan_heff_ac(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
                          const htn_tensor* like, htn_plan** out);
+/* Multi-GPU: shard `shard` of `nshards` of the same application ("partitioned by symmetry sector and
+   by MPO virtual index, NCCL allreduce only for the sharded sums"; reference analogue: MPSKit's per-term task
+   parallelism, HubbardFunctions.jl:37).  The plan computes a PARTIAL y; allreduce(sum) over the shards gives H_AC x.
+   Units are the left symmetry sectors of the output (heavy sectors are split further by MPO level). */
+int32_t htn_plan_heff_ac_sharded(htn_ctx* ctx, const htn_tensor* GL, const htn_mpo* W, const htn_tensor* GR,
+                                 const htn_tensor* like, int32_t nshards, int32_t shard, htn_plan** out);
 /* Replaces: MPSKit `AC2_hamiltonian` / `∂∂AC2` (two-site effective Hamiltonian of IDMRG2,
  * HubbardFunctions.jl:1010): y2 = GL . x2 . W1 . W2 . GR; GL = left environment of the first site,
  * GR = right environment of the second site; `like` is a HTN_T_MPS2 tensor. */

@@ -33,3 +33,27 @@ def test_sharded_applies_sum_to_full_apply(ctx, mode, world):
     assert flops >= case.plan.stats["flops"]                  # duplication of shared stages is visible, never hidden
     arr = case.y.device_array().__cuda_array_interface__
     assert arr["typestr"] == "<f8" and arr["shape"][0] >= case.y.nelem
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_library_sector_shards_sum_to_full_apply(ctx, world):
+    """htn_plan_heff_ac_sharded (sector / MPO-level units decided inside the library): the partial applies of all
+    shards sum to the unsharded apply, every stage-L block is computed exactly once, and the shards are balanced."""
+    case = synthetic.HeffCase(ctx, PS.SU2U1, D=256, chi=20)
+    case.plan.apply(case.x, case.y)
+    full = case.y.download()
+    acc = case.y.like()
+    part = case.y.like()
+    flops, n_l = [], 0
+    for rank in range(world):
+        plan = dev.HeffAC(ctx, case.GL, case.W, case.GR, case.x, nshards=world, shard=rank)
+        plan.apply(case.x, part)
+        acc.axpby(1.0, part, 1.0 if rank else 0.0)
+        flops.append(plan.stats["flops"])
+        n_l += plan.stats["n_gemm_L"]
+    got = acc.download()
+    assert np.abs(got - full).max() < 1e-12 * np.abs(full).max()
+    assert n_l == case.plan.stats["n_gemm_L"]                 # stage L is partitioned, never duplicated
+    total = case.plan.stats["flops"]
+    assert total <= sum(flops) <= 1.6 * total                 # stage R of split heavy sectors runs on each owner
+    assert max(flops) <= 2.2 * sum(flops) / world             # no shard carries much more than a fair share
