@@ -63,18 +63,75 @@ int32_t mul_bond(htn_ctx* ctx, const htn_tensor* A, const htn_tensor* B, bool ri
   return rc;
 }
 
-int32_t inv_diag(htn_ctx* ctx, const htn_tensor* C, htn_tensor** out) {
+// out = C^-1 block by block (MPSKit idmrg2: `inv(psi.C[end])`).  The bonds produced by the truncated SVD are diagonal
+// and are inverted on the device; the caller's initial C[L-1] is a general matrix (triangular after the QR gauge,
+// dense after VUMPS): those blocks go through an LU inverse with partial pivoting on the host (<= 342^2 each, once per
+// run -- every later edge bond is diagonal).
+int32_t inv_bond(htn_ctx* ctx, const htn_tensor* C, htn_tensor** out) {
   RC(htn_tensor_create_like(C, out));
-  std::vector<FillBlock> fb;
-  for (const Block& b : C->blocks) fb.push_back(FillBlock{b.off, b.rows, b.cols, b.ld, 0});
-  FillBlock* d = nullptr;
-  if (fb.empty()) return HTN_OK;
-  if (cudaMalloc(&d, fb.size() * sizeof(FillBlock)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "idmrg2: table allocation failed");
-  htn::h2d_on_stream(d, fb.data(), fb.size() * sizeof(FillBlock), ctx->stream);
-  launch_diag_inv(d, (int)fb.size(), C->d, (*out)->d, ctx->stream);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
-  return HTN_OK;
+  if (C->blocks.empty()) return HTN_OK;
+  std::vector<double> host(C->hsize);
+  RC(htn_download_locked(C, host.data(), C->hsize));
+  bool all_diag = true;
+  for (const Block& b : C->blocks) {
+    const double* B = host.data() + b.hoff;
+    const int n = b.rows;
+    for (int i = 0; i < n && all_diag; ++i)
+      for (int j = 0; j < n; ++j)
+        if (i != j && B[(size_t)i * n + j] != 0.0) {
+          all_diag = false;
+          break;
+        }
+    if (!all_diag) break;
+  }
+  if (all_diag) {
+    std::vector<FillBlock> fb;
+    for (const Block& b : C->blocks) fb.push_back(FillBlock{b.off, b.rows, b.cols, b.ld, 0});
+    FillBlock* d = nullptr;
+    if (cudaMalloc(&d, fb.size() * sizeof(FillBlock)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "idmrg2: table allocation failed");
+    htn::h2d_on_stream(d, fb.data(), fb.size() * sizeof(FillBlock), ctx->stream);
+    launch_diag_inv(d, (int)fb.size(), C->d, (*out)->d, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    return HTN_OK;
+  }
+  std::vector<double> inv(C->hsize, 0.0);
+  for (const Block& b : C->blocks) {
+    const int n = b.rows;
+    if (b.cols != n) return ctx->fail(HTN_ERR_SHAPE, "idmrg2: bond blocks must be square");
+    std::vector<double> A(host.begin() + b.hoff, host.begin() + b.hoff + (size_t)n * n);
+    double* X = inv.data() + b.hoff;  // starts as the identity, ends as A^-1 (Gauss-Jordan with row pivoting)
+    for (int i = 0; i < n; ++i) X[(size_t)i * n + i] = 1.0;
+    double amax = 0.0;
+    for (double v : A) amax = std::max(amax, std::fabs(v));
+    for (int k = 0; k < n; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < n; ++i)
+        if (std::fabs(A[(size_t)i * n + k]) > std::fabs(A[(size_t)piv * n + k])) piv = i;
+      if (std::fabs(A[(size_t)piv * n + k]) <= 1e-300 * (1.0 + amax))
+        return ctx->fail(HTN_ERR_INVALID, "idmrg2: singular bond matrix on the unit-cell edge");
+      if (piv != k)
+        for (int j = 0; j < n; ++j) {
+          std::swap(A[(size_t)k * n + j], A[(size_t)piv * n + j]);
+          std::swap(X[(size_t)k * n + j], X[(size_t)piv * n + j]);
+        }
+      const double d = 1.0 / A[(size_t)k * n + k];
+      for (int j = 0; j < n; ++j) {
+        A[(size_t)k * n + j] *= d;
+        X[(size_t)k * n + j] *= d;
+      }
+      for (int i = 0; i < n; ++i) {
+        if (i == k) continue;
+        const double f = A[(size_t)i * n + k];
+        if (f == 0.0) continue;
+        for (int j = 0; j < n; ++j) {
+          A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+          X[(size_t)i * n + j] -= f * X[(size_t)k * n + j];
+        }
+      }
+    }
+  }
+  return htn_upload_locked(*out, inv.data(), C->hsize);
 }
 
 void replace(htn_tensor*& slot, htn_tensor* nw) {
@@ -352,7 +409,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
       // ---- edge (sites L-1, 0) ----
       {
         htn_tensor *ci = nullptr, *left = nullptr, *right = nullptr, *al = nullptr, *c = nullptr, *ar = nullptr;
-        RC(inv_diag(ctx, D.C[L - 1], &ci));
+        RC(inv_bond(ctx, D.C[L - 1], &ci));
         RC(mul_bond(ctx, D.AC[L - 1], ci, true, &left));
         RC(mul_bond(ctx, D.AL[0], D.C[0], true, &right));
         htn_tensor_destroy(ci);
@@ -368,7 +425,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
         replace(D.AR[0], ar);
         replace(D.AC[L - 1], ac1);
         replace(D.AC[0], ac0);
-        RC(inv_diag(ctx, D.C[0], &c0i));
+        RC(inv_bond(ctx, D.C[0], &c0i));
         RC(mul_bond(ctx, D.AC[0], c0i, true, &al0));
         htn_tensor_destroy(c0i);
         replace(D.AL[0], al0);
@@ -380,7 +437,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
       // ---- edge again ----
       {
         htn_tensor *ci = nullptr, *left = nullptr, *right = nullptr, *al = nullptr, *c = nullptr, *ar = nullptr;
-        RC(inv_diag(ctx, D.C[L - 1], &ci));
+        RC(inv_bond(ctx, D.C[L - 1], &ci));
         RC(mul_bond(ctx, D.AC[0], ci, false, &right));
         RC(mul_bond(ctx, D.AR[L - 1], D.C[L - 2], false, &left));
         htn_tensor_destroy(ci);
@@ -396,7 +453,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
         replace(D.AR[0], ar);
         replace(D.AC[L - 1], ac1);
         replace(D.AC[0], ac0);
-        RC(inv_diag(ctx, D.C[L - 2], &cmi));
+        RC(inv_bond(ctx, D.C[L - 2], &cmi));
         RC(mul_bond(ctx, D.AC[L - 1], cmi, false, &arl));
         htn_tensor_destroy(cmi);
         replace(D.AR[L - 1], arl);

@@ -388,7 +388,8 @@ def initial_spaces(sym: int, phys: list, L: int, P: int, max_dimension: int) -> 
         for s, n in v.items():
             inside = (s[1] <= 6 if sym == S.SU2U1 else abs(s[1]) <= L) and abs(s[2]) <= L * P
             if inside or s == (0, 0, 0):
-                capped[s] = min(n, max_dimension) if inside else 1
+                # HF:935/944: Vmax holds (0,0,0)=>1 next to (0,0,0)=>max_dimension
+                capped[s] = min(n, max_dimension + (1 if s == (0, 0, 0) else 0)) if inside else 1
         out.append({s: n for s, n in capped.items() if n > 0})
     return _full_rank(sym, out, phys)
 
@@ -485,16 +486,20 @@ def compute_groundstate(simul: OB_Sim, ctx=None, tol: float = 1e-6, verbosity: i
         raise NotImplementedError("one-site unit cells (VUMPS + SvdCut bond growing, HF:1011-1022) are not mirrored yet")
     psi = init_state if init_state is not None else initialize_mps(H, simul.P, simul.bond_dim, simul.spin, ctx, seed)
     schmidtcut = 10.0 ** (-simul.svalue)                                   # HF:1007
-    AL, AR, C, AC, info1 = dev.idmrg2(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=schmidtcut, tol=tol,
+    # htn_idmrg2 replaces the tensors it is given: work on copies so that the caller's init_state survives (HF:997-1005)
+    start = [[t.like_copy() for t in lst] for lst in (psi.AL, psi.AR, psi.C, psi.AC)]
+    AL, AR, C, AC, info1 = dev.idmrg2(ctx, start[0], start[1], start[2], start[3], H.W, cut=schmidtcut, tol=tol,
                                       maxiter=min(maxiter, 200))           # HF:1010 (MPSKit default maxiter 200)
     AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], simul.sym)      # MPSKit: InfiniteMPS(psi.AR) at the end of IDMRG2
     psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC)
     GL, GR = _make_envs(ctx, psi, H)
     info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))  # HF:1025-1027
+    # ... & GradientGrassmann(; maxiter, tol): MPSKit runs both stages; the second returns at once when tol is already met
     info3 = None
-    if not info2["converged"]:                                             # ... & GradientGrassmann(; maxiter, tol)
+    if True:
         info3 = dev.gradient_grassmann(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))
-        info2 = dict(info2, delta=info3["delta"], energy_per_site=info3["energy_per_site"], converged=info3["converged"])
+        if info3["iterations"] > 0 or not info2["converged"]:
+            info2 = dict(info2, delta=info3["delta"], energy_per_site=info3["energy_per_site"], converged=info3["converged"])
     if verbosity > 0:
         print("IDMRG2: %d iterations, delta %.3e; VUMPS: %d iterations, galerkin %.3e, E/site %.10f"
               % (info1["iterations"], info1["delta"], info2["iterations"], info2["delta"], info2["energy_per_site"]))
@@ -513,6 +518,9 @@ def produce_groundstate(simul: OB_Sim, force: bool = False, **kw):
     else:
         key = (tuple(simul.t), tuple(simul.u), simul.mu, simul.P, simul.Q, simul.svalue, simul.bond_dim, simul.spin,
                simul.period, tuple(simul.kwargs.get("JMs", (0.0, 0.0))))
+    key = key + (kw.get("tol", 1e-6), kw.get("maxiter", 1000), kw.get("seed", 20261018), id(kw.get("ctx")))
+    if kw.get("init_state") is not None:                 # a caller-supplied start is never served from the cache
+        return compute_groundstate(simul, **kw)
     if force or key not in _CACHE:
         _CACHE[key] = compute_groundstate(simul, **kw)
     return _CACHE[key]

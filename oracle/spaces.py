@@ -104,6 +104,6 @@ def initial_bond_spaces(kind: int, phys: list, P: int, bond_dim: int) -> list:
             else:
                 inside = abs(s[1]) <= L and abs(s[2]) <= L * P
             if inside or s == S.trivial(kind):
-                capped[s] = min(n, bond_dim) if inside else 1
+                capped[s] = min(n, bond_dim + (1 if s == (0, 0, 0) else 0)) if inside else 1   # HF:935/944
         out.append(Space(kind, capped))
     return out

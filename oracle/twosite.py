@@ -237,9 +237,14 @@ def tsvd(x: TwoSiteTensor, cut: float = 0.0, maxdim: int = None):
 # IDMRG2
 # ----------------------------------------------------------------------------------------
 def _inv_diag(C: BondTensor) -> BondTensor:
+    """inv(C) block by block (MPSKit idmrg2: `inv(psi.C[end])`): the SVD-made bonds are diagonal, the caller's initial
+    C[L-1] is a general matrix (triangular from the QR gauge, dense after VUMPS)."""
     out = BondTensor(C.V)
     for c, b in C.blocks.items():
-        out.blocks[c] = np.diag(1.0 / np.diag(b))
+        if np.count_nonzero(b - np.diag(np.diag(b))) == 0:
+            out.blocks[c] = np.diag(1.0 / np.diag(b))
+        else:
+            out.blocks[c] = np.linalg.inv(b)
     return out
 
 
