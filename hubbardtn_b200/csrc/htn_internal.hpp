@@ -223,7 +223,9 @@ struct MixChunk {
 };
 
 // Arguments of the fused stage L + W launch.  Counters (64-bit, never reset: `epoch` = 1-based launch number):
-//   ctr[0] job ticket, ctr[1] mix ticket, ctr[2] watchdog flag, ctr[4 + w] consumer-warp arrivals of wave w.
+//   ctr[0] job ticket, ctr[1] mix ticket, ctr[2] watchdog flag, ctr[4 + w] consumer-warp arrivals of wave w,
+//   ctr[4 + nwaves + w] finished mix chunks of wave w (back-pressure: jobs of wave w + lag wait for them),
+//   ctr[4 + 2 nwaves ..] timeline probe (HTN_STACK_DEBUG & 32): first start, last job end, last mix end (globaltimer ns).
 struct StackArgs {
   const StackJob* jobs;
   int njobs;
@@ -232,7 +234,9 @@ struct StackArgs {
   const MixSrc* ms;
   const MixChunk* mc;  // sorted by wave; pad_ = wave the chunk waits for (-1: none)
   int nmix;
-  const int* wave_need;  // arrivals that complete wave w (= SL_NCONS * jobs of the wave)
+  const int* wave_need;  // [w]: arrivals that complete wave w (= SL_NCONS * jobs of the wave); [nwaves + w]: mix chunks of wave w
+  int nwaves;
+  int mix_lag;           // > 0: the jobs of wave w are held back until the mix of wave w - mix_lag is done (T stays in L2)
   unsigned long long* ctr;
   unsigned long long epoch;
   int dbg;

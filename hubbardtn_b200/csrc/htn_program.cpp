@@ -299,10 +299,16 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
   }
   std::stable_sort(mixes.begin(), mixes.end(), [](const MixTaskH& a, const MixTaskH& b) { return a.wave < b.wave; });
   fill_mix_tables(st, mixes);
+  {  // mix chunks per wave, behind the job counts
+    const size_t nw = st.wave_need.size();
+    st.wave_need.resize(2 * nw, 0);
+    for (const MixChunk& c : st.mc)
+      if (c.pad_ >= 0 && c.pad_ < (int)nw) st.wave_need[nw + c.pad_] += 1;
+  }
   n_gemm_tiles_tag[TAG_L] += (int)st.sjobs.size();
   if (getenv("HTN_PLAN_DEBUG")) {
     long long tiles = 0;
-    std::vector<int> per_wave(st.wave_need.size(), 0);
+    std::vector<int> per_wave(st.wave_need.size() / 2, 0);
     for (const StackJob& j : st.sjobs) {
       tiles += (j.M + 63) / 64;
       if (j.wave >= 0) per_wave[j.wave]++;
@@ -545,7 +551,7 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
         st.n_sjobs = (int)st.sjobs.size();
         if (st.sjobs.empty()) st.sjobs.push_back(StackJob{});
         if ((rc = to_device(ctx, st.sjobs, &st.d_sjobs)) || (rc = to_device(ctx, st.wave_need, &st.d_wave_need))) return rc;
-        const size_t nctr = 4 + st.wave_need.size();
+        const size_t nctr = 4 + st.wave_need.size() + 8;
         if (cudaMalloc(&st.d_ctr, nctr * sizeof(unsigned long long)) != cudaSuccess)
           return ctx->fail(HTN_ERR_OOM, "program counters allocation failed");
         cudaMemsetAsync(st.d_ctr, 0, nctr * sizeof(unsigned long long), ctx->stream);
@@ -567,10 +573,12 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
 int32_t Program::run(const double* const* slots, int mask, const unsigned char* const* slot_tmaps) const {
   Bases bs;
   for (int i = 0; i < MAX_SLOTS; ++i) bs.p[i] = i < nslots ? slots[i] : nullptr;
-  static int stack_dbg = -1;
+  static int stack_dbg = -1, mix_lag = 0;
   if (stack_dbg < 0) {
-    const char* e = getenv("HTN_STACK_DEBUG");  // timing experiments only (results are wrong when set)
+    const char* e = getenv("HTN_STACK_DEBUG");  // timing experiments only (results are wrong when bits 1, 2, 4 are set)
     stack_dbg = e ? atoi(e) : 0;
+    e = getenv("HTN_MIX_LAG");  // > 0: back-pressure on the stacked jobs (measured slower: profiles/r2_stack_mix_analysis.md)
+    if (e) mix_lag = atoi(e);
   }
   for (const Stage& st : stages) {
     if (!(st.tag & mask)) continue;
@@ -589,11 +597,26 @@ int32_t Program::run(const double* const* slots, int mask, const unsigned char* 
       a.mc = st.d_mc;
       a.nmix = (stack_dbg & 16) ? 0 : st.n;  // experiment 16: the mix as a separate launch
       a.wave_need = st.d_wave_need;
+      a.nwaves = std::max(st.nwaves, 1);
+      a.mix_lag = mix_lag;
       a.ctr = st.d_ctr;
       a.epoch = ++st.epoch;
       a.dbg = stack_dbg;
+      if (stack_dbg & 32) cudaMemsetAsync(st.d_ctr + 4 + 2 * a.nwaves, 0, 8 * sizeof(unsigned long long), ctx->stream);
       launch_stack_gemm(a, bs, st.grid, ctx->stream);
       if ((stack_dbg & 16) && st.n > 0) launch_mix(st.d_mt, st.d_ms, st.d_mc, st.n, bs, ctx->stream);
+      if (stack_dbg & 32) {  // timeline probe: when did the DMMA warps and the mixers finish?
+        unsigned long long t[8];
+        cudaMemcpyAsync(t, st.d_ctr + 4 + 2 * a.nwaves, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        static int printed = 0;
+        if (printed++ < 6)
+          fprintf(stderr,
+                  "[htn] stack timeline: jobs done at %.1f us, mix done at %.1f us after the first warp started; mixer warps: %llu chunks, "
+                  "per chunk %.0f clk ticket+record, %.0f clk wave wait, %.0f clk data\n",
+                  (t[1] - (~t[0])) * 1e-3, (t[2] - (~t[0])) * 1e-3, t[7], (double)t[4] / std::max<unsigned long long>(t[7], 1),
+                  (double)t[5] / std::max<unsigned long long>(t[7], 1), (double)t[6] / std::max<unsigned long long>(t[7], 1));
+      }
     }
   }
   cudaError_t e = cudaGetLastError();

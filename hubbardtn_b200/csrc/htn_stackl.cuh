@@ -210,6 +210,16 @@ __device__ __forceinline__ double2 sl_ld_stream(const double* p) {
   return v;
 }
 
+// streaming 16-byte store: U is written once and read next by stage R (another launch) -- keep it from pushing T out of L2
+__device__ __forceinline__ void sl_st_stream(double* p, double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned long long sl_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+
 // one mix chunk by one warp: dst[e] = sum_s coef_s src_s[e] over a flat element range (identical padded layouts)
 template <int U>
 __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk& ch, const Bases& bases, int lane) {
@@ -270,7 +280,12 @@ __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk&
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int e = e0 + 64 * u;
-        if (e < end) *reinterpret_cast<double2*>(dst + e) = acc[u];
+        if (e < end) {
+          if (nsrc <= SL_MIXSRC)
+            sl_st_stream(dst + e, acc[u]);
+          else
+            *reinterpret_cast<double2*>(dst + e) = acc[u];  // re-read by the next source batch
+        }
       }
     }
     if (nsrc == 0) break;
@@ -281,12 +296,16 @@ __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk&
 template <int U>
 __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
   const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
+  const bool prof = (a.dbg & 32) != 0;
+  long long c_desc = 0, c_wait = 0, c_work = 0, n_chunks = 0;
   while (true) {
+    const long long t0 = prof ? clock64() : 0;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned long long)a.nmix) break;
     const MixChunk ch = a.mc[tk];
+    const long long t1 = prof ? clock64() : 0;
     if (ch.pad_ >= 0) {
       if (lane == 0) {
         // wave 0 holds the jobs of the light panels (every left sector reads from them), wave pad_ the heavy ones
@@ -305,7 +324,27 @@ __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& b
       }
       __syncwarp();
     }
+    const long long t2 = prof ? clock64() : 0;
     if (!(a.dbg & 4)) sl_mix_chunk<U>(a, ch, bases, lane);
+    if (ch.pad_ >= 0) {  // this chunk's reads of T are over: the wave's mix is done when all its chunks are
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.ctr + 4 + a.nwaves + ch.pad_, 1ull);
+    }
+    if (prof) {
+      const long long t3 = clock64();
+      c_desc += t1 - t0;
+      c_wait += t2 - t1;
+      c_work += t3 - t2;
+      ++n_chunks;
+    }
+  }
+  if (prof && lane == 0) {
+    unsigned long long* d = a.ctr + 4 + 2 * a.nwaves;
+    atomicMax(d + 2, sl_globaltimer());
+    atomicAdd(d + 4, (unsigned long long)c_desc);
+    atomicAdd(d + 5, (unsigned long long)c_wait);
+    atomicAdd(d + 6, (unsigned long long)c_work);
+    atomicAdd(d + 7, (unsigned long long)n_chunks);
   }
 }
 
@@ -406,6 +445,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
         jphase ^= 1u;
       }
     }
+    if ((dbg & 32) && lane == 0) atomicMax(a.ctr + 4 + 2 * a.nwaves + 1, sl_globaltimer());
     // no stack jobs left: help with the mix (the last wave's targets are still to be formed)
     if (a.nmix > 0) sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
   } else {
@@ -413,6 +453,8 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
     if (warp == SL_NCONS) {
       // =========================== PRODUCER ===========================
       const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.njobs + (int)gridDim.x);
+      if ((dbg & 32) && lane == 0) atomicMax(a.ctr + 4 + 2 * a.nwaves, ~sl_globaltimer());  // = min start time
+      int mix_passed = 0;  // waves whose mix is known to be complete: 0 .. mix_passed - 1
       while (true) {
         unsigned long long tk = 0;
         if (lane == 0) tk = atomicAdd(a.ctr, 1ull) - base;
@@ -420,6 +462,26 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
         const bool done = tk >= (unsigned long long)a.njobs;
         StackJob job{};
         if (!done) job = a.jobs[tk];
+        if (!done && a.mix_lag > 0 && a.nmix > 0 && job.wave - a.mix_lag >= mix_passed && job.wave - a.mix_lag >= 1) {
+          // back-pressure: the T blocks of wave w - lag must have been mixed before wave w is started, so that what the
+          // mixers read is still in L2 (without it the DMMA warps run ahead and T makes a round trip through HBM)
+          const int need_wave = job.wave - a.mix_lag;
+          if (lane == 0) {
+            for (int w = mix_passed > 1 ? mix_passed : 1; w <= need_wave; ++w) {
+              const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[a.nwaves + w];
+              unsigned spins = 0;
+              while (sl_ld_acquire(a.ctr + 4 + a.nwaves + w) < need) {
+                __nanosleep(128);
+                if (++spins > (1u << 22)) {
+                  atomicAdd(a.ctr + 2, 1ull);
+                  break;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          mix_passed = need_wave + 1;
+        }
         sl_mbar_wait(&jempty[jq], jphase ^ 1u);
         int* slot = job_slot + jq * SL_JOBWORDS;
         if (done) job.M = -1;  // stop record
