@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--sym", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-groundstate", action="store_true", help="skip the time-to-converge leg")
+    ap.add_argument("--no-groundstate", action="store_true", help="skip the time-to-converge legs")
+    ap.add_argument("--no-groundstate-scale", action="store_true", help="skip the D_red=256 / 1024 time-to-converge legs")
     ap.add_argument("--shard", default="sector", choices=["sector", "site"],
                     help="N>1: 'sector' (default) = ONE apply sharded over the left symmetry sectors / MPO levels inside "
                          "libhtn (htn_plan_heff_ac_sharded) with an NCCL allreduce of y per apply, strong scaling; "
@@ -227,6 +228,82 @@ def groundstate_leg(ctx, args):
         out["cpu_port_energy_per_site"] = envs.energy_per_site
         out["cpu_port_note"] = ("oracle restatement (numpy, 1 process, python block loops), not MPSKit/Julia; at this "
                                 "size (D_full ~ 30) both sides are latency-bound, not flop-bound")
+    return out
+
+
+def groundstate_scale_leg(ctx, args, D_cap, cut, vumps_tol, vumps_maxiter, idmrg_iters, cpu_iters):
+    """BASELINE metric part 2 at a size where the GPU is not launch-bound: config C2 (one-band Hubbard with
+    next-nearest-neighbour hopping, t=[1,0.2], U=6, half filling, U1xSU2) grown by IDMRG2 to D_red <= D_cap multiplets per
+    bond, then VUMPS to `vumps_tol` -- the reference's schedule HF:993-1030 with a `truncdim`-style cap.  The CPU port
+    (oracle VUMPS, numpy, BLAS threads = all cores) runs `cpu_iters` VUMPS iterations from the SAME post-IDMRG2 state
+    (downloaded from the device): a bounded sample; its seconds per iteration sit beside the GPU's."""
+    import numpy as np
+    from hubbardtn_b200 import device as dev, hubbardfunctions as hf
+    model = hf.OB_Sim([1.0, 0.2], [6.0], 0.0, [0.0], 1, 1, 5.0)
+    H = hf.hamiltonian(model, ctx)
+    psi = hf.initialize_mps(H, model.P, model.bond_dim, model.spin, ctx)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    AL, AR, C, AC, info1 = dev.idmrg2(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=cut, tol=1e-6, maxiter=idmrg_iters, maxdim=D_cap)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], model.sym)
+    ctx.synchronize()
+    t2 = time.perf_counter()
+    psi = hf.InfiniteMPS(ctx, model.sym, AL, AR, C, AC)
+    start_AL = [t.download() for t in psi.AL]
+    start_C = psi.C[-1].download()
+    GL, GR = hf._make_envs(ctx, psi, H)
+    ctx.synchronize()
+    t3 = time.perf_counter()
+    info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=vumps_tol, maxiter=vumps_maxiter)
+    ctx.synchronize()
+    t4 = time.perf_counter()
+    log = info2["log"]
+    out = {
+        "workload": "C2: OB_Sim t=[1,0.2] u=[6] P=Q=1, U1xSU2; IDMRG2(truncbelow %.0e, cap %d multiplets, %d sweeps) -> "
+                    "InfiniteMPS gauge -> VUMPS(tol %.0e, maxiter %d)" % (cut, D_cap, idmrg_iters, vumps_tol, vumps_maxiter),
+        "D_red": [int(sum(c.space(0, model.sym).mult)) for c in psi.C], "D_full": hf.dim_state(psi),
+        "mpo_levels": H.chi,
+        "gpu_seconds": {"idmrg2": t1 - t0, "gauge": t2 - t1, "vumps": t4 - t3, "total": (t1 - t0) + (t2 - t1) + (t4 - t3)},
+        "idmrg2_phase_seconds": dict(zip(["planning", "lanczos", "svd", "env_growth"], [float(v) for v in info1["log"][-1][3:7]])),
+        "idmrg2_iterations": info1["iterations"], "idmrg2_applies": int(info1["log"][-1][2]),
+        "vumps_iterations": info2["iterations"], "vumps_converged": bool(info2["converged"]), "galerkin": info2["delta"],
+        "energy_per_site": info2["energy_per_site"],
+        "vumps_phase_seconds": {"eigensolves": float(log[:, 4].sum()), "gauge": float(log[:, 5].sum()), "environments": float(log[:, 6].sum())},
+        "vumps_applies": int(log[:, 3].sum()),
+        "gpu_seconds_per_vumps_iteration": (t4 - t3) / max(info2["iterations"], 1),
+    }
+    if not args.no_cpu and cpu_iters > 0:
+        from oracle import bridge, mps as M, sectors as OS
+        from oracle.hubbard import OB_Sim as OSim, mpo
+        from oracle.tensors import Space as OSpace
+        Ws, P, _ = mpo(OSim(t=[1.0, 0.2], u=[6.0]))
+        L = len(psi)
+        Vd = [psi.C[i].space(0, psi.sym) for i in range(L)]
+        Vo = [OSpace(OS.SU2U1, dict(zip(v.sectors, v.mult))) for v in Vd]
+        tab = lambda t: (t.labels, t.rows, t.cols, t.offsets)  # noqa: E731
+        ALo = [bridge.mps_from_packed(Vo[i - 1], P, Vo[i], tab(psi.AL[i]), start_AL[i]) for i in range(L)]
+        C0 = bridge.bond_from_packed(Vo[L - 1], tab(psi.C[L - 1]), start_C)
+        c0 = time.perf_counter()
+        ARo, Co, _ = M.uniform_rightorth(ALo, C0, tol=1e-12)
+        st = dict(AL=ALo, AR=ARo, C=Co, AC=[M.mul_right(ALo[i], Co[i]) for i in range(L)])
+        c1 = time.perf_counter()
+        _, envs, eps_c, log_c = M.vumps(st, Ws, tol=vumps_tol, maxiter=cpu_iters)
+        c2 = time.perf_counter()
+        n_c = max(len(log_c), 1)
+        out["cpu_port"] = {
+            "kind": "port", "cores": os.cpu_count(), "vumps_iterations_timed": n_c, "seconds": c2 - c1,
+            "seconds_per_vumps_iteration": (c2 - c1) / n_c, "gauge_seconds": c1 - c0,
+            "galerkin_after": eps_c, "energy_per_site_after": envs.energy_per_site,
+            "gpu_galerkin_after_same_iterations": float(log[min(n_c, len(log)) - 1, 0]),
+            "gpu_energy_after_same_iterations": float(log[min(n_c, len(log)) - 1, 1]),
+            "estimated_seconds_to_converge": (c2 - c1) / n_c * info2["iterations"],
+            "note": "oracle restatement (numpy/OpenBLAS with all cores, python block loops), NOT MPSKit/Julia; bounded sample: "
+                    "%d VUMPS iterations from the GPU arm's post-IDMRG2 state; the estimate assumes the GPU arm's iteration "
+                    "count" % n_c,
+        }
+        out["vumps_iteration_speedup_vs_cpu_port"] = out["cpu_port"]["seconds_per_vumps_iteration"] / out["gpu_seconds_per_vumps_iteration"]
     return out
 
 
@@ -464,6 +541,12 @@ def main():
     gs = None
     if rank == 0 and world == 1 and not args.no_groundstate:
         gs = groundstate_leg(ctx, args)
+        if not args.no_groundstate_scale:
+            # C2 at D_red <= 256 to a Galerkin error of 1e-10, CPU port beside it for 2 VUMPS iterations
+            gs["C2_D256"] = groundstate_scale_leg(ctx, args, 256, 1e-9, 1e-10, 300, 30, 2)
+            # the same model at D_red <= 1024: per-phase seconds where the contractions dominate (GPU only: one CPU-port
+            # iteration at this size takes minutes)
+            gs["C2_D1024"] = groundstate_scale_leg(ctx, args, 1024, 1e-11, 1e-10, 20, 10, 0)
 
     line = None
     if rank == 0:
@@ -490,7 +573,15 @@ def main():
                 "bound": "tensor", "kernel": "stack_gemm_kernel (stage L, the stage-W mix rides along) + grouped_gemm_kernel (stage R)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": traffic_note,
-                "algorithmic_flop_per_launch": st["flops"] / 2.0,
+                "launches": [
+                    {"kernel": "stack_gemm_kernel (stage L: T = GL.x, the stage-W recoupling mix fused in)",
+                     "algorithmic_flop": st["flops_L"], "ms": prof["stage_L_ms"],
+                     "tflops": st["flops_L"] / (prof["stage_L_ms"] * 1e-3) / 1e12,
+                     "frac": st["flops_L"] / (prof["stage_L_ms"] * 1e-3) / 1e12 / peak},
+                    {"kernel": "grouped_gemm_kernel (stage R: y = U.GR, split-K)",
+                     "algorithmic_flop": st["flops_R"], "ms": prof["stage_R_ms"],
+                     "tflops": st["flops_R"] / (prof["stage_R_ms"] * 1e-3) / 1e12,
+                     "frac": st["flops_R"] / (prof["stage_R_ms"] * 1e-3) / 1e12 / peak}],
                 "peak_source": "peak measured by this repo's probe, live on this GPU: max(DMMA.8x8x4 issue loop %.2f, DFMA loop "
                                "%.2f, cuBLAS DGEMM 8192^3 %.2f) TFLOP/s; MEASURED_PEAKS.json has no FP64 entry "
                                "(profiles/fp64_peak.json holds the committed probe run)" % (dmma_peak, dfma_peak, cublas_peak),

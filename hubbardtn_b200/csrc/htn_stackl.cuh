@@ -292,20 +292,21 @@ __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk&
   }
 }
 
-// mixer loop: mix chunks by ticket, each after the wave of stack jobs it reads from is complete
-template <int U>
-__device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
+// mixer loop: mix chunks by ticket, each after the wave of stack jobs it reads from is complete.
+// PROF (HTN_STACK_DEBUG & 32, a separate instantiation so that the product loop carries none of it): clocks spent per
+// chunk on ticket + record, on the wave wait and on the data, summed into the probe slots behind the wave counters.
+template <int U, bool PROF>
+__device__ __forceinline__ void sl_mixer_loop_t(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
   const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
-  const bool prof = (a.dbg & 32) != 0;
   long long c_desc = 0, c_wait = 0, c_work = 0, n_chunks = 0;
   while (true) {
-    const long long t0 = prof ? clock64() : 0;
+    const long long t0 = PROF ? clock64() : 0;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned long long)a.nmix) break;
     const MixChunk ch = a.mc[tk];
-    const long long t1 = prof ? clock64() : 0;
+    const long long t1 = PROF ? clock64() : 0;
     if (ch.pad_ >= 0) {
       if (lane == 0) {
         // wave 0 holds the jobs of the light panels (every left sector reads from them), wave pad_ the heavy ones
@@ -324,13 +325,13 @@ __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& b
       }
       __syncwarp();
     }
-    const long long t2 = prof ? clock64() : 0;
+    const long long t2 = PROF ? clock64() : 0;
     if (!(a.dbg & 4)) sl_mix_chunk<U>(a, ch, bases, lane);
-    if (ch.pad_ >= 0) {  // this chunk's reads of T are over: the wave's mix is done when all its chunks are
+    if (a.mix_lag > 0 && ch.pad_ >= 0) {  // back-pressure experiments: count the finished chunks of the wave
       __syncwarp();
       if (lane == 0) atomicAdd(a.ctr + 4 + a.nwaves + ch.pad_, 1ull);
     }
-    if (prof) {
+    if (PROF) {
       const long long t3 = clock64();
       c_desc += t1 - t0;
       c_wait += t2 - t1;
@@ -338,7 +339,7 @@ __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& b
       ++n_chunks;
     }
   }
-  if (prof && lane == 0) {
+  if (PROF && lane == 0) {
     unsigned long long* d = a.ctr + 4 + 2 * a.nwaves;
     atomicMax(d + 2, sl_globaltimer());
     atomicAdd(d + 4, (unsigned long long)c_desc);
@@ -346,6 +347,17 @@ __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& b
     atomicAdd(d + 6, (unsigned long long)c_work);
     atomicAdd(d + 7, (unsigned long long)n_chunks);
   }
+}
+template <int U>
+__device__ __forceinline__ void sl_mixer_loop_prof(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
+  sl_mixer_loop_t<U, true>(a, bases, lane, nwarps_total);
+}
+template <int U>
+__device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
+  if (a.dbg & 32)
+    sl_mixer_loop_prof<U>(a, bases, lane, nwarps_total);
+  else
+    sl_mixer_loop_t<U, false>(a, bases, lane, nwarps_total);
 }
 
 // Roles: warps 0 .. SL_NCONS-1 = consumers (DMMA; they also load the slab of a job themselves, all 128 threads,
