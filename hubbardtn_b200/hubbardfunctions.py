@@ -429,8 +429,9 @@ def _full_rank(sym, spaces, phys):
 class InfiniteMPS:
     """Uniform MPS in mixed gauge, resident on the device: AL, AR, AC, C (C[i] right of site i)."""
 
-    def __init__(self, ctx, sym, AL, AR, C, AC):
+    def __init__(self, ctx, sym, AL, AR, C, AC, phys=None):
         self.ctx, self.sym, self.AL, self.AR, self.C, self.AC = ctx, sym, AL, AR, C, AC
+        self.phys = list(phys) if phys is not None else None      # physical multiplets (sector labels), needed by save_state
 
     def __len__(self):
         return len(self.AL)
@@ -460,7 +461,7 @@ def initialize_mps(H: Hamiltonian, P: int, max_dimension: int, spin: bool = Fals
         blk[...] = np.eye(blk.shape[0]) + 0.1 * rng.standard_normal(blk.shape)
     guess.upload(g)
     dev.mixed_gauge(ctx, AL, guess, AR, C, AC, tol=1e-12)
-    return InfiniteMPS(ctx, sym, AL, AR, C, AC)
+    return InfiniteMPS(ctx, sym, AL, AR, C, AC, H.phys)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -491,7 +492,7 @@ def compute_groundstate(simul: OB_Sim, ctx=None, tol: float = 1e-6, verbosity: i
     AL, AR, C, AC, info1 = dev.idmrg2(ctx, start[0], start[1], start[2], start[3], H.W, cut=schmidtcut, tol=tol,
                                       maxiter=min(maxiter, 200))           # HF:1010 (MPSKit default maxiter 200)
     AL, AR, C, AC = dev.uniform_from_right(ctx, AR, C[-1], simul.sym)      # MPSKit: InfiniteMPS(psi.AR) at the end of IDMRG2
-    psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC)
+    psi = InfiniteMPS(ctx, simul.sym, AL, AR, C, AC, H.phys)
     GL, GR = _make_envs(ctx, psi, H)
     info2 = dev.vumps(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, GL, GR, tol=tol, maxiter=min(maxiter, 1000))  # HF:1025-1027
     # ... & GradientGrassmann(; maxiter, tol): MPSKit runs both stages; the second returns at once when tol is already met
@@ -547,7 +548,7 @@ def TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, **kw):
         else:
             AL, AR, C, AC, _, _ = dev.changebonds_vumpssvdcut(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, H.P, psi.sym,
                                                               maxdim=cap)
-        return InfiniteMPS(ctx, psi.sym, AL, AR, C, AC)
+        return InfiniteMPS(ctx, psi.sym, AL, AR, C, AC, psi.phys)
 
     # multiplets are kept largest-first; find the largest multiplet count whose full dimension fits
     best = None
@@ -574,6 +575,69 @@ def produce_TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, force: bool
     GL, GR = _make_envs(d["ctx"], psi, d["ham"])
     dev.environments(d["ctx"], psi.AL, psi.AR, psi.C, d["ham"].W, GL, GR, tol=1e-10)
     return {"ψ_trunc": psi, "psi_trunc": psi, "envs_trunc": (GL, GR)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# state I/O (HF:1669-1691)
+# ---------------------------------------------------------------------------------------------------
+STATE_FORMAT = "hubbardtn-b200/state-v1"
+
+
+def save_state(psi: InfiniteMPS, path: str, name: str):
+    """HF:1669-1677: one file per site under `path/name/` holding the left isometry AL[i] as a plain dictionary --
+    the reference stores `convert(Dict, psi.AL[i])` in `state$i.jld2`; here `state{i}.npz` (1-based like the
+    reference) with the symmetry, the three graded spaces (sector labels (p, q, n) and multiplicities), the block
+    table (labels, rows, cols, offsets of the packed row-major blocks in canonical order) and the data.  JLD2/HDF5
+    cannot be written from this image; INTEGRATION.md shows the NPZ.jl reader that turns a file back into a
+    TensorMap."""
+    import os
+    d = os.path.join(path, name)
+    os.mkdir(d)                                                   # like the reference: fails if the state exists
+    if psi.phys is None:
+        raise ValueError("save_state: the state does not carry its physical space (InfiniteMPS(..., phys=...))")
+    phys = psi.phys
+    for i in range(len(psi)):
+        A = psi.AL[i]
+        vl, vr = A.space(0, psi.sym), A.space(1, psi.sym)
+        np.savez(os.path.join(d, "state%d.npz" % (i + 1)), format=STATE_FORMAT, sym=psi.sym,
+                 left_sectors=np.array(vl.sectors, dtype=np.int32).reshape(-1, 3), left_mult=np.array(vl.mult, dtype=np.int32),
+                 right_sectors=np.array(vr.sectors, dtype=np.int32).reshape(-1, 3), right_mult=np.array(vr.mult, dtype=np.int32),
+                 phys_sectors=np.array(phys, dtype=np.int32).reshape(-1, 3),
+                 labels=A.labels, rows=A.rows, cols=A.cols, offsets=A.offsets, data=A.download())
+        print("State %d saved." % (i + 1))
+
+
+def load_state(path: str, ctx=None, tol: float = 1e-12):
+    """HF:1679-1691: reads `state1 .. stateN` and rebuilds the uniform MPS from the left isometries
+    (`InfiniteMPS(PeriodicArray(A))`: gauge fixing on the device)."""
+    import os
+    files = sorted((f for f in os.listdir(path) if os.path.isfile(os.path.join(path, f)) and f.startswith("state")),
+                   key=lambda f: int("".join(ch for ch in f if ch.isdigit())))
+    if not files:
+        raise FileNotFoundError("no state files under %s" % path)
+    if ctx is None:
+        ctx = dev.Context(0)
+    AL, sym = [], None
+    for f in files:
+        z = np.load(os.path.join(path, f))
+        if str(z["format"]) != STATE_FORMAT:
+            raise ValueError("%s: unknown state format %r" % (f, str(z["format"])))
+        sym = int(z["sym"])
+        Vl = dev.Space(ctx, sym, {tuple(int(v) for v in s): int(m) for s, m in zip(z["left_sectors"], z["left_mult"])})
+        Vr = dev.Space(ctx, sym, {tuple(int(v) for v in s): int(m) for s, m in zip(z["right_sectors"], z["right_mult"])})
+        P = dev.Legs(ctx, sym, [tuple(int(v) for v in s) for s in z["phys_sectors"]])
+        A = dev.Tensor.mps(ctx, Vl, P, Vr)
+        if not (np.array_equal(A.labels, z["labels"]) and np.array_equal(A.rows, z["rows"]) and np.array_equal(A.cols, z["cols"])
+                and np.array_equal(A.offsets, z["offsets"])):
+            raise ValueError("%s: block table differs from the canonical one of its spaces" % f)
+        A.upload(np.ascontiguousarray(z["data"], dtype=np.float64))
+        AL.append(A)
+    n = len(AL)
+    AR = [a.like() for a in AL]
+    AC = [a.like() for a in AL]
+    Cs = [dev.Tensor.bond(ctx, AL[i].space(1, sym)) for i in range(n)]
+    dev.mixed_gauge(ctx, AL, dev._identity_bond(ctx, AL[n - 1].space(1, sym)), AR, Cs, AC, tol=tol)
+    return InfiniteMPS(ctx, sym, AL, AR, Cs, AC, [tuple(int(v) for v in s) for s in z["phys_sectors"]])
 
 
 def dim_state(psi: InfiniteMPS):
