@@ -111,6 +111,7 @@ SIGNATURES = {
     "htn_idmrg2": (_i32, [_p, _i32, _pp, _pp, _pp, _pp, _pp, C.c_double, C.c_double, _i32, _i32, C.c_double, _i32, _pd,
                           _pi32, _pd, _i32]),
     "htn_mixed_gauge": (_i32, [_p, _i32, _pp, _p, _pp, _pp, _pp, _i32, C.c_double, _i32, _pi32]),
+    "htn_changebonds": (_i32, [_p, _i32, _i32, _pp, _pp, _pp, _pp, _pp, C.c_double, _i32, _i32, C.c_double, C.c_double]),
     "htn_gauge_left": (_i32, [_p, _i32, _pp, _p, _pp, _pp, C.c_double, _i32, _pi32, _pd]),
     "htn_heff_apply": (_i32, [_p, _p, _p]),
     "htn_heff_apply_host": (_i32, [_p, _p, _p, _i64]),

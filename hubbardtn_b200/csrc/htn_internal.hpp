@@ -201,7 +201,9 @@ struct StackJob {
   int M;    // rows of the run (tiles of 64)
   int tmap; // >= 0: A is read through the 2-D tensor map tmaps[tmap] (TMA), rows arow .. arow + M of that panel
   int arow;
-  int wave; // host scheduling only
+  int wave; // >= 0: one arrival per consumer warp on that wave's counter when the job is done; < 0: tile-level (tile0)
+  int tile0; // first entry of this job's tiles in StackArgs::tile_waves
+  int pad_;
 };
 constexpr int STACK_SLAB_ELEMS = 10080;
 inline bool stack_job_fits(int K, int nt) { return ((K + 3) & ~3) * (((nt + 7) & ~7) + 4) <= STACK_SLAB_ELEMS && nt <= 64; }
@@ -221,6 +223,14 @@ struct MixTarget {
 struct MixChunk {
   int target, elem0, nelem, pad_;  // pad_: wave the chunk waits for in the fused stage (-1: none)
 };
+// self-contained chunk record of the fused stage (one 32-byte load instead of chunk -> target): same order as MixChunk
+struct MixChunkX {
+  long long off;  // destination block
+  int base;
+  int src_begin, nsrc;
+  int elem0, nelem;
+  int wave;
+};
 
 // Arguments of the fused stage L + W launch.  Counters (64-bit, never reset: `epoch` = 1-based launch number):
 //   ctr[0] job ticket, ctr[1] mix ticket, ctr[2] watchdog flag, ctr[4 + w] consumer-warp arrivals of wave w,
@@ -233,18 +243,23 @@ struct StackArgs {
   const MixTarget* mt;
   const MixSrc* ms;
   const MixChunk* mc;  // sorted by wave; pad_ = wave the chunk waits for (-1: none)
+  const MixChunkX* mcx;
   int nmix;
+  const int2* tile_waves;  // per tile of the tile-level jobs: first and last wave it reports to
   const int* wave_need;  // [w]: arrivals that complete wave w (= SL_NCONS * jobs of the wave); [nwaves + w]: mix chunks of wave w
   int nwaves;
   int mix_lag;           // > 0: the jobs of wave w are held back until the mix of wave w - mix_lag is done (T stays in L2)
   unsigned long long* ctr;
   unsigned long long epoch;
   int dbg;
+  unsigned long long* dbg_ts;  // HTN_STACK_DEBUG & 32: per mix chunk (start, end) globaltimer stamps
 };
 
 void launch_stack_gemm(const StackArgs& args, const Bases& bases, int grid, cudaStream_t st);
 
 int stack_gemm_ctas_per_sm();
+int stack_gemm_groups();      // consumer groups per CTA (HTN_STACK_NG)
+int stack_gemm_cons_warps();  // consumer warps per CTA: arrivals per job on the wave counters
 
 void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const Bases& bases, int grid,
                  cudaStream_t st);

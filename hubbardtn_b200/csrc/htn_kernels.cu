@@ -507,23 +507,40 @@ void launch_gemm(const GemmItem* items, const GemmSeg* segs, int nitems, const B
 // ------------------------------------------------------------------------------------
 // stacked stage L with the mix riding along (htn_stackl.cuh)
 // ------------------------------------------------------------------------------------
+// consumer groups per CTA of the stacked kernel: 1 (two CTAs per SM) or 2 (one CTA per SM, shared slab); HTN_STACK_NG
+int stack_gemm_groups() {
+  static int ng = -1;
+  if (ng < 0) {
+    const char* e = getenv("HTN_STACK_NG");
+    ng = e ? atoi(e) : 1;
+    if (ng != 2) ng = 1;
+  }
+  return ng;
+}
+
+int stack_gemm_cons_warps() { return stack_gemm_groups() == 2 ? SlCfg<2>::NCONS : SlCfg<1>::NCONS; }
+
+template <int NG>
+static int stack_occupancy() {
+  cudaFuncSetAttribute(stack_gemm_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SlCfg<NG>::SMEM_BYTES);
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stack_gemm_kernel<NG>, SlCfg<NG>::THREADS, SlCfg<NG>::SMEM_BYTES);
+  return n > 0 ? n : 1;
+}
+
 int stack_gemm_ctas_per_sm() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  cudaFuncSetAttribute(stack_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES);
-  int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stack_gemm_kernel, SL_THREADS, SL_SMEM_BYTES);
-  cached = n > 0 ? n : 1;
+  cached = stack_gemm_groups() == 2 ? stack_occupancy<2>() : stack_occupancy<1>();
   return cached;
 }
 
 void launch_stack_gemm(const StackArgs& args, const Bases& bases, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(stack_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES);
-    attr = true;
-  }
-  stack_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, st>>>(args, bases);
+  stack_gemm_ctas_per_sm();  // sets the shared-memory attribute of the chosen instantiation once
+  if (stack_gemm_groups() == 2)
+    stack_gemm_kernel<2><<<grid, SlCfg<2>::THREADS, SlCfg<2>::SMEM_BYTES, st>>>(args, bases);
+  else
+    stack_gemm_kernel<1><<<grid, SlCfg<1>::THREADS, SlCfg<1>::SMEM_BYTES, st>>>(args, bases);
 }
 
 // ------------------------------------------------------------------------------------

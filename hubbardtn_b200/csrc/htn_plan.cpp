@@ -89,6 +89,8 @@ static int stack_max_atoms(int K) {
   return std::min(at, 7);
 }
 
+static int tile_waves_mode = 0;
+
 static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView& GL,
                              const std::map<HTerm, double>& terms, int slot_x, int slot_gl, bool allow_stack = false) {
   LeftFront F;
@@ -139,27 +141,62 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
     std::vector<double> bytes(nlp, 0.0);
     for (size_t ti = 0; ti < tkeys.size(); ++ti)
       if (is_stacked[ti] && !light_panel(std::get<2>(tkeys[ti]))) bytes[std::get<1>(tkeys[ti])] += 8.0 * tb[ti].rows * tb[ti].ld;
-    static double wave_mb = -1.0;
+    static double wave_mb = -1.0, wave_taper = 1.0;
     if (wave_mb < 0) {
       const char* e = getenv("HTN_WAVE_MB");
       wave_mb = e ? atof(e) : 48.0;
+      e = getenv("HTN_WAVE_TAPER");  // < 1: every wave holds this fraction of the bytes of the one before (short tail)
+      if (e) wave_taper = atof(e);
     }
     std::vector<int> order;
     for (int lp = 0; lp < nlp; ++lp)
       if (bytes[lp] > 0) order.push_back(lp);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bytes[x] > bytes[y]; });
-    double acc = 0.0;
+    static int wave_order = -1;
+    if (wave_order < 0) {
+      const char* e = getenv("HTN_WAVE_ORDER");  // 1: waves = consecutive left sectors (contiguous panel rows), 0: heavy sectors first
+      wave_order = e ? atoi(e) : 0;
+      e = getenv("HTN_TILE_WAVES");  // 1: jobs span waves, completion is reported tile by tile (implies HTN_WAVE_ORDER=1)
+      tile_waves_mode = e ? atoi(e) : 0;
+      if (tile_waves_mode) wave_order = 1;
+    }
+    if (!wave_order) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bytes[x] > bytes[y]; });
+    // the LAST wave is kept small (its mix cannot hide behind any DMMA work): the lightest sectors up to tail_mb
+    static double tail_mb = -1.0;
+    if (tail_mb < 0) {
+      const char* e = getenv("HTN_WAVE_TAIL_MB");
+      tail_mb = e ? atof(e) : 0.0;
+    }
+    size_t ntail = 0;
+    if (tail_mb > 0 && !wave_order) {
+      double t = 0.0;
+      while (ntail + 1 < order.size() && t + bytes[order[order.size() - 1 - ntail]] <= tail_mb * 1e6) {
+        t += bytes[order[order.size() - 1 - ntail]];
+        ++ntail;
+      }
+    }
+    double acc = 0.0, cap = wave_mb * 1e6;
     int w = 1;
-    for (int lp : order) {
-      if (acc > 0 && acc + bytes[lp] > wave_mb * 1e6) {
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+      const int lp = order[oi];
+      if (acc > 0 && (acc + bytes[lp] > cap || (ntail > 0 && oi == order.size() - ntail))) {
         ++w;
         acc = 0.0;
+        cap = std::max(cap * wave_taper, 2e6);
       }
       F.wave_of_lp[lp] = w;
       acc += bytes[lp];
     }
     F.nwaves = w + 1;
     F.stacked = true;
+    if (tile_waves_mode) {  // sectors without heavy T ride with the wave of their predecessor: waves stay monotone in lp
+      int cur = 1;
+      for (int lp = 0; lp < nlp; ++lp) {
+        if (bytes[lp] > 0)
+          cur = F.wave_of_lp[lp];
+        else
+          F.wave_of_lp[lp] = cur;
+      }
+    }
   }
   // ---- stacked T arrays and jobs ----
   for (auto& kv : by_xi) {
@@ -190,8 +227,9 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
       size_t j = i;
       int r0 = rows[i].prow, r1 = rows[i].prow + rows[i].rows;
       const bool light = light_panel(l);
-      const int wave = light ? 0 : F.wave_of_lp[rows[i].lp];
-      while (j + 1 < rows.size() && (light || (F.wave_of_lp[rows[j + 1].lp] == wave && rows[j + 1].prow - r1 < 32))) {
+      const bool by_tile = tile_waves_mode && !light;
+      const int wave = light ? 0 : (by_tile ? -1 : F.wave_of_lp[rows[i].lp]);
+      while (j + 1 < rows.size() && (light || ((by_tile || F.wave_of_lp[rows[j + 1].lp] == wave) && rows[j + 1].prow - r1 < 32))) {
         ++j;
         r1 = rows[j].prow + rows[j].rows;
       }
@@ -203,15 +241,24 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
         // mixers, smaller ones pay a slab reload each; HTN_STACK_FALL=1 cuts the end of every run finer)
         int m0 = r0;
         while (m0 < r1) {
-          static int tpj = -1, fall = -1;
+          static int tpj = -1, fall = -1, tpj_tail = -1, tail_waves = 2, tpj_head = -1;
           if (tpj < 0) {
             const char* e = getenv("HTN_STACK_TPJ");  // tiles per job (tuning)
-            tpj = e ? std::max(1, atoi(e)) : 6;
+            tpj = e ? std::max(1, atoi(e)) : 6 * stack_gemm_groups();
             e = getenv("HTN_STACK_FALL");
             fall = e ? atoi(e) : 0;
+            // a wave is complete one job duration after its last job was drawn: short jobs in the last waves bring the
+            // end of the mix closer to the end of the DMMA work
+            e = getenv("HTN_STACK_TPJ_TAIL");
+            tpj_tail = e ? std::max(1, atoi(e)) : tpj;
+            e = getenv("HTN_STACK_TAIL_WAVES");
+            if (e) tail_waves = atoi(e);
+            e = getenv("HTN_STACK_TPJ_HEAD");  // jobs of the first heavy wave: the mixers cannot start before it is complete
+            tpj_head = e ? std::max(1, atoi(e)) : tpj;
           }
           const int rem_tiles = (r1 - m0 + 63) / 64;
-          const int tiles = fall ? std::max(1, std::min(tpj, (rem_tiles + 2) / 3)) : tpj;
+          const int tpj_w = (light || by_tile) ? tpj : (wave <= 1 ? tpj_head : (wave >= F.nwaves - tail_waves ? tpj_tail : tpj));
+          const int tiles = fall ? std::max(1, std::min(tpj_w, (rem_tiles + 2) / 3)) : tpj_w;
           const int M = std::min(tiles * 64, r1 - m0);
           StackJobH jb{};
           jb.A = Opnd{slot_gl, pn.off + (int64_t)m0 * pn.ld};
@@ -227,6 +274,18 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
           jb.tmap = G->d_tmaps ? l : -1;
           jb.arow = m0;
           jb.wave = wave;
+          if (by_tile) {  // waves of the T blocks under every 64-row tile of the job (rows i .. j of `rows`, sorted by prow)
+            for (int t0 = m0; t0 < m0 + M; t0 += 64) {
+              int lo = INT32_MAX, hi = -1;
+              for (size_t q = i; q <= j; ++q)
+                if (rows[q].prow < t0 + 64 && rows[q].prow + rows[q].rows > t0) {
+                  lo = std::min(lo, F.wave_of_lp[rows[q].lp]);
+                  hi = std::max(hi, F.wave_of_lp[rows[q].lp]);
+                }
+              if (hi < 0) lo = 0;  // a tile of gap rows only
+              jb.tw.push_back({lo, hi});
+            }
+          }
           F.jobs.push_back(jb);
           m0 += M;
         }
@@ -457,15 +516,26 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     tasksR[yi].segs.push_back(GemmSegH{Opnd{SLOT_WS, w.off}, w.ld, Opnd{3, gr.off}, gr.ld, gr.rows});
     ++n_u;
   }
+  // direct (identity right level) contributions: ~60 sources per y block.  A mix chunk is one warp's serial chain over
+  // its sources, so the list is cut into partial sums of <= Y0_GROUP sources; the final reduce of stage R adds them up.
+  static int y0_group = -1;
+  if (y0_group < 0) {
+    const char* e = getenv("HTN_Y0_GROUP");
+    y0_group = e ? std::max(1, atoi(e)) : 16;
+  }
   for (auto& kv : y0) {
     const Block& yb = like->blocks[kv.first];
-    MixTaskH& t = kv.second;
-    const int64_t off = pg.ws_alloc((int64_t)yb.rows * yb.ld);
-    t.dst = Opnd{SLOT_WS, off};
-    t.nelem = yb.rows * yb.ld;
-    t.wave = F.wave_of_lp[yb.lab[0]];
-    yextra[kv.first].push_back(MixSrcH{t.dst, 1.0});
-    mixU.push_back(std::move(t));
+    MixTaskH& all = kv.second;
+    for (size_t s0 = 0; s0 < all.srcs.size(); s0 += (size_t)y0_group) {
+      MixTaskH t;
+      t.srcs.assign(all.srcs.begin() + s0, all.srcs.begin() + std::min(all.srcs.size(), s0 + (size_t)y0_group));
+      const int64_t off = pg.ws_alloc((int64_t)yb.rows * yb.ld);
+      t.dst = Opnd{SLOT_WS, off};
+      t.nelem = yb.rows * yb.ld;
+      t.wave = F.wave_of_lp[yb.lab[0]];
+      yextra[kv.first].push_back(MixSrcH{t.dst, 1.0});
+      mixU.push_back(std::move(t));
+    }
   }
   *n_mix_t = (int)(mixU.size() + like->blocks.size());
   if (F.stacked) {

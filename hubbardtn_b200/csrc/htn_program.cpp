@@ -274,8 +274,9 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
   auto cost = [](const StackJobH& j) {
     return (double)((j.M + 63) / 64) * (((j.K + 15) / 16) * (((j.nt + 7) / 8) + 0.75) + 6.0) + 20.0;
   };
+  auto first_wave = [](const StackJobH& j) { return j.wave >= 0 ? j.wave : (j.tw.empty() ? 0 : j.tw.front().first); };
   std::stable_sort(jobs.begin(), jobs.end(), [&](const StackJobH& a, const StackJobH& b) {
-    if (a.wave != b.wave) return a.wave < b.wave;
+    if (first_wave(a) != first_wave(b)) return first_wave(a) < first_wave(b);
     return cost(a) > cost(b);
   });
   for (const StackJobH& j : jobs) {
@@ -293,11 +294,30 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
     d.tmap = j.tmap;
     d.arow = j.arow;
     d.wave = j.wave;
+    d.tile0 = -1;
+    if (j.wave < 0) {
+      d.tile0 = (int)st.tile_waves.size();
+      for (auto& pr : j.tw) {
+        st.tile_waves.push_back(make_int2(pr.first, pr.second));
+        for (int w = pr.first; w <= pr.second; ++w)
+          if (w >= 0 && w < (int)st.wave_need.size()) st.wave_need[w] += 4;  // the four warps of the group that computes the tile
+      }
+    }
     st.sjobs.push_back(d);
-    if (j.wave >= 0 && j.wave < (int)st.wave_need.size()) st.wave_need[j.wave] += 4;  // SL_NCONS consumer warps signal per job
+    if (j.wave >= 0 && j.wave < (int)st.wave_need.size()) st.wave_need[j.wave] += stack_gemm_cons_warps();  // every consumer warp signals per job
     padded_flops += 2.0 * ((j.M + 7) / 8 * 8) * ((j.nt + 7) / 8 * 8) * ((j.K + 3) / 4 * 4.0);
   }
-  std::stable_sort(mixes.begin(), mixes.end(), [](const MixTaskH& a, const MixTaskH& b) { return a.wave < b.wave; });
+  // ticket order of the mix: wave by wave; inside a wave the targets with the longest source lists first (a chunk is one
+  // warp's serial chain of source pieces: the direct-y targets with ~60 sources must not be the last tickets of a wave)
+  static int mix_lpt = -1;
+  if (mix_lpt < 0) {
+    const char* e = getenv("HTN_MIX_LPT");
+    mix_lpt = e ? atoi(e) : 1;
+  }
+  std::stable_sort(mixes.begin(), mixes.end(), [](const MixTaskH& a, const MixTaskH& b) {
+    if (a.wave != b.wave) return a.wave < b.wave;
+    return mix_lpt ? a.srcs.size() > b.srcs.size() : false;
+  });
   fill_mix_tables(st, mixes);
   {  // mix chunks per wave, behind the job counts
     const size_t nw = st.wave_need.size();
@@ -311,7 +331,7 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
     std::vector<int> per_wave(st.wave_need.size() / 2, 0);
     for (const StackJob& j : st.sjobs) {
       tiles += (j.M + 63) / 64;
-      if (j.wave >= 0) per_wave[j.wave]++;
+      if (j.wave >= 0 && j.wave < (int)per_wave.size()) per_wave[j.wave]++;
     }
     fprintf(stderr, "[htn] stacked stage: %zu jobs, %lld tiles, %d waves, %zu mix targets, %zu mix chunks; jobs per wave:", st.sjobs.size(),
             tiles, st.nwaves, st.mt.size(), st.mc.size());
@@ -322,6 +342,13 @@ void Program::add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mix
 }
 
 static void fill_mix_tables(Stage& st, const std::vector<MixTaskH>& tasks) {
+  int last_wave = -1;
+  for (const MixTaskH& t : tasks) last_wave = std::max(last_wave, t.wave);
+  static int tail_div = -1;
+  if (tail_div < 0) {
+    const char* e = getenv("HTN_MIX_TAIL_DIV");  // chunks of the last wave are this many times smaller (they run with nothing to hide behind)
+    tail_div = e ? std::max(1, atoi(e)) : 1;
+  }
   for (const MixTaskH& t : tasks) {
     if (t.nelem <= 0) continue;
     MixTarget mt{};
@@ -339,6 +366,7 @@ static void fill_mix_tables(Stage& st, const std::vector<MixTaskH>& tasks) {
     st.mt.push_back(mt);
     // ~16k element-sources per CTA, chunk a multiple of 512 elements (256 threads x double2)
     int per = 16384 / std::max<int>(1, (int)t.srcs.size());
+    if (st.kind == 2 && last_wave > 0 && t.wave == last_wave) per /= tail_div;
     per = std::max(512, std::min(8192, per / 512 * 512));
     for (int e = 0; e < t.nelem; e += per) st.mc.push_back(MixChunk{ti, e, std::min(per, t.nelem - e), t.wave});
   }
@@ -541,6 +569,14 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
       if ((rc = to_device(ctx, st.mt, &st.d_mt)) || (rc = to_device(ctx, st.ms, &st.d_ms)) ||
           (rc = to_device(ctx, st.mc, &st.d_mc)))
         return rc;
+      if (st.kind == 2) {
+        std::vector<MixChunkX> mcx;
+        for (const MixChunk& c : st.mc) {
+          const MixTarget& t = st.mt[c.target];
+          mcx.push_back(MixChunkX{t.off, t.base, t.src_begin, t.src_end - t.src_begin, c.elem0, c.nelem, c.pad_});
+        }
+        if ((rc = to_device(ctx, mcx, &st.d_mcx))) return rc;
+      }
       if (st.kind == 1) st.n = (int)st.mc.size();
       if (st.kind == 2) {
         for (StackJob& j : st.sjobs) {
@@ -550,7 +586,10 @@ int32_t Program::finalize(htn_ctx* c, int nslots_) {
         }
         st.n_sjobs = (int)st.sjobs.size();
         if (st.sjobs.empty()) st.sjobs.push_back(StackJob{});
-        if ((rc = to_device(ctx, st.sjobs, &st.d_sjobs)) || (rc = to_device(ctx, st.wave_need, &st.d_wave_need))) return rc;
+        if (st.tile_waves.empty()) st.tile_waves.push_back(make_int2(0, -1));
+        if ((rc = to_device(ctx, st.sjobs, &st.d_sjobs)) || (rc = to_device(ctx, st.wave_need, &st.d_wave_need)) ||
+            (rc = to_device(ctx, st.tile_waves, &st.d_tile_waves)))
+          return rc;
         const size_t nctr = 4 + st.wave_need.size() + 8;
         if (cudaMalloc(&st.d_ctr, nctr * sizeof(unsigned long long)) != cudaSuccess)
           return ctx->fail(HTN_ERR_OOM, "program counters allocation failed");
@@ -595,14 +634,27 @@ int32_t Program::run(const double* const* slots, int mask, const unsigned char* 
       a.mt = st.d_mt;
       a.ms = st.d_ms;
       a.mc = st.d_mc;
+      a.mcx = st.d_mcx;
       a.nmix = (stack_dbg & 16) ? 0 : st.n;  // experiment 16: the mix as a separate launch
       a.wave_need = st.d_wave_need;
+      a.tile_waves = st.d_tile_waves;
       a.nwaves = std::max(st.nwaves, 1);
       a.mix_lag = mix_lag;
       a.ctr = st.d_ctr;
       a.epoch = ++st.epoch;
       a.dbg = stack_dbg;
-      if (stack_dbg & 32) cudaMemsetAsync(st.d_ctr + 4 + 2 * a.nwaves, 0, 8 * sizeof(unsigned long long), ctx->stream);
+      static unsigned long long* d_ts = nullptr;
+      static int ts_cap = 0;
+      if (stack_dbg & 32) {
+        cudaMemsetAsync(st.d_ctr + 4 + 2 * a.nwaves, 0, 8 * sizeof(unsigned long long), ctx->stream);
+        if (ts_cap < st.n) {
+          cudaFree(d_ts);
+          cudaMalloc(&d_ts, ((size_t)2 * st.n + 256) * sizeof(unsigned long long));
+          ts_cap = st.n;
+        }
+        cudaMemsetAsync(d_ts, 0, ((size_t)2 * st.n + 256) * sizeof(unsigned long long), ctx->stream);
+        a.dbg_ts = d_ts;
+      }
       launch_stack_gemm(a, bs, st.grid, ctx->stream);
       if ((stack_dbg & 16) && st.n > 0) launch_mix(st.d_mt, st.d_ms, st.d_mc, st.n, bs, ctx->stream);
       if (stack_dbg & 32) {  // timeline probe: when did the DMMA warps and the mixers finish?
@@ -610,11 +662,43 @@ int32_t Program::run(const double* const* slots, int mask, const unsigned char* 
         cudaMemcpyAsync(t, st.d_ctr + 4 + 2 * a.nwaves, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         static int printed = 0;
+        if (printed == 3 && d_ts) {  // chunk-level view of one launch: what runs after the DMMA warps are done?
+          std::vector<unsigned long long> ts((size_t)2 * st.n + 256);
+          cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+          const unsigned long long t_start = ~t[0], t_jobs = t[1];
+          int n_after = 0, n_started_after = 0;
+          double sum_dur_after = 0, max_dur = 0, sum_dur_before = 0;
+          int n_before = 0;
+          std::vector<int> hist(12, 0);
+          for (int c = 0; c < st.n; ++c) {
+            const unsigned long long b = ts[2 * c], e = ts[2 * c + 1];
+            if (!b || !e) continue;
+            const double dur = (e - b) * 1e-3;
+            if (e > t_jobs) {
+              ++n_after;
+              sum_dur_after += dur;
+              max_dur = std::max(max_dur, dur);
+              if (b > t_jobs) ++n_started_after;
+              const int bin = std::min(11, (int)((e - t_jobs) * 1e-3 / 10.0));
+              hist[bin]++;
+            } else {
+              ++n_before;
+              sum_dur_before += dur;
+            }
+          }
+          fprintf(stderr, "[htn] mix chunks: %d ended before the jobs were done (mean %.1f us each), %d after (%d of them also started after; mean %.1f us, max %.1f us); "
+                          "ends per 10 us after jobs-done:", n_before, sum_dur_before / std::max(n_before, 1), n_after, n_started_after,
+                  sum_dur_after / std::max(n_after, 1), max_dur);
+          for (int v : hist) fprintf(stderr, " %d", v);
+          fprintf(stderr, "\n[htn] waves complete at (us):");
+          for (int w = 0; w < std::min(a.nwaves, 256); ++w) fprintf(stderr, " %.0f", ts[(size_t)2 * st.n + w] ? (ts[(size_t)2 * st.n + w] - t_start) * 1e-3 : -1.0);
+          fprintf(stderr, "\n");
+        }
         if (printed++ < 6)
           fprintf(stderr,
-                  "[htn] stack timeline: jobs done at %.1f us, mix done at %.1f us after the first warp started; mixer warps: %llu chunks, "
-                  "per chunk %.0f clk ticket+record, %.0f clk wave wait, %.0f clk data\n",
-                  (t[1] - (~t[0])) * 1e-3, (t[2] - (~t[0])) * 1e-3, t[7], (double)t[4] / std::max<unsigned long long>(t[7], 1),
+                  "[htn] stack timeline: jobs done at %.1f us (%llu of %d mix chunks drawn by then), mix done at %.1f us after the first warp "
+                  "started; mixer warps: %llu chunks, per chunk %.0f clk ticket+record, %.0f clk wave wait, %.0f clk data\n",
+                  (t[1] - (~t[0])) * 1e-3, t[3], st.n, (t[2] - (~t[0])) * 1e-3, t[7], (double)t[4] / std::max<unsigned long long>(t[7], 1),
                   (double)t[5] / std::max<unsigned long long>(t[7], 1), (double)t[6] / std::max<unsigned long long>(t[7], 1));
       }
     }
@@ -638,8 +722,10 @@ void Program::destroy() {
     cudaFree(st.d_mt);
     cudaFree(st.d_ms);
     cudaFree(st.d_mc);
+    cudaFree(st.d_mcx);
     cudaFree(st.d_sjobs);
     cudaFree(st.d_wave_need);
+    cudaFree(st.d_tile_waves);
     cudaFree(st.d_ctr);
   }
   stages.clear();

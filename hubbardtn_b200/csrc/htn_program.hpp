@@ -53,7 +53,10 @@ struct StackJobH {
   int ldc;
   int K, nt, nb, M;
   int tmap, arow;  // tensor map index / first row inside that panel (tmap < 0: plain pointer path)
-  int wave;
+  int wave;        // >= 0: the whole job belongs to this wave (one arrival per consumer warp at the end of the job)
+  // tile-level waves (wave < 0): tile t of the job covers T blocks of the waves tw[t].x .. tw[t].y; every consumer warp of
+  // the group that computed the tile reports to each of them when the tile is stored
+  std::vector<std::pair<int, int>> tw;
 };
 
 enum StageTag { TAG_L = 1, TAG_W = 2, TAG_R = 4, TAG_Y = 8 };
@@ -73,6 +76,7 @@ struct Stage {
   MixTarget* d_mt = nullptr;
   MixSrc* d_ms = nullptr;
   MixChunk* d_mc = nullptr;
+  MixChunkX* d_mcx = nullptr;
   int n = 0;  // items or chunks
   int grid = 0;
   // kind 2
@@ -80,6 +84,8 @@ struct Stage {
   std::vector<int> wave_need;
   StackJob* d_sjobs = nullptr;
   int* d_wave_need = nullptr;
+  std::vector<int2> tile_waves;
+  int2* d_tile_waves = nullptr;
   unsigned long long* d_ctr = nullptr;
   int n_sjobs = 0, nwaves = 0;
   int tmap_slot = -1;  // slot whose tensor supplies the tensor maps at launch (-1: none needed)

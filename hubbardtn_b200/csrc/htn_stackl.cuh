@@ -39,15 +39,34 @@ constexpr int SL_KC = 16;            // k extent of one ring stage (128 bytes: o
 constexpr int SL_STAGES = SL_RING_STAGES;
 constexpr int SL_STAGE_ELEMS = SL_TM * SL_KC;  // 8 KB, unpadded, 128B-swizzled
 constexpr int SL_SLAB = STACK_SLAB_ELEMS;      // slab capacity (doubles): round4(K) * (8 CA + 4) must fit
-constexpr int SL_NCONS = SL_TM / 16;           // consumer warps: 16 rows each
-constexpr int SL_NMIX = 3;                     // mixer warps (stage W), warps SL_NCONS+1 ..
-constexpr int SL_THREADS = (SL_NCONS + 1 + SL_NMIX) * 32;
+constexpr int SL_GW = SL_TM / 16;              // warps of one consumer group: 16 rows each
 constexpr int SL_JOBWORDS = (int)(sizeof(StackJob) / 4);
 constexpr int SL_MIXSRC = 32;                  // source descriptors staged per mixer warp
+constexpr int SL_JOBQ = 2;
+// Two shapes of the CTA (template parameter NG = consumer groups):
+//   NG = 1: 4 consumer warps + 1 producer + 3 mixers = 256 threads, 2 CTAs per SM (each with its own 80 KB slab);
+//   NG = 2: 2 x 4 consumer warps working on alternate 64-row tiles of the SAME job (ONE slab), one producer warp and one
+//           A ring per group, 6 mixers = 512 threads, 1 CTA per SM.  The second slab's 80 KB become the staging area
+//           into which the mixers pull their sources with cp.async.bulk (see sl_mix_chunk_tma).
+constexpr int SLM_SLOT_BYTES = 2048;           // one staged piece of one mix source: 256 doubles
+constexpr int SLM_SLOTS = 6;                   // pieces in flight per mixer warp
+template <int NG>
+struct SlCfg {
+  static constexpr int NCONS = SL_GW * NG;
+  static constexpr int NPROD = NG;
+  static constexpr int NMIX = NG == 1 ? 3 : 6;
+  static constexpr int WARPS = NCONS + NPROD + NMIX;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int RING_ELEMS = NG * SL_STAGES * SL_STAGE_ELEMS;
+  static constexpr int MIXSTAGE_BYTES = NG == 1 ? 0 : NMIX * SLM_SLOTS * SLM_SLOT_BYTES;
+  static constexpr int NBAR = NG * 2 * SL_STAGES + 2 * SL_JOBQ + (NG == 1 ? 0 : (NMIX + NCONS) * SLM_SLOTS);
+  static constexpr int SMEM_BYTES = (RING_ELEMS + SL_SLAB) * 8 + MIXSTAGE_BYTES + NBAR * 8 + SL_JOBQ * SL_JOBWORDS * 4 + 16;
+  static constexpr int CTAS_PER_SM = NG == 1 ? 2 : 1;
+};
 // 2 CTAs per SM need 2 x (this + 1 KB) <= 228 KB: the slab leaves no room for per-warp staging of the mix sources
 // (they travel through warp shuffles instead)
-constexpr int SL_SMEM_BYTES = (SL_STAGES * SL_STAGE_ELEMS + SL_SLAB) * 8 + (2 * SL_STAGES + 4) * 8 + 2 * SL_JOBWORDS * 4 + 16;
-static_assert(2 * (SL_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
+static_assert(2 * (SlCfg<1>::SMEM_BYTES + 1024) <= 233472, "two CTAs per SM must fit");
+static_assert(SlCfg<2>::SMEM_BYTES + 1024 <= 233472, "the one-CTA shape must fit");
 
 __device__ __forceinline__ unsigned sl_smem(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void sl_mbar_init(uint64_t* bar, int count) {
@@ -80,6 +99,25 @@ __device__ __forceinline__ void sl_tma_2d(void* dst, const void* tmap, int c0, i
                "l"(tmap), "r"(c0), "r"(c1), "r"(sl_smem(bar))
                : "memory");
 }
+// the same with an L2 eviction-priority hint (the environment panels are re-read by every column piece of every x block
+// of their sector: evict_last keeps them in front of the streaming mix traffic)
+__device__ __forceinline__ void sl_tma_2d_hint(void* dst, const void* tmap, int c0, int c1, uint64_t* bar, unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(
+          sl_smem(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(sl_smem(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long sl_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long sl_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void sl_cp16(void* dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sl_smem(dst)), "l"(src), "r"(src_bytes));
 }
@@ -91,6 +129,12 @@ __device__ __forceinline__ void sl_dmma(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ unsigned long long sl_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
 }
 
 struct SlRing {
@@ -107,10 +151,21 @@ struct SlRing {
   }
 };
 
+// tile-level waves: one consumer warp's strip of a tile is stored -- report to every wave whose T blocks the tile covers
+__device__ __forceinline__ void sl_report_tile(const StackArgs& a, int2 tw, int dbg) {
+  if (tw.y < tw.x) return;
+  __threadfence();
+  for (int w = tw.x; w <= tw.y; ++w) {
+    const unsigned long long old = atomicAdd(a.ctr + 4 + w, 1ull);
+    if ((dbg & 32) && a.dbg_ts && old + 1 == a.epoch * (unsigned long long)a.wave_need[w]) a.dbg_ts[2 * a.nmix + w] = sl_globaltimer();
+  }
+}
+
 // consumer side of one job, specialised on the number of 8-column atoms of the slab
 template <int CA>
 __device__ __forceinline__ void sl_consume_job(const StackJob& job, SlRing& rg, const double* __restrict__ slab, int role,
-                                               int lane, const Bases& bases, int dbg) {
+                                               int lane, const Bases& bases, int dbg, int m_begin, int m_step,
+                                               const StackArgs& a) {
   const int g = lane >> 2, t = lane & 3;
   const int rho = 2 * (g & 3) + (g >> 2);  // tile row (within an 8-row atom) held by fragment row g
   const int SB = CA * 8 + 4;
@@ -126,11 +181,15 @@ __device__ __forceinline__ void sl_consume_job(const StackJob& job, SlRing& rg, 
   const long long ldc = job.ldc;
   const int nt = job.nt;
   unsigned ready = 0;
-  for (int m0 = 0; m0 < job.M; m0 += SL_TM) {
+  int2 pend = make_int2(0, -1);  // waves of the previous tile: its stores have drained by the time the next K loop ends,
+                                 // so the fence in front of the report costs nothing there
+  for (int m0 = m_begin; m0 < job.M; m0 += m_step) {  // this group's tiles of the job
+    int2 tw_cur = make_int2(0, -1);
+    if (job.tile0 >= 0 && lane == 0) tw_cur = a.tile_waves[job.tile0 + m0 / SL_TM];
     double acc[CA][2][2];
 #pragma unroll
     for (int j = 0; j < CA; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
-    const bool last_tile = m0 + SL_TM >= job.M;
+    const bool last_tile = m0 + m_step >= job.M;
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       if (!ready) sl_mbar_wait(&rg.full[rg.stage], rg.phase);
@@ -174,6 +233,7 @@ __device__ __forceinline__ void sl_consume_job(const StackJob& job, SlRing& rg, 
       __syncwarp();
       if (lane == 0) sl_mbar_arrive(&rg.empty[cur]);
     }
+    if (job.tile0 >= 0 && lane == 0) sl_report_tile(a, pend, dbg);
     // ---- store the 16 x nt strip of this warp (rows beyond the run / columns beyond nt are dropped) ----
     const int mt = min(SL_TM, job.M - m0);
 #pragma unroll
@@ -191,6 +251,11 @@ __device__ __forceinline__ void sl_consume_job(const StackJob& job, SlRing& rg, 
         }
       }
     }
+    pend = tw_cur;  // reported behind the next tile's K loop (or at the end of the job)
+  }
+  if (job.tile0 >= 0) {
+    __syncwarp();
+    if (lane == 0) sl_report_tile(a, pend, dbg);
   }
 }
 
@@ -213,11 +278,6 @@ __device__ __forceinline__ double2 sl_ld_stream(const double* p) {
 // streaming 16-byte store: U is written once and read next by stage R (another launch) -- keep it from pushing T out of L2
 __device__ __forceinline__ void sl_st_stream(double* p, double2 v) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ unsigned long long sl_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
-  return t;
 }
 
 // one mix chunk by one warp: dst[e] = sum_s coef_s src_s[e] over a flat element range (identical padded layouts)
@@ -326,6 +386,7 @@ __device__ __forceinline__ void sl_mixer_loop_t(const StackArgs& a, const Bases&
       __syncwarp();
     }
     const long long t2 = PROF ? clock64() : 0;
+    if (PROF && a.dbg_ts && lane == 0) a.dbg_ts[2 * tk] = sl_globaltimer();
     if (!(a.dbg & 4)) sl_mix_chunk<U>(a, ch, bases, lane);
     if (a.mix_lag > 0 && ch.pad_ >= 0) {  // back-pressure experiments: count the finished chunks of the wave
       __syncwarp();
@@ -333,6 +394,7 @@ __device__ __forceinline__ void sl_mixer_loop_t(const StackArgs& a, const Bases&
     }
     if (PROF) {
       const long long t3 = clock64();
+      if (a.dbg_ts && lane == 0) a.dbg_ts[2 * tk + 1] = sl_globaltimer();
       c_desc += t1 - t0;
       c_wait += t2 - t1;
       c_work += t3 - t2;
@@ -360,49 +422,210 @@ __device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& b
     sl_mixer_loop_t<U, false>(a, bases, lane, nwarps_total);
 }
 
-// Roles: warps 0 .. SL_NCONS-1 = consumers (DMMA; they also load the slab of a job themselves, all 128 threads,
-// while the A chunks the producer has already queued wait in the ring: a job switch costs one slab latency);
-// warp SL_NCONS = producer (job tickets, job records, the A ring); warps SL_NCONS+1 .. = mixers (stage W).
-// Register budget: launched with 128 per thread (2 CTAs x 256 threads); the consumer warp group grows to 168 (with 124
-// the DMMA loops lose a third of their speed: fewer fragment loads in flight), the other warp group shrinks to 88,
-// enough for 12 independent 16-byte loads per mixer lane.
-constexpr int SL_JOBQ = 2;
-__global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_constant__ StackArgs a,
-                                                                    const __grid_constant__ Bases bases) {
+// ---- mixers of the one-CTA shape: sources staged through shared memory by cp.async.bulk ----
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void sl_bulk_g2s_hint(void* dst, const void* src, unsigned bytes, uint64_t* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   sl_smem(dst)),
+               "l"(src), "r"(bytes), "r"(sl_smem(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void sl_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sl_smem(dst)),
+               "l"(src), "r"(bytes), "r"(sl_smem(bar))
+               : "memory");
+}
+
+// One mixer warp: chunks by ticket; the (piece, source) items of a chunk -- 2 KB of one source each -- are pulled into the
+// warp's SLM_SLOTS staging slots SLM_SLOTS items ahead of their use, so that 12 KB per warp (72 KB per SM) are in flight
+// all the time without holding registers; a lane reads 4 x 16 bytes of a landed slot, accumulates coef * v and, after the
+// last source of a piece, streams the piece out.  The ticket of the NEXT chunk is drawn before the data loop of the
+// current one, its 32-byte record is loaded right after (both hidden behind the data).
+__device__ __forceinline__ void sl_mixer_loop_tma(const StackArgs& a, const Bases& bases, int lane, int nwarps_total,
+                                                  unsigned char* stage, uint64_t* bar) {
+  const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
+  const bool prof = (a.dbg & 32) != 0;
+  long long c_wait = 0, c_work = 0, n_chunks = 0;
+  unsigned it = 0;  // items issued so far by this warp (slot = it % SLM_SLOTS, parity = (it / SLM_SLOTS) & 1)
+  const unsigned long long pol_first = sl_policy_evict_first();
+  unsigned long long tk = 0;
+  if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  while (tk < (unsigned long long)a.nmix) {
+    const MixChunkX ch = a.mcx[tk];
+    // next ticket: in flight during this chunk
+    unsigned long long tk_next = 0;
+    if (lane == 0) tk_next = atomicAdd(a.ctr + 1, 1ull) - base;
+    const long long t1 = prof ? clock64() : 0;
+    if (ch.wave >= 0) {
+      if (lane == 0) {
+        for (int w = ch.wave;; w = 0) {
+          const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[w];
+          unsigned spins = 0;
+          while (sl_ld_acquire(a.ctr + 4 + w) < need) {
+            __nanosleep(256);
+            if (++spins > (1u << 22)) {
+              atomicAdd(a.ctr + 2, 1ull);
+              break;
+            }
+          }
+          if (w == 0) break;
+        }
+      }
+      __syncwarp();
+    }
+    const long long t2 = prof ? clock64() : 0;
+    if (prof && a.dbg_ts && lane == 0) a.dbg_ts[2 * tk] = sl_globaltimer();
+    if (!(a.dbg & 4)) {
+      double* dst = const_cast<double*>(resolve(ch.off, ch.base, bases)) + ch.elem0;
+      const int npieces = (ch.nelem + 255) >> 8;
+      for (int s0 = 0; s0 < ch.nsrc || s0 == 0; s0 += 32) {
+        const int ns = min(32, ch.nsrc - s0);
+        unsigned long long my_ptr = 0;
+        double my_coef = 0.0;
+        if (lane < ns) {
+          const MixSrc S = a.ms[ch.src_begin + s0 + lane];
+          my_ptr = reinterpret_cast<unsigned long long>(resolve(S.off, S.base, bases) + ch.elem0);
+          my_coef = S.coef;
+        }
+        const int total = npieces * max(ns, 0);
+        int issued = 0;
+        auto issue = [&](int item) {  // all lanes call (shuffle); lane 0 issues the copy
+          const int p = item / ns, s = item - p * ns;
+          const unsigned long long sp = __shfl_sync(0xffffffffu, my_ptr, s);
+          if (lane == 0) {
+            const unsigned slot = it % SLM_SLOTS;
+            const unsigned bytes = (unsigned)min(256, ch.nelem - (p << 8)) * 8u;
+            sl_mbar_expect_tx(&bar[slot], bytes);
+            if (a.dbg & 256)
+              sl_bulk_g2s_hint(stage + slot * SLM_SLOT_BYTES, reinterpret_cast<const double*>(sp) + (p << 8), bytes, &bar[slot], pol_first);
+            else
+              sl_bulk_g2s(stage + slot * SLM_SLOT_BYTES, reinterpret_cast<const double*>(sp) + (p << 8), bytes, &bar[slot]);
+          }
+          ++it;
+        };
+        const unsigned it0 = it;
+        for (; issued < total && issued < SLM_SLOTS; ++issued) issue(issued);
+        double2 acc[4];
+        for (int c = 0; c < total; ++c) {
+          const int p = c / ns, s = c - p * ns;
+          const unsigned gi = it0 + (unsigned)c;
+          const unsigned slot = gi % SLM_SLOTS, par = (gi / SLM_SLOTS) & 1u;
+          sl_mbar_wait(&bar[slot], par);
+          const double cf = __shfl_sync(0xffffffffu, my_coef, s);
+          const double2* sv = reinterpret_cast<const double2*>(stage + slot * SLM_SLOT_BYTES) + lane;
+          const int e = (p << 8) + 2 * lane;  // element of the chunk held by this lane in quarter q: e + 64 q
+          if (s == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              acc[q] = (s0 == 0 || e + 64 * q >= ch.nelem) ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(dst + e + 64 * q);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 v = sv[32 * q];
+            acc[q].x = fma(cf, v.x, acc[q].x);
+            acc[q].y = fma(cf, v.y, acc[q].y);
+          }
+          if (s == ns - 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (e + 64 * q < ch.nelem) {
+                if (s0 + 32 >= ch.nsrc)
+                  sl_st_stream(dst + e + 64 * q, acc[q]);
+                else
+                  *reinterpret_cast<double2*>(dst + e + 64 * q) = acc[q];
+              }
+          }
+          __syncwarp();  // every lane has read the slot: it may be refilled
+          if (issued < total) {
+            issue(issued);
+            ++issued;
+          }
+        }
+        if (ch.nsrc == 0) {  // a target without sources is cleared
+          for (int e = 2 * lane; e < ch.nelem; e += 64) *reinterpret_cast<double2*>(dst + e) = make_double2(0.0, 0.0);
+          break;
+        }
+      }
+    }
+    if (a.mix_lag > 0 && ch.wave >= 0) {
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.ctr + 4 + a.nwaves + ch.wave, 1ull);
+    }
+    if (prof) {
+      const long long t3 = clock64();
+      c_wait += t2 - t1;
+      c_work += t3 - t2;
+      ++n_chunks;
+      if (a.dbg_ts && lane == 0) a.dbg_ts[2 * tk + 1] = sl_globaltimer();
+    }
+    tk = __shfl_sync(0xffffffffu, tk_next, 0);
+  }
+  if (prof && lane == 0) {
+    unsigned long long* d = a.ctr + 4 + 2 * a.nwaves;
+    atomicMax(d + 2, sl_globaltimer());
+    atomicAdd(d + 5, (unsigned long long)c_wait);
+    atomicAdd(d + 6, (unsigned long long)c_work);
+    atomicAdd(d + 7, (unsigned long long)n_chunks);
+  }
+}
+
+// Roles: warps 0 .. NCONS-1 = consumers in groups of four (DMMA; all of them load the slab of a job together while the A
+// chunks the producers have already queued wait in the rings: a job switch costs one slab latency); warps NCONS ..
+// NCONS+NPROD-1 = producers, one per consumer group (producer 0 also draws the job tickets and publishes the job records);
+// the rest = mixers (stage W).
+// Register budget: launched with 128 per thread; the consumer warp groups grow (with 124 the DMMA loops lose a third of
+// their speed: fewer fragment loads in flight), the other warp groups shrink.
+template <int NG>
+__global__ void __launch_bounds__(SlCfg<NG>::THREADS, SlCfg<NG>::CTAS_PER_SM)
+    stack_gemm_kernel(const __grid_constant__ StackArgs a, const __grid_constant__ Bases bases) {
+  using Cfg = SlCfg<NG>;
+  constexpr int NCONS = Cfg::NCONS, NPROD = Cfg::NPROD;
   extern __shared__ __align__(1024) double sl_sm[];
-  SlRing rg;
-  rg.ring = sl_sm;  // 1024-byte aligned stages (128-byte swizzle atom = 8 rows x 128 B)
-  double* slab = sl_sm + SL_STAGES * SL_STAGE_ELEMS;
-  rg.full = reinterpret_cast<uint64_t*>(slab + SL_SLAB);
-  rg.empty = rg.full + SL_STAGES;
-  uint64_t* jfull = rg.empty + SL_STAGES;
+  double* rings = sl_sm;  // 1024-byte aligned stages (128-byte swizzle atom = 8 rows x 128 B)
+  double* slab = sl_sm + Cfg::RING_ELEMS;
+  unsigned char* mixstage = reinterpret_cast<unsigned char*>(slab + SL_SLAB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mixstage + Cfg::MIXSTAGE_BYTES);
+  uint64_t* full_all = bars;                                // [NG][SL_STAGES]
+  uint64_t* empty_all = full_all + NG * SL_STAGES;          // [NG][SL_STAGES]
+  uint64_t* jfull = empty_all + NG * SL_STAGES;
   uint64_t* jempty = jfull + SL_JOBQ;
-  int* job_slot = reinterpret_cast<int*>(jempty + SL_JOBQ);  // SL_JOBQ records
-  rg.stage = 0;
-  rg.phase = 0;
+  uint64_t* mixbar = jempty + SL_JOBQ;                      // [NMIX][SLM_SLOTS] (NG = 2)
+  int* job_slot = reinterpret_cast<int*>(bars + Cfg::NBAR);  // SL_JOBQ records
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dbg = a.dbg;
-  // the ring must never hold NaN patterns: K tails multiply stale columns by the zero rows of the slab
-  for (int i = tid; i < SL_STAGES * SL_STAGE_ELEMS; i += SL_THREADS) rg.ring[i] = 0.0;
+  // the rings must never hold NaN patterns: K tails multiply stale columns by the zero rows of the slab
+  for (int i = tid; i < Cfg::RING_ELEMS; i += Cfg::THREADS) rings[i] = 0.0;
   if (tid == 0) {
-    for (int s = 0; s < SL_STAGES; ++s) {
-      sl_mbar_init(&rg.full[s], 32);          // every producer lane arrives once (cp.async noinc, or plain / expect_tx)
-      sl_mbar_init(&rg.empty[s], SL_NCONS);   // one elected lane per consumer warp
+    for (int s = 0; s < NG * SL_STAGES; ++s) {
+      sl_mbar_init(&full_all[s], 32);      // every producer lane arrives once (cp.async noinc, or plain / expect_tx)
+      sl_mbar_init(&empty_all[s], SL_GW);  // one elected lane per consumer warp of the group
     }
     for (int s = 0; s < SL_JOBQ; ++s) {
       sl_mbar_init(&jfull[s], 1);
-      sl_mbar_init(&jempty[s], SL_NCONS);
+      sl_mbar_init(&jempty[s], NCONS + NPROD - 1);
     }
+    if (NG > 1)
+      for (int s = 0; s < (Cfg::NMIX + NCONS) * SLM_SLOTS; ++s) sl_mbar_init(&mixbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero fill before async-proxy (TMA) writes
   __syncthreads();
   int jq = 0;
   unsigned jphase = 0;
+  // warps that draw mix tickets (each overshoots the ticket counter by one): in the one-CTA shape the producers do not mix
+  const int nwarps_total = (int)gridDim.x * (NG == 1 ? Cfg::WARPS : Cfg::WARPS - NPROD);
 
-  if (warp < SL_NCONS) {
+  if (warp < NCONS) {
     // =========================== CONSUMERS ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 144;\n");
+    const int group = warp / SL_GW, role = warp % SL_GW;
+    SlRing rg;
+    rg.ring = rings + group * SL_STAGES * SL_STAGE_ELEMS;
+    rg.full = full_all + group * SL_STAGES;
+    rg.empty = empty_all + group * SL_STAGES;
+    rg.stage = 0;
+    rg.phase = 0;
     while (true) {
       sl_mbar_wait(&jfull[jq], jphase);
       StackJob job;
@@ -411,12 +634,12 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
       for (int w = 0; w < SL_JOBWORDS; ++w) reinterpret_cast<int*>(&job)[w] = slot[w];
       if (job.M < 0) break;
       // ---- slab: K rows of nb doubles, rows K .. round4(K) zero; loaded by all consumer threads ----
-      asm volatile("bar.sync 1, %0;\n" ::"n"(SL_NCONS * 32) : "memory");  // every warp has left the previous slab
+      asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");  // every warp has left the previous slab
       {
         const int CA = (job.nt + 7) >> 3, SB = CA * 8 + 4, K = job.K;
         const double* Bg = resolve(job.b_off, job.b_base, bases);
         const int np = job.nb >> 1, total = K * np;  // 16-byte pieces per row
-        constexpr int NT_ = SL_NCONS * 32;
+        constexpr int NT_ = NCONS * 32;
         int k = tid / np, q = tid - k * np;
         const int dk = NT_ / np, dq = NT_ - dk * np;
         for (int i = tid; i < total; i += NT_) {
@@ -432,24 +655,26 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
         for (int i = tid; i < kz * SB; i += NT_) slab[K * SB + i] = 0.0;
         asm volatile("cp.async.wait_all;\n" ::: "memory");
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(SL_NCONS * 32) : "memory");
-      const int role = warp;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
+      const int mb = group * SL_TM, ms = NG * SL_TM;
       switch ((job.nt + 7) >> 3) {
-        case 1: sl_consume_job<1>(job, rg, slab, role, lane, bases, dbg); break;
-        case 2: sl_consume_job<2>(job, rg, slab, role, lane, bases, dbg); break;
-        case 3: sl_consume_job<3>(job, rg, slab, role, lane, bases, dbg); break;
-        case 4: sl_consume_job<4>(job, rg, slab, role, lane, bases, dbg); break;
-        case 5: sl_consume_job<5>(job, rg, slab, role, lane, bases, dbg); break;
-        case 6: sl_consume_job<6>(job, rg, slab, role, lane, bases, dbg); break;
-        case 7: sl_consume_job<7>(job, rg, slab, role, lane, bases, dbg); break;
-        default: sl_consume_job<8>(job, rg, slab, role, lane, bases, dbg); break;
+        case 1: sl_consume_job<1>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 2: sl_consume_job<2>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 3: sl_consume_job<3>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 4: sl_consume_job<4>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 5: sl_consume_job<5>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 6: sl_consume_job<6>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        case 7: sl_consume_job<7>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
+        default: sl_consume_job<8>(job, rg, slab, role, lane, bases, dbg, mb, ms, a); break;
       }
       __syncwarp();
       if (lane == 0) {
         sl_mbar_arrive(&jempty[jq]);
         if (job.wave >= 0) {  // this warp's strips of the job's T tiles are written: publish them to the mixers
           __threadfence();
-          atomicAdd(a.ctr + 4 + job.wave, 1ull);
+          const unsigned long long old = atomicAdd(a.ctr + 4 + job.wave, 1ull);
+          if ((dbg & 32) && a.dbg_ts && old + 1 == a.epoch * (unsigned long long)a.wave_need[job.wave])
+            a.dbg_ts[2 * a.nmix + job.wave] = sl_globaltimer();  // the arrival that completed the wave
         }
       }
       if (++jq == SL_JOBQ) {
@@ -457,64 +682,100 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
         jphase ^= 1u;
       }
     }
-    if ((dbg & 32) && lane == 0) atomicMax(a.ctr + 4 + 2 * a.nwaves + 1, sl_globaltimer());
+    if ((dbg & 32) && lane == 0) {
+      atomicMax(a.ctr + 4 + 2 * a.nwaves + 1, sl_globaltimer());
+      // mix tickets drawn so far when this warp ran out of jobs (max over warps = at the end of the job phase)
+      const unsigned long long drawn = sl_ld_acquire(a.ctr + 1) - (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
+      atomicMax(a.ctr + 4 + 2 * a.nwaves + 3, drawn);
+    }
     // no stack jobs left: help with the mix (the last wave's targets are still to be formed)
-    if (a.nmix > 0) sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
+    if (a.nmix > 0) {
+      if (NG == 1 || (dbg & 64)) {
+        sl_mixer_loop<8>(a, bases, lane, nwarps_total);
+      } else {
+        // every consumer warp has left its last tile: rings and slab (144 KB) are free and become staging slots, so the
+        // tail of the mix runs with 8 more bulk-copy fed warps
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        sl_mixer_loop_tma(a, bases, lane, nwarps_total, reinterpret_cast<unsigned char*>(sl_sm) + warp * SLM_SLOTS * SLM_SLOT_BYTES,
+                          mixbar + (Cfg::NMIX + warp) * SLM_SLOTS);
+      }
+    }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 112;\n");
-    if (warp == SL_NCONS) {
-      // =========================== PRODUCER ===========================
+    if (warp < NCONS + NPROD) {
+      // =========================== PRODUCERS ===========================
+      const int pg = warp - NCONS;  // the consumer group this warp feeds
+      SlRing rg;
+      rg.ring = rings + pg * SL_STAGES * SL_STAGE_ELEMS;
+      rg.full = full_all + pg * SL_STAGES;
+      rg.empty = empty_all + pg * SL_STAGES;
+      rg.stage = 0;
+      rg.phase = 0;
       const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.njobs + (int)gridDim.x);
-      if ((dbg & 32) && lane == 0) atomicMax(a.ctr + 4 + 2 * a.nwaves, ~sl_globaltimer());  // = min start time
+      if ((dbg & 32) && lane == 0 && pg == 0) atomicMax(a.ctr + 4 + 2 * a.nwaves, ~sl_globaltimer());  // = min start time
       int mix_passed = 0;  // waves whose mix is known to be complete: 0 .. mix_passed - 1
+      const unsigned long long pol_last = sl_policy_evict_last();
       while (true) {
-        unsigned long long tk = 0;
-        if (lane == 0) tk = atomicAdd(a.ctr, 1ull) - base;
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        const bool done = tk >= (unsigned long long)a.njobs;
         StackJob job{};
-        if (!done) job = a.jobs[tk];
-        if (!done && a.mix_lag > 0 && a.nmix > 0 && job.wave - a.mix_lag >= mix_passed && job.wave - a.mix_lag >= 1) {
-          // back-pressure: the T blocks of wave w - lag must have been mixed before wave w is started, so that what the
-          // mixers read is still in L2 (without it the DMMA warps run ahead and T makes a round trip through HBM)
-          const int need_wave = job.wave - a.mix_lag;
-          if (lane == 0) {
-            for (int w = mix_passed > 1 ? mix_passed : 1; w <= need_wave; ++w) {
-              const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[a.nwaves + w];
-              unsigned spins = 0;
-              while (sl_ld_acquire(a.ctr + 4 + a.nwaves + w) < need) {
-                __nanosleep(128);
-                if (++spins > (1u << 22)) {
-                  atomicAdd(a.ctr + 2, 1ull);
-                  break;
+        bool done;
+        if (pg == 0) {
+          unsigned long long tk = 0;
+          if (lane == 0) tk = atomicAdd(a.ctr, 1ull) - base;
+          tk = __shfl_sync(0xffffffffu, tk, 0);
+          done = tk >= (unsigned long long)a.njobs;
+          if (!done) job = a.jobs[tk];
+          if (!done && a.mix_lag > 0 && a.nmix > 0 && job.wave - a.mix_lag >= mix_passed && job.wave - a.mix_lag >= 1) {
+            // back-pressure (experiments): the T blocks of wave w - lag must have been mixed before wave w is started
+            const int need_wave = job.wave - a.mix_lag;
+            if (lane == 0) {
+              for (int w = mix_passed > 1 ? mix_passed : 1; w <= need_wave; ++w) {
+                const unsigned long long need = a.epoch * (unsigned long long)a.wave_need[a.nwaves + w];
+                unsigned spins = 0;
+                while (sl_ld_acquire(a.ctr + 4 + a.nwaves + w) < need) {
+                  __nanosleep(128);
+                  if (++spins > (1u << 22)) {
+                    atomicAdd(a.ctr + 2, 1ull);
+                    break;
+                  }
                 }
               }
             }
+            __syncwarp();
+            mix_passed = need_wave + 1;
           }
+          sl_mbar_wait(&jempty[jq], jphase ^ 1u);
+          int* slot = job_slot + jq * SL_JOBWORDS;
+          if (done) job.M = -1;  // stop record
+          if (lane < SL_JOBWORDS) slot[lane] = reinterpret_cast<const int*>(&job)[lane];
           __syncwarp();
-          mix_passed = need_wave + 1;
+          if (lane == 0) sl_mbar_arrive(&jfull[jq]);
+        } else {
+          sl_mbar_wait(&jfull[jq], jphase);
+          const int* slot = job_slot + jq * SL_JOBWORDS;
+#pragma unroll
+          for (int w = 0; w < SL_JOBWORDS; ++w) reinterpret_cast<int*>(&job)[w] = slot[w];
+          __syncwarp();
+          if (lane == 0) sl_mbar_arrive(&jempty[jq]);
+          done = job.M < 0;
         }
-        sl_mbar_wait(&jempty[jq], jphase ^ 1u);
-        int* slot = job_slot + jq * SL_JOBWORDS;
-        if (done) job.M = -1;  // stop record
-        if (lane < SL_JOBWORDS) slot[lane] = reinterpret_cast<const int*>(&job)[lane];
-        __syncwarp();
-        if (lane == 0) sl_mbar_arrive(&jfull[jq]);
         if (++jq == SL_JOBQ) {
           jq = 0;
           jphase ^= 1u;
         }
         if (done) break;
         const int K = job.K;
-        // ---- A tiles ----
+        // ---- A tiles of this group ----
         if (job.tmap >= 0) {
           const unsigned char* tm = a.tmaps + (size_t)job.tmap * 128;
-          for (int m0 = 0; m0 < job.M; m0 += SL_TM) {
+          for (int m0 = pg * SL_TM; m0 < job.M; m0 += NG * SL_TM) {
             for (int k0 = 0; k0 < K; k0 += SL_KC) {
               sl_mbar_wait(&rg.empty[rg.stage], rg.phase ^ 1u);
               if (lane == 0) {
                 sl_mbar_expect_tx(&rg.full[rg.stage], SL_STAGE_ELEMS * 8);
-                if (!(dbg & 1))
+                if (dbg & 128)
+                  sl_tma_2d_hint(rg.ring + rg.stage * SL_STAGE_ELEMS, tm, k0, job.arow + m0, &rg.full[rg.stage], pol_last);
+                else if (!(dbg & 1))
                   sl_tma_2d(rg.ring + rg.stage * SL_STAGE_ELEMS, tm, k0, job.arow + m0, &rg.full[rg.stage]);
                 else
                   asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(sl_smem(&rg.full[rg.stage])),
@@ -530,7 +791,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
           // lane = (row % 4, 16-byte piece of the 128-byte chunk row); piece q of row r lands at chunk q ^ (r & 7)
           const double* Ag = resolve(job.a_off, job.a_base, bases);
           const int arow = lane >> 3, aq = lane & 7;
-          for (int m0 = 0; m0 < job.M; m0 += SL_TM) {
+          for (int m0 = pg * SL_TM; m0 < job.M; m0 += NG * SL_TM) {
             const int mt = min(SL_TM, job.M - m0);
             const double* At = Ag + (long long)(m0 + arow) * job.lda + 2 * aq;
             const long long step = 4ll * job.lda;
@@ -555,10 +816,15 @@ __global__ void __launch_bounds__(SL_THREADS, 2) stack_gemm_kernel(const __grid_
           }
         }
       }
-      if (a.nmix > 0) sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
+      if (a.nmix > 0 && NG == 1) sl_mixer_loop<8>(a, bases, lane, nwarps_total);
     } else if (a.nmix > 0) {
       // =========================== MIXERS (stage W) ===========================
-      sl_mixer_loop<8>(a, bases, lane, (int)gridDim.x * (SL_NMIX + SL_NCONS + 1));
+      if (NG == 1 || (dbg & 64)) {
+        sl_mixer_loop<8>(a, bases, lane, nwarps_total);
+      } else {
+        const int mw = warp - NCONS - NPROD;
+        sl_mixer_loop_tma(a, bases, lane, nwarps_total, mixstage + mw * SLM_SLOTS * SLM_SLOT_BYTES, mixbar + mw * SLM_SLOTS);
+      }
     }
   }
 }

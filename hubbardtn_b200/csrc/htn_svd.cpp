@@ -6,7 +6,7 @@
 //   M_m[(s1,l),(r,s2)] = sqrt(d_r/d_m) x2[l,s1,m,s2,r] = U S V^T  per middle sector m,
 //   AL[l,s1,m] = rows of U, C[m] = diag(S), AR[m,s2,r] = columns of V^T / sqrt(d_r/d_m);
 // truncation is global over all sectors: keep sigma >= cut * ||x2|| (and > 1e-14 ||x2||), at most
-// `maxdim` multiplets (largest first).  Only the singular values travel to the host.
+// `maxdim` multiplets (largest first); maxdim < 0 caps the FULL dimension sum_c dim(c) n_c at |maxdim| (TensorKit truncdim).  Only the singular values travel to the host.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -197,10 +197,14 @@ extern "C" int32_t htn_tsvd(const htn_tensor* x2, double cut, int32_t maxdim, ht
     std::stable_sort(all.begin(), all.end(), [](const SV& a, const SV& b) { return a.s > b.s; });
     std::vector<int> keep(panels.size(), 0);
     int nkept = 0;
+    long long nfull = 0;  // maxdim < 0: cap on the FULL dimension sum_c dim(c) n_c (TensorKit truncdim)
     for (const SV& v : all) {
       if (v.s < cut * nrm || v.s <= 1e-14 * nrm || (maxdim > 0 && nkept >= maxdim)) break;
+      const int dm = sdim(sym, x2->mid[panels[v.panel]->m]);
+      if (maxdim < 0 && nfull + dm > -(long long)maxdim) break;
       ++keep[v.panel];
       ++nkept;
+      nfull += dm;
     }
     if (nkept == 0) return fail(HTN_ERR_INVALID, "tsvd: truncation removed every singular value");
     double disc = 0.0;

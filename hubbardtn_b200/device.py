@@ -566,6 +566,27 @@ def changebonds_svdcut(ctx: Context, AL, AR, Cs, AC, Ws, cut=0.0, maxdim=0, sym=
     return uniform_from_right(ctx, AR, Cs[-1], sym)
 
 
+def changebonds(ctx: Context, kind: int, AL, AR, Cs, AC, Ws, cut: float = 0.0, maxdim: int = 0, krylovdim: int = 30,
+                eig_tol: float = 1e-10, tol_gauge: float = 1e-12):
+    """`changebonds(psi, SvdCut(trscheme))` (kind 0) / `changebonds(psi, H, VUMPSSvdCut(trscheme))` (kind 1) in ONE library
+    call (htn_changebonds; HF:1013-1018, 1363-1365).  maxdim > 0 caps the multiplets per bond, maxdim < 0 the full
+    dimension (`truncdim(|maxdim|)`).  The inputs are left untouched (the library works on copies made here); returns new
+    (AL, AR, C, AC) lists."""
+    lists = [[t.like_copy() for t in lst] for lst in (AL, AR, Cs, AC)]
+    arrs = [_harr(x) for x in lists]
+    rc = lib.htn_changebonds(ctx.h, kind, len(AL), arrs[0], arrs[1], arrs[2], arrs[3], _harr(Ws), cut, maxdim, krylovdim,
+                             eig_tol, tol_gauge)
+    out = []
+    for x, arr in zip(lists, arrs):
+        new = []
+        for i, t in enumerate(x):
+            t.h = None                                   # retired: destroyed or re-wrapped below
+            new.append(Tensor(ctx, C.c_void_p(arr[i])))
+        out.append(new)
+    L.check(rc, ctx.h)
+    return out[0], out[1], out[2], out[3]
+
+
 def mul_bond(A: Tensor, Cb: Tensor, right: bool = True) -> Tensor:
     """A . C (right) or C . A (left) as a new MPS tensor (MPSKit `_mul_tail` / `_mul_front`)."""
     h = C.c_void_p()

@@ -540,29 +540,10 @@ def TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, **kw):
     d = produce_groundstate(simul, **kw)
     psi, H, ctx = d["groundstate"], d["ham"], d["ctx"]
 
-    def truncated(cap):
-        if trunc_scheme == 1:
-            AL, AR, C, AC = dev.changebonds_svdcut(ctx, [t.like_copy() for t in psi.AL], [t.like_copy() for t in psi.AR],
-                                                   [t.like_copy() for t in psi.C], [t.like_copy() for t in psi.AC], H.W,
-                                                   maxdim=cap, sym=psi.sym)
-        else:
-            AL, AR, C, AC, _, _ = dev.changebonds_vumpssvdcut(ctx, psi.AL, psi.AR, psi.C, psi.AC, H.W, H.P, psi.sym,
-                                                              maxdim=cap)
-        return InfiniteMPS(ctx, psi.sym, AL, AR, C, AC, psi.phys)
-
-    # multiplets are kept largest-first; find the largest multiplet count whose full dimension fits
-    best = None
-    lo, hi = 1, max(sum(sp.values()) for sp in (psi.bond_space(i) for i in range(len(psi))))
-    while lo <= hi:
-        mid = (lo + hi) // 2
-        cand = truncated(mid)
-        if max(dim_state(cand)) <= trunc_dim:
-            best, lo = cand, mid + 1
-        else:
-            hi = mid - 1
-    if best is None:
-        raise ValueError("trunc_dim is smaller than the smallest non-trivial bond dimension")
-    return best
+    # htn_changebonds with maxdim < 0 = truncdim(trunc_dim) on the FULL dimension: the kept set of every bond is decided
+    # in one pass from its singular values (TensorKit's truncdim), no search over multiplet caps
+    AL, AR, C, AC = dev.changebonds(ctx, 1 if trunc_scheme == 0 else 0, psi.AL, psi.AR, psi.C, psi.AC, H.W, maxdim=-int(trunc_dim))
+    return InfiniteMPS(ctx, psi.sym, AL, AR, C, AC, psi.phys)
 
 
 def produce_TruncState(simul, trunc_dim: int, trunc_scheme: int = 0, force: bool = False, **kw):

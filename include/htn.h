@@ -271,7 +271,8 @@ int32_t htn_gradient_grassmann(htn_ctx* ctx, int32_t nsites, htn_tensor* const* 
                                double* log, int32_t log_cap);
 /* Replaces: `find_groundstate(psi, H, IDMRG2(trscheme = truncbelow(cut), tol, maxiter))`
  * (HubbardFunctions.jl:1010): two-site infinite DMRG over a unit cell of nsites >= 2 with bond spaces
- * re-defined by the truncated SVD (keep Schmidt values >= cut, at most maxdim multiplets if maxdim > 0).
+ * re-defined by the truncated SVD (keep Schmidt values >= cut, at most maxdim multiplets if maxdim > 0, at most a full
+ * dimension of |maxdim| if maxdim < 0).
  * In/out handle arrays: the library destroys every tensor it replaces and stores the new handle; the
  * caller destroys the final ones.  delta = || C_new - C_old || on the common subspace of the edge bond.
  * log (may be NULL): rows of 8 doubles (delta, sum of D_red over the bonds, cumulative H_AC2 applies, cumulative
@@ -291,6 +292,16 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
 int32_t htn_mixed_gauge(htn_ctx* ctx, int32_t nsites, htn_tensor* const* AL, const htn_tensor* C_guess,
                         htn_tensor* const* AR, htn_tensor* const* C, htn_tensor* const* AC, int32_t from_right,
                         double tol, int32_t maxiter, int32_t* iterations);
+/* Replaces: `changebonds(psi, SvdCut(; trscheme))` (kind 0; HubbardFunctions.jl:1013,1018,1365) and
+ * `changebonds(psi, H, VUMPSSvdCut(; trscheme))` (kind 1; HubbardFunctions.jl:1016,1363; unit cells of >= 2 sites, MPSKit
+ * `changebonds_n`).  trscheme: cut > 0 = truncbelow(cut) relative to the norm of the two-site tensor; maxdim > 0 caps the
+ * kept multiplets sum_c n_c per bond; maxdim < 0 = truncdim(|maxdim|): caps the FULL dimension sum_c dim(c) n_c (what
+ * TensorKit counts and `dim_state` reports, HF:1363-1365, 1402).  The kept set is decided in one pass from the singular
+ * values.  In/out handle arrays as in htn_idmrg2 (replaced tensors are destroyed by the library); on return the state is a
+ * consistent uniform MPS in mixed gauge.  krylovdim / eig_tol (kind 1; <= 0: 30 / 1e-10), tol_gauge (<= 0: 1e-12). */
+int32_t htn_changebonds(htn_ctx* ctx, int32_t kind, int32_t nsites, htn_tensor** AL, htn_tensor** AR, htn_tensor** C,
+                        htn_tensor** AC, const htn_mpo* const* W, double cut, int32_t maxdim, int32_t krylovdim,
+                        double eig_tol, double tol_gauge);
 /* Replaces: `expectation_value(psi, i => op)` (HubbardFunctions.jl:1448-1449,1507,1533) for one-site
  * operators that are scalars on every physical multiplet (n, n_up, n_dn): values[s] per multiplet s. */
 int32_t htn_expval_diag(const htn_tensor* AC, const double* values, int32_t nvalues, double* out);

@@ -253,3 +253,39 @@ def test_save_and_load_state_round_trip(ctx, tmp_path):
         a, b = hf.entanglement_spectrum(psi, i), hf.entanglement_spectrum(back, i)
         for s, v in a.items():
             assert np.allclose(b[s], v, atol=1e-9)
+
+
+def test_changebonds_c_abi_full_dimension_cap(ctx):
+    """htn_changebonds: SvdCut and VUMPSSvdCut in one library call with `truncdim` counting the FULL
+    dimension (maxdim < 0), decided in one pass per bond.  kind 0 with nothing to cut is the identity on the state; with
+    a cap every bond's full dimension (what `dim_state` reports, HF:1402) is <= the cap and the largest Schmidt values
+    are the ones kept; kind 1 respects the same cap and does not end above kind 0 in energy.  The inputs survive."""
+    import numpy as np
+    from hubbardtn_b200 import device as dev
+    model = hf.OB_Sim([1.0], [5.0], 0.0, [0.0], 1, 1, 2.5)
+    d = hf.produce_groundstate(model, ctx=ctx, force=True)
+    psi, H = d["groundstate"], d["ham"]
+
+    def energy(p):
+        GL, GR = hf._make_envs(ctx, p, H)
+        e = dev.environments(ctx, p.AL, p.AR, p.C, H.W, GL, GR, tol=1e-12)
+        return 0.5 * (e["energy_cell_left"] + e["energy_cell_right"]) / len(p)
+
+    E = energy(psi)
+    same = hf.InfiniteMPS(ctx, psi.sym, *dev.changebonds(ctx, 0, psi.AL, psi.AR, psi.C, psi.AC, H.W, cut=1e-13))
+    assert abs(energy(same) - E) < 1e-9
+    full = max(hf.dim_state(psi))
+    cap = max(6, full // 2)
+    cut0 = hf.InfiniteMPS(ctx, psi.sym, *dev.changebonds(ctx, 0, psi.AL, psi.AR, psi.C, psi.AC, H.W, maxdim=-cap))
+    cut1 = hf.InfiniteMPS(ctx, psi.sym, *dev.changebonds(ctx, 1, psi.AL, psi.AR, psi.C, psi.AC, H.W, maxdim=-cap))
+    for c in (cut0, cut1):
+        assert max(hf.dim_state(c)) <= cap < full
+        n = hf.density_state(c)
+        assert abs(sum(n) / len(n) - 1.0) < 1e-8
+    # one more multiplet of the smallest kept sector would not have fitted: the cap is used, not undershot by a search
+    assert max(hf.dim_state(cut0)) > cap - 4
+    E0, E1 = energy(cut0), energy(cut1)
+    assert E - 1e-10 < E1 < E0 + 1e-6 < E + 0.05
+    assert abs(energy(psi) - E) < 1e-12                      # the caller's state is untouched
+    with pytest.raises(Exception):
+        dev.changebonds(ctx, 2, psi.AL, psi.AR, psi.C, psi.AC, H.W)

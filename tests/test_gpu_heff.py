@@ -162,3 +162,32 @@ def test_error_paths(ctx):
         case.x.upload(np.zeros(3))
     with pytest.raises(_lib.HtnError):
         device.Space(ctx, 0, {(0, -1, 0): 2})
+
+
+def test_heff_ac_one_cta_shape_in_a_subprocess():
+    """The other shape of the fused stage L+W kernel (HTN_STACK_NG=2: two consumer groups on one slab, mixers fed by
+    cp.async.bulk through shared memory, tile-level wave reports) is selected per process: run the C4-shape parity check
+    of `test_heff_ac_full_size_properties`'s little brother in a child process with the switches set."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from hubbardtn_b200 import device, sectors, synthetic\n"
+        "from oracle import bridge, heff\n"
+        "from util import oracle_view, table\n"
+        "ctx = device.Context(0)\n"
+        "case = synthetic.HeffCase(ctx, sectors.SU2U1, D=256, chi=16)\n"
+        "case.plan.apply(case.x, case.y)\n"
+        "y = case.y.download()\n"
+        "ov = oracle_view(case)\n"
+        "ref = bridge.mps_to_packed(heff.HeffACPlan(ov['GL'], ov['W'], ov['GR'], ov['x']).apply(ov['x']), table(case.y))\n"
+        "err = float(np.abs(y - ref).max() / np.abs(ref).max())\n"
+        "print('ERR', err)\n"
+        "assert err < 1e-12, err\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({"HTN_STACK_NG": "2"}, {"HTN_STACK_NG": "2", "HTN_TILE_WAVES": "1", "HTN_WAVE_MB": "2"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, (extra, out.stdout[-2000:], out.stderr[-2000:])
