@@ -381,7 +381,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        import faulthandler
+        faulthandler.dump_traceback_later(240, exit=True)      # a rank stuck in a collective: dump where, and leave
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
 
     from hubbardtn_b200 import device, synthetic
     from hubbardtn_b200 import sharding
@@ -451,15 +454,17 @@ def main():
     ms = run_steps(args.steps)
     barrier()
     t_hi = time.time()
-    reps_more = int(1.0 / max(ms / args.steps * 1e-3, 1e-6))   # ~1 s more of the same loop for the clock samples
-    run_steps(max(1, reps_more))
-    t_end = time.time()
-    sampler.window, sampler.timed = (t_lo, t_end), (t_lo, t_hi)
-    clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    # ~1 s more of the same loop for the clock samples; the count must be the SAME on every rank (the loop holds one
+    # collective per step), so it is derived from the max-over-ranks time, not from the local one
+    reps_more = int(1.0 / max(ms_max / args.steps * 1e-3, 1e-6))
+    run_steps(max(1, reps_more))
+    t_end = time.time()
+    sampler.window, sampler.timed = (t_lo, t_end), (t_lo, t_hi)
+    clocks = sampler.stop()
     value = (1 if strong else world) * args.steps / (ms_max * 1e-3)
     checksum_dev = float(y_t.sum().item())                     # of the (reduced) y left by the timed loop
 
@@ -616,6 +621,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
     return 0
 
 
