@@ -59,8 +59,8 @@ struct SlCfg {
   static constexpr int THREADS = WARPS * 32;
   static constexpr int RING_ELEMS = NG * SL_STAGES * SL_STAGE_ELEMS;
   static constexpr int MIXSTAGE_BYTES = NG == 1 ? 0 : NMIX * SLM_SLOTS * SLM_SLOT_BYTES;
-  static constexpr int NBAR = NG * 2 * SL_STAGES + 2 * SL_JOBQ + (NG == 1 ? 0 : (NMIX + NCONS) * SLM_SLOTS);
-  static constexpr int SMEM_BYTES = (RING_ELEMS + SL_SLAB) * 8 + MIXSTAGE_BYTES + NBAR * 8 + SL_JOBQ * SL_JOBWORDS * 4 + 16;
+  static constexpr int NBAR = NG * 2 * SL_STAGES + 2 * SL_JOBQ + (NG == 1 ? WARPS * SLM_SLOTS : (NMIX + NCONS) * SLM_SLOTS);
+  static constexpr int SMEM_BYTES = (RING_ELEMS + SL_SLAB) * 8 + MIXSTAGE_BYTES + NBAR * 8 + SL_JOBQ * SL_JOBWORDS * 4 + 32;
   static constexpr int CTAS_PER_SM = NG == 1 ? 2 : 1;
 };
 // 2 CTAs per SM need 2 x (this + 1 KB) <= 228 KB: the slab leaves no room for per-warp staging of the mix sources
@@ -356,10 +356,18 @@ __device__ __forceinline__ void sl_mix_chunk(const StackArgs& a, const MixChunk&
 // PROF (HTN_STACK_DEBUG & 32, a separate instantiation so that the product loop carries none of it): clocks spent per
 // chunk on ticket + record, on the wave wait and on the data, summed into the probe slots behind the wave counters.
 template <int U, bool PROF>
-__device__ __forceinline__ void sl_mixer_loop_t(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
+__device__ __forceinline__ bool sl_mixer_loop_t(const StackArgs& a, const Bases& bases, int lane, int nwarps_total,
+                                                const volatile int* switch_flag = nullptr) {
   const unsigned long long base = (a.epoch - 1ull) * (unsigned long long)(a.nmix + nwarps_total);
   long long c_desc = 0, c_wait = 0, c_work = 0, n_chunks = 0;
+  bool switched = false;
   while (true) {
+    // the CTA's shared memory has become free (all jobs done): leave before drawing a ticket, the caller carries on with the
+    // bulk-copy fed loop
+    if (switch_flag && __shfl_sync(0xffffffffu, *switch_flag, 0)) {
+      switched = true;
+      break;
+    }
     const long long t0 = PROF ? clock64() : 0;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(a.ctr + 1, 1ull) - base;
@@ -409,17 +417,18 @@ __device__ __forceinline__ void sl_mixer_loop_t(const StackArgs& a, const Bases&
     atomicAdd(d + 6, (unsigned long long)c_work);
     atomicAdd(d + 7, (unsigned long long)n_chunks);
   }
+  return switched;
 }
 template <int U>
-__device__ __forceinline__ void sl_mixer_loop_prof(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
-  sl_mixer_loop_t<U, true>(a, bases, lane, nwarps_total);
+__device__ __forceinline__ bool sl_mixer_loop_prof(const StackArgs& a, const Bases& bases, int lane, int nwarps_total,
+                                                   const volatile int* switch_flag) {
+  return sl_mixer_loop_t<U, true>(a, bases, lane, nwarps_total, switch_flag);
 }
 template <int U>
-__device__ __forceinline__ void sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total) {
-  if (a.dbg & 32)
-    sl_mixer_loop_prof<U>(a, bases, lane, nwarps_total);
-  else
-    sl_mixer_loop_t<U, false>(a, bases, lane, nwarps_total);
+__device__ __forceinline__ bool sl_mixer_loop(const StackArgs& a, const Bases& bases, int lane, int nwarps_total,
+                                              const volatile int* switch_flag = nullptr) {
+  if (a.dbg & 32) return sl_mixer_loop_prof<U>(a, bases, lane, nwarps_total, switch_flag);
+  return sl_mixer_loop_t<U, false>(a, bases, lane, nwarps_total, switch_flag);
 }
 
 // ---- mixers of the one-CTA shape: sources staged through shared memory by cp.async.bulk ----
@@ -592,6 +601,7 @@ __global__ void __launch_bounds__(SlCfg<NG>::THREADS, SlCfg<NG>::CTAS_PER_SM)
   uint64_t* jempty = jfull + SL_JOBQ;
   uint64_t* mixbar = jempty + SL_JOBQ;                      // [NMIX][SLM_SLOTS] (NG = 2)
   int* job_slot = reinterpret_cast<int*>(bars + Cfg::NBAR);  // SL_JOBQ records
+  volatile int* smem_free = job_slot + SL_JOBQ * SL_JOBWORDS;  // NG = 1: set when rings and slab may be reused as mix staging
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dbg = a.dbg;
   // the rings must never hold NaN patterns: K tails multiply stale columns by the zero rows of the slab
@@ -605,8 +615,8 @@ __global__ void __launch_bounds__(SlCfg<NG>::THREADS, SlCfg<NG>::CTAS_PER_SM)
       sl_mbar_init(&jfull[s], 1);
       sl_mbar_init(&jempty[s], NCONS + NPROD - 1);
     }
-    if (NG > 1)
-      for (int s = 0; s < (Cfg::NMIX + NCONS) * SLM_SLOTS; ++s) sl_mbar_init(&mixbar[s], 1);
+    for (int s = 0; s < (NG == 1 ? Cfg::WARPS : Cfg::NMIX + NCONS) * SLM_SLOTS; ++s) sl_mbar_init(&mixbar[s], 1);
+    *smem_free = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic zero fill before async-proxy (TMA) writes
@@ -690,7 +700,20 @@ __global__ void __launch_bounds__(SlCfg<NG>::THREADS, SlCfg<NG>::CTAS_PER_SM)
     }
     // no stack jobs left: help with the mix (the last wave's targets are still to be formed)
     if (a.nmix > 0) {
-      if (NG == 1 || (dbg & 64)) {
+      if (NG == 1 && !(dbg & 64)) {
+        // every consumer warp has left its last tile: ring and slab (112 KB) are free.  They become staging slots of the
+        // bulk-copy fed mix loop for all eight warps of the CTA (the mixers and the producer switch over at their next chunk)
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NCONS * 32) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (tid == 0) {
+          *smem_free = 1;
+          __threadfence_block();
+        }
+        sl_mixer_loop_tma(a, bases, lane, nwarps_total, reinterpret_cast<unsigned char*>(sl_sm) + warp * SLM_SLOTS * SLM_SLOT_BYTES,
+                          mixbar + warp * SLM_SLOTS);
+      } else if (NG == 1) {
+        sl_mixer_loop<8>(a, bases, lane, nwarps_total);
+      } else if (dbg & 64) {
         sl_mixer_loop<8>(a, bases, lane, nwarps_total);
       } else {
         // every consumer warp has left its last tile: rings and slab (144 KB) are free and become staging slots, so the
@@ -816,10 +839,18 @@ __global__ void __launch_bounds__(SlCfg<NG>::THREADS, SlCfg<NG>::CTAS_PER_SM)
           }
         }
       }
-      if (a.nmix > 0 && NG == 1) sl_mixer_loop<8>(a, bases, lane, nwarps_total);
+      if (a.nmix > 0 && NG == 1) {
+        if (sl_mixer_loop<8>(a, bases, lane, nwarps_total, (dbg & 64) ? nullptr : smem_free))
+          sl_mixer_loop_tma(a, bases, lane, nwarps_total, reinterpret_cast<unsigned char*>(sl_sm) + warp * SLM_SLOTS * SLM_SLOT_BYTES,
+                            mixbar + warp * SLM_SLOTS);
+      }
     } else if (a.nmix > 0) {
       // =========================== MIXERS (stage W) ===========================
-      if (NG == 1 || (dbg & 64)) {
+      if (NG == 1) {
+        if (sl_mixer_loop<8>(a, bases, lane, nwarps_total, (dbg & 64) ? nullptr : smem_free))
+          sl_mixer_loop_tma(a, bases, lane, nwarps_total, reinterpret_cast<unsigned char*>(sl_sm) + warp * SLM_SLOTS * SLM_SLOT_BYTES,
+                            mixbar + warp * SLM_SLOTS);
+      } else if (dbg & 64) {
         sl_mixer_loop<8>(a, bases, lane, nwarps_total);
       } else {
         const int mw = warp - NCONS - NPROD;
