@@ -84,7 +84,7 @@ def hamiltonian_dense(simul: OB_Sim):
     (HF:424-444) as an upper-triangular MPO W[a, s', s, b] with explicit Jordan-Wigner strings.
     Returns (W dense, level sectors)."""
     if simul.period != 0 or "U13" in simul.kwargs or any(abs(j) > 0 for j in simul.J):
-        raise NotImplementedError("exchange / U13 terms (HF:445-457) are not mirrored yet; helix and staggered field go "
+        raise NotImplementedError("U13 terms (HF:452-457) are not mirrored yet; helix, staggered field and exchange go "
                                   "through ob_extended_terms")
     sym, Q = simul.sym, simul.Q
     cu, cd, par, num, dbl = _fermion_ops(sym)
@@ -187,16 +187,33 @@ class MB_Sim:
         return (self.Q if self.P % 2 == 0 else 2 * self.Q) * self.bands          # HF:829-834, InfiniteStrip(B, T*B)
 
 
-def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict):
+def _spin_ops(sym: int):
+    """(S^+, S^-, S^z, Delta^+) as 4x4 matrices in the local basis of `_fermion_ops`; Delta^+ = c+_up c+_dn creates the
+    doubly occupied state (|double> = c+_up c+_dn |0>)."""
+    cu, cd, par, num, dbl = _fermion_ops(sym)
+    sp = cu.T @ cd                      # S^+ = c+_up c_dn
+    sz = 0.5 * (cu.T @ cu - cd.T @ cd)
+    dp = cu.T @ cd.T                    # Delta^+
+    return sp, sp.T, sz, dp
+
+
+def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict, spins: dict = None, pairs: dict = None):
     """Finite-state-machine MPO of  sum_p onsite[p] + sum c (c+_{p,s} c_{p+d,s} + h.c.) + sum v n_p n_{p+d}
-    on a chain with an L-site unit cell (L = len(onsite)).  hops / dens: {(p mod L, d >= 1): coefficient}.
+    + sum g S_p . S_{p+d} + sum h (Delta+_p Delta_{p+d} + h.c.)
+    on a chain with an L-site unit cell (L = len(onsite)).  hops / dens / spins / pairs: {(p mod L, d >= 1): coefficient}.
+    The spin-spin term travels on a triplet level (0, j=1, 0) whose three dense members carry the spherical components
+    S^(q), q = -1, 0, +1, on the opening site and their adjoints on the closing site (U(1)xU(1): three abelian levels
+    S^z, S^+, S^-); the pair term on the two scalar levels of charge +-2Q.  Both are bosonic: identity fillers.
     A level (kind, d) means "d more sites until the term closes"; the coefficient sits on the opening
     site, so every site shares the level list and only the dense entries differ.  Fermionic pairs carry
     an explicit Jordan-Wigner parity string.  Returns ([W_p dense (chi,4,4,chi)], level sectors)."""
     L = len(onsite)
     cu, cd, par, num, dbl = _fermion_ops(sym)
+    spins, pairs = spins or {}, pairs or {}
     dh = max([d for (_, d) in hops] + [0])
     dn = max([d for (_, d) in dens] + [0])
+    ds = max([d for (_, d) in spins] + [0])
+    dp_ = max([d for (_, d) in pairs] + [0])
     levels = [(0, 0, 0)]
     first = {}
 
@@ -210,6 +227,11 @@ def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict):
         add(("B", d), [(1, 1, -Q)] if sym == S.SU2U1 else [(1, -1, -Q), (1, 1, -Q)])
     for d in range(1, dn + 1):
         add(("N", d), [(0, 0, 0)])
+    for d in range(1, ds + 1):
+        add(("S", d), [(0, 2, 0)] if sym == S.SU2U1 else [(0, -2, 0), (0, 0, 0), (0, 2, 0)])
+    for d in range(1, dp_ + 1):
+        add(("Dp", d), [(0, 0, 2 * Q)])
+        add(("Dm", d), [(0, 0, -2 * Q)])
     levels.append((0, 0, 0))
     off, acc = [], 0
     for s in levels:
@@ -250,6 +272,35 @@ def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict):
                 W[n_, :, :, off[first[("N", d - 1)]]] = np.eye(4)
             else:
                 W[n_, :, :, end] = num
+        if ds:
+            sp, sm, sz, _ = _spin_ops(sym)
+            # spherical components q = -1, 0, +1 (dense members of the triplet in this order) and their adjoints:
+            # sum_q S^(q)_i (S^(q))^+_j = S_i . S_j
+            sph = [sm / np.sqrt(2.0), sz, -sp / np.sqrt(2.0)]
+            for d in range(1, ds + 1):
+                s0 = off[first[("S", d)]]
+                g = spins.get((p, d), 0.0)
+                for q in range(3):
+                    if g != 0.0:
+                        W[0, :, :, s0 + q] = g * sph[q]
+                    if d > 1:
+                        W[s0 + q, :, :, off[first[("S", d - 1)]] + q] = np.eye(4)
+                    else:
+                        W[s0 + q, :, :, end] = sph[q].T
+        if dp_:
+            _, _, _, dpl = _spin_ops(sym)
+            for d in range(1, dp_ + 1):
+                a, b = off[first[("Dp", d)]], off[first[("Dm", d)]]
+                h = pairs.get((p, d), 0.0)
+                if h != 0.0:
+                    W[0, :, :, a] = h * dpl          # Delta+_p ... Delta_{p+d}
+                    W[0, :, :, b] = h * dpl.T        # h.c.
+                if d > 1:
+                    W[a, :, :, off[first[("Dp", d - 1)]]] = np.eye(4)
+                    W[b, :, :, off[first[("Dm", d - 1)]]] = np.eye(4)
+                else:
+                    W[a, :, :, end] = dpl.T
+                    W[b, :, :, end] = dpl
         Ws.append(W)
     return Ws, levels
 
@@ -257,19 +308,35 @@ def fsm_mpo_dense(sym: int, Q: int, onsite: list, hops: dict, dens: dict):
 def mb_terms(simul: MB_Sim):
     """Term lists of the multi-band Hamiltonian (HF:811-910) on the chain p = band + cell * B:
     on-band U and band energies (HF:531-551, 852-870), on-site and inter-site hopping (HF:477-519), direct
-    on-site and inter-site interactions (HF:542-561, 645-659).  Exchange, U_ijjj and the three-/four-band
-    dictionaries (HF:563-643, 662-809) are not mirrored."""
+    on-site and inter-site interactions (HF:542-561, 645-659), on-site and inter-site exchange (HF:563-616, 668-700).
+    U_ijjj and the three-/four-band dictionaries (HF:617-643, 702-809) are not mirrored.
+
+    Exchange: the reference contracts two hopping tensors into `C4_1 = sum_ss' c+_is c+_js' c_is' c_js` (HF:580, 675) and
+    `C4_2 = sum_ss' c+_is c+_is' c_js' c_js` (HF:604, 690).  In operators C4_1 = -(2 S_i.S_j + n_i n_j / 2) and
+    C4_2{i,j} + C4_2{j,i} = 2 (Delta+_i Delta_j + h.c.), so a pair with exchange integral J carries
+    -2J S_i.S_j - (J/2) n_i n_j + J (Delta+_i Delta_j + h.c.)  (Hund's coupling and pair hopping of the Kanamori form).
+    The signs are those of the second-quantised operators the terms are named after; TensorKit's fermionic braiding signs
+    of the `@tensor` lines cannot be checked without Julia (no reference golden has J != 0).
+    Returns (onsite, hops, dens, spins, pairs)."""
     B, L = simul.bands, simul.unit_cell
-    if np.any(simul.J != 0) or np.any(simul.U13 != 0) or any(k in simul.kwargs for k in ("U112", "U1111", "U13_IS")):
-        raise NotImplementedError("exchange / U_ijjj / U_ijkk / U_ijkl terms (HF:563-643, 662-809) are not mirrored yet")
+    if np.any(simul.U13 != 0) or any(k in simul.kwargs for k in ("U112", "U1111", "U13_IS")):
+        raise NotImplementedError("U_ijjj / U_ijkk / U_ijkl terms (HF:617-643, 702-809) are not mirrored yet")
+    if np.any(np.diag(simul.J[:, :B]) != 0):
+        raise ValueError("On-band interaction is not taken into account in Exchange_OS.")    # HF:575 (a warning there)
     _, _, _, num, dbl = _fermion_ops(simul.sym)
     t, u = simul.t, simul.u
     onsite = [u[p % B, p % B] * dbl - t[p % B, p % B] * num for p in range(L)]      # OB_interaction + Chem_pot
-    hops, dens = {}, {}
+    hops, dens, spins, pairs = {}, {}, {}, {}
+    J = simul.J
 
     def acc(dct, p, d, c):
         if c != 0.0:
             dct[(p % L, d)] = dct.get((p % L, d), 0.0) + c
+
+    def exchange(p, d, j):
+        acc(spins, p, d, -2.0 * j)
+        acc(dens, p, d, -0.5 * j)
+        acc(pairs, p, d, j)
 
     for cell in range(L // B):
         for bi in range(B):
@@ -277,6 +344,7 @@ def mb_terms(simul: MB_Sim):
                 p = cell * B + bi
                 acc(hops, p, bf - bi, -0.5 * (t[bi, bf] + t[bf, bi]))                  # OS_Hopping (both orders of (bi,bf))
                 acc(dens, p, bf - bi, 0.5 * (u[bi, bf] + u[bf, bi]))                   # Direct_OS: U_av on the lower triangle
+                exchange(p, bf - bi, 0.5 * (J[bi, bf] + J[bf, bi]))                    # Exchange_OS: 0.5 J over both orders
         for k in range(1, t.shape[1] // B):
             for bi in range(B):
                 for bf in range(B):
@@ -285,7 +353,11 @@ def mb_terms(simul: MB_Sim):
             for bi in range(B):
                 for bf in range(B):
                     acc(dens, cell * B + bi, k * B + bf - bi, u[bi, k * B + bf])       # Direct_IS
-    return onsite, hops, dens
+        for k in range(1, J.shape[1] // B):
+            for bi in range(B):
+                for bf in range(B):
+                    exchange(cell * B + bi, k * B + bf - bi, J[bi, k * B + bf])        # Exchange_IS
+    return onsite, hops, dens, spins, pairs
 
 
 def ob_extended_terms(simul: OB_Sim):
@@ -296,10 +368,10 @@ def ob_extended_terms(simul: OB_Sim):
     cu, cd, par, num, dbl = _fermion_ops(simul.sym)
     t, u = list(simul.t), list(simul.u)
     JMs = simul.kwargs.get("JMs", (0.0, 0.0))
-    if any(abs(j) > 0 for j in simul.J) or "U13" in simul.kwargs:
-        raise NotImplementedError("exchange / U13 terms (HF:445-457) are not mirrored yet")
+    if "U13" in simul.kwargs:
+        raise NotImplementedError("U13 terms (HF:452-457) are not mirrored yet")
     onsite = [(u[0] if u else 0.0) * dbl - simul.mu * num for _ in range(L)]
-    hops, dens = {}, {}
+    hops, dens, spins, pairs = {}, {}, {}, {}
     if simul.period != 0:
         if len(t) != 1 or len(u) != 1:
             raise ValueError("Extended models in 2D not implemented.")            # HF:467
@@ -314,11 +386,18 @@ def ob_extended_terms(simul: OB_Sim):
             for r, ur in enumerate(u[1:], start=1):
                 if ur != 0.0:
                     dens[(p, r)] = ur
+    if simul.period == 0:
+        for p in range(L):
+            for r, jr in enumerate(simul.J, start=1):                  # HF:445-450: J1 + J2 at range r (see mb_terms)
+                if jr != 0.0:
+                    spins[(p, r)] = spins.get((p, r), 0.0) - 2.0 * jr
+                    dens[(p, r)] = dens.get((p, r), 0.0) - 0.5 * jr
+                    pairs[(p, r)] = pairs.get((p, r), 0.0) + jr
     if JMs[1] != 0.0 and simul.spin:
         sz = 0.5 * (cu.T @ cu - cd.T @ cd)
         for p in range(L):
             onsite[p] = onsite[p] + JMs[0] * JMs[1] * (-1.0) ** (p + 1) * sz
-    return onsite, hops, dens
+    return onsite, hops, dens, spins, pairs
 
 
 class Hamiltonian:
@@ -328,7 +407,8 @@ class Hamiltonian:
         self.simul, self.sym = simul, simul.sym
         if isinstance(simul, MB_Sim):
             Wd, self.levels = fsm_mpo_dense(self.sym, simul.Q, *mb_terms(simul))
-        elif simul.period != 0 or (simul.kwargs.get("JMs", (0.0, 0.0))[1] != 0.0 and simul.spin):
+        elif (simul.period != 0 or (simul.kwargs.get("JMs", (0.0, 0.0))[1] != 0.0 and simul.spin)
+              or any(abs(j) > 0 for j in simul.J)):
             Wd, self.levels = fsm_mpo_dense(self.sym, simul.Q, *ob_extended_terms(simul))
         else:
             W1, self.levels = hamiltonian_dense(simul)

@@ -289,3 +289,27 @@ def test_changebonds_c_abi_full_dimension_cap(ctx):
     assert abs(energy(psi) - E) < 1e-12                      # the caller's state is untouched
     with pytest.raises(Exception):
         dev.changebonds(ctx, 2, psi.AL, psi.AR, psi.C, psi.AC, H.W)
+
+
+def test_polyacetylene_model_with_exchange_both_symmetries(ctx):
+    """The reference's example model (examples/polyacetylene.jl:29-31 = BASELINE config C4's Hamiltonian: two bands, hopping,
+    direct AND exchange interactions, chi = 10 MPO levels with a triplet and two pair-hopping levels) through the reference
+    schedule on the GPU.  No golden exists for it; the check is internal: the U(1)xSU(2) run (spin-spin term on a triplet
+    level, reduced by Wigner-Eckart) and the U(1)xU(1) run (three abelian levels) are different code paths for the same
+    Hamiltonian and must agree on the energy per site; filling is conserved; switching the exchange off changes the energy."""
+    import numpy as np
+    t = np.array([[0.000, 3.803, -0.548, 0.000], [3.803, 0.000, 2.977, -0.501]])
+    U = np.array([[10.317, 6.264, 0.000, 0.000], [6.264, 10.317, 6.162, 0.000]])
+    J = np.array([[0.000, 0.123, 0.000, 0.000], [0.123, 0.000, 0.113, 0.000]])
+    E = {}
+    for spin in (False, True):
+        model = hf.MB_Sim(t, U, J, None, 1, 1, 2.5, 20, kwargs={"spin": spin})
+        d = hf.compute_groundstate(model, ctx=ctx, tol=1e-7)
+        assert len(d["groundstate"]) == 4 and d["ham"].chi == (10 if not spin else 16)
+        n = hf.density_state(d["groundstate"])
+        assert abs(sum(n) / 4 - 1.0) < 1e-8
+        assert d["delta"] < 1e-5
+        E[spin] = d["energy"]
+    assert abs(E[False] - E[True]) < 2e-3, E                 # truncation-limited (svalue 2.5), not term-limited
+    d0 = hf.compute_groundstate(hf.MB_Sim(t, U, np.zeros((2, 4)), None, 1, 1, 2.5, 20), ctx=ctx, tol=1e-7)
+    assert abs(d0["energy"] - E[False]) > 1e-3               # the exchange terms are felt
