@@ -2,6 +2,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -66,17 +67,21 @@ int32_t htn_ctx_create(int32_t device, htn_ctx** out) {
     return HTN_ERR_CUDA;
   }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-  if (prop.major < 10) {
-    g_noctx_err = "libhtn is built for sm_100a only";
+  const bool have_prop = cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+  if (have_prop) c->sm_count = prop.multiProcessorCount;
+  // the library holds one sm_100a cubin and no PTX: any other device would fail later with "no kernel image"
+  if (!have_prop || prop.major != 10 || prop.minor != 0) {
+    g_noctx_err = "libhtn is built for sm_100a (B200) only";
     cudaStreamDestroy(c->stream);
     delete c;
     return HTN_ERR_NO_DEVICE;
   }
-  cudaMallocHost(&c->red_host, 64 * sizeof(double));
-  cudaMalloc(&c->kry_scal, 8192 * sizeof(double));
-  cudaMallocHost(&c->kry_scal_host, 8192 * sizeof(double));
-  cudaMalloc(&c->d_status, sizeof(int));
+  if (cudaMallocHost(&c->red_host, 64 * sizeof(double)) != cudaSuccess || cudaMalloc(&c->kry_scal, 8192 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&c->kry_scal_host, 8192 * sizeof(double)) != cudaSuccess || cudaMalloc(&c->d_status, sizeof(int)) != cudaSuccess) {
+    g_noctx_err = "context allocation failed";
+    htn_ctx_destroy(c);
+    return HTN_ERR_OOM;
+  }
   cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
   *out = c;
   return HTN_OK;
@@ -311,7 +316,7 @@ static int32_t finalize_tensor(htn_tensor* t) {
 }
 
 static htn_tensor* new_tensor(htn_ctx* ctx, int kind, int sym) {
-  static uint64_t next_uid = 0;
+  static std::atomic<uint64_t> next_uid{0};
   htn_tensor* t = new htn_tensor();
   t->ctx = ctx;
   t->uid = ++next_uid;

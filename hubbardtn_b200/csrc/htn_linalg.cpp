@@ -40,7 +40,10 @@ static int32_t cached_table(htn_tensor* owner, const void* partner, int mode, co
   T* d = nullptr;
   if (!host.empty()) {
     if (cudaMalloc(&d, host.size() * sizeof(T)) != cudaSuccess) return ctx->fail(HTN_ERR_OOM, "device table allocation failed");
-    h2d_on_stream(d, host.data(), host.size() * sizeof(T), ctx->stream);
+    if (h2d_on_stream(d, host.data(), host.size() * sizeof(T), ctx->stream) != cudaSuccess) {  // do not cache a table that never arrived
+      cudaFree(d);
+      return ctx->fail(HTN_ERR_CUDA, "device table upload failed");
+    }
   }
   owner->devtables[key] = {d, (int)host.size()};
   *dev = d;

@@ -195,6 +195,9 @@ static int32_t run2(Program* pg, const double* a, double* b) {
   return pg->run(slots);
 }
 
+// the device flag is sticky: an early return between a QR launch and its check must not leak into the next driver call
+static void clear_qr_status(htn_ctx* ctx) { cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream); }
+
 static int32_t check_qr_status(htn_ctx* ctx) {
   int st = 0;
   cudaMemcpyAsync(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -315,6 +318,7 @@ struct Uniform {
 
   // AL -> (AR, C): iterated LQ through the unit cell (oracle/mps.py:uniform_rightorth)
   int32_t rightorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
+    clear_qr_status(ctx);
     cudaStream_t st = ctx->stream;
     RC(t_copy(C_guess, C[L - 1]));
     RC(t_normalize(C[L - 1], C[L - 1]->d));
@@ -376,6 +380,7 @@ struct Uniform {
 
   // AR -> (AL, C): iterated positive QR through the unit cell (oracle/mps.py:uniform_leftorth)
   int32_t leftorth(const htn_tensor* C_guess, double tol, int maxiter, int* iters, double* delta_out) {
+    clear_qr_status(ctx);
     cudaStream_t st = ctx->stream;
     std::vector<Program*> mulL;
     for (int i = 0; i < L; ++i) {
@@ -683,6 +688,7 @@ int32_t htn_qrpos(const htn_tensor* A, htn_tensor* Q, htn_tensor* R) {
   if (A->kind != HTN_T_MPS && A->kind != HTN_T_BOND) return ctx->fail(HTN_ERR_INVALID, "qrpos: A must be an MPS or bond tensor");
   if (!htn_same_structure(A, Q)) return ctx->fail(HTN_ERR_SHAPE, "qrpos: Q must have the structure of A");
   cudaSetDevice(ctx->device);
+  clear_qr_status(ctx);
   RC(t_copy(A, Q));
   RC(t_qr_inplace(Q, R));
   return check_qr_status(ctx);
