@@ -131,6 +131,30 @@ static LeftFront build_front(Program& pg, const htn_tensor* like, const EnvView&
       by_xi[xi].push_back((int)ti);
     }
   }
+  // ---- the stacked kernel pays off only when there are enough 64-row tiles to keep its 296 persistent CTAs busy with
+  // multi-tile jobs (C4-synthetic, chi = 96: 16.5 k tiles).  On a small MPO -- the reference's polyacetylene model has
+  // chi = 10: ~2 k tiles, one job per CTA -- the classic grouped GEMM with its static balanced schedule is 3.7x faster for
+  // stage L (0.036 ms against 0.133 ms at D_red = 1024; gpurun_out/r2_real_c4_variants.txt), so those plans stay classic.
+  {
+    static long long min_tiles = -1;
+    if (min_tiles < 0) {
+      const char* e = getenv("HTN_STACK_MIN_TILES");
+      min_tiles = e ? atoll(e) : 7000;
+    }
+    long long tiles = 0;
+    for (auto& kv : by_xi) {
+      const Block& xb = like->blocks[kv.first];
+      long long rows = 0;
+      for (int ti : kv.second) rows += tb[ti].rows;
+      const int l = std::get<2>(tkeys[kv.second[0]]);
+      const int atoms = (xb.cols + 7) / 8, maxat = std::max(1, stack_max_atoms(G->panels[l].cols));
+      tiles += (rows + 63) / 64 * ((atoms + maxat - 1) / maxat);
+    }
+    if (tiles < min_tiles) {
+      by_xi.clear();
+      std::fill(is_stacked.begin(), is_stacked.end(), 0);
+    }
+  }
   // ---- waves.  Wave 0: the jobs of the LIGHT panels (contracted multiplicity <= 16: hardly any flops or bytes, but
   // many rows) -- one run per x block, every mix target waits for it.  Waves 1..: the left sectors lp grouped by the
   // bytes of heavy T they own (heavy sectors first); a target of sector lp waits for wave_of_lp[lp] (and wave 0).
