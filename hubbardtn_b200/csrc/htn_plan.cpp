@@ -578,7 +578,7 @@ static void build_heff_backend(Program& pg, const htn_tensor* like, const htn_te
     }
     pg.add_mix(mixU, TAG_W);
   }
-  pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y);
+  pg.add_gemm_reduce(tasksR, yextra, TAG_R, TAG_Y, true);
   *n_u_out = n_u;
   *n_mix_s_out = n_mix_s;
 }

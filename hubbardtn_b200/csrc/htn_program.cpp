@@ -172,7 +172,7 @@ void Program::add_gemm(std::vector<GemmTaskH>& tasks, int tag) {
 }
 
 void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::vector<MixSrcH>>& extra, int tag_gemm,
-                              int tag_mix) {
+                              int tag_mix, bool adaptive_split) {
   // split-K: a reduce task has few tiles but a K loop over every (level, sector) pair; cut the
   // segment list into nsplit parts of ~SPLIT_CHUNKS chunks, each writing its own partial copy of
   // the output block (summed in fixed order by the mix => deterministic, no atomics)
@@ -181,7 +181,21 @@ void Program::add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::ve
     const char* e = getenv("HTN_SPLIT_K");  // tuning knob: K extent of one split-K part
     split_k = e ? std::max(GEMM_BK, atoi(e)) : 640;
   }
-  const int SPLIT_CHUNKS = split_k / GEMM_BK, SPLIT_MAX = 32;
+  int SPLIT_CHUNKS = split_k / GEMM_BK;
+  const int SPLIT_MAX = 32;
+  if (adaptive_split && !getenv("HTN_SPLIT_K")) {
+    // small reduce stages (a chi = 10 MPO at D_red = 1024: 282 tile-parts of K = 640 for 444 persistent CTAs) are cut finer,
+    // down to K = 128 per part, until there are ~3 parts per CTA
+    long long chunk_tiles = 0;
+    for (const GemmTaskH& t : tasks) {
+      long long ch = 0;
+      for (const GemmSegH& sg : t.segs)
+        if (sg.K > 0) ch += (sg.K + GEMM_BK - 1) / GEMM_BK;
+      if (t.M > 0 && t.N > 0) chunk_tiles += ch * (long long)tile_block(t.M, t.N).size();
+    }
+    const long long target_items = 3LL * 148 * 3;
+    SPLIT_CHUNKS = (int)std::max<long long>(8, std::min<long long>(SPLIT_CHUNKS, chunk_tiles / target_items));
+  }
   Stage st;
   st.kind = 0;
   st.tag = tag_gemm;

@@ -110,8 +110,9 @@ struct Program {
   // reduce stage: long K loops are split, partial tiles go to workspace, and a following mix stage
   // sums partials (fixed order => deterministic) plus `extra[i]` into task i's C.  Tasks with
   // neither segments nor extra sources are zero-filled.
+  // adaptive_split: cut the K loops finer when the stage has too few tile-parts for the persistent grid (H_eff stage R)
   void add_gemm_reduce(std::vector<GemmTaskH>& tasks, std::vector<std::vector<MixSrcH>>& extra, int tag_gemm,
-                       int tag_mix);
+                       int tag_mix, bool adaptive_split = false);
   void add_mix(std::vector<MixTaskH>& tasks, int tag);
   // fused stage: stack jobs (ordered by wave) + the mix targets that consume their outputs
   void add_stack(std::vector<StackJobH>& jobs, std::vector<MixTaskH>& mixes, int nwaves, int tmap_slot, int tag);
