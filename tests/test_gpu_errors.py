@@ -67,7 +67,8 @@ def test_idmrg2_needs_two_sites_and_rejects_unmirrored_models(ctx):
     with pytest.raises(NotImplementedError):
         hf.compute_groundstate(hf.OB_Sim([1.0], [4.0], 0.0, [0.0], 2, 1, 2.0), ctx=ctx)   # one-site unit cell
     with pytest.raises(NotImplementedError):
-        hf.hamiltonian(hf.OB_Sim([1.0], [4.0], 0.0, [0.5], 1, 1, 2.0), ctx)               # exchange term
+        hf.hamiltonian(hf.OB_Sim([1.0], [4.0], 0.0, [0.0], 1, 1, 2.0, kwargs={"U13": [0.3]}), ctx)   # U_ijjj term
+    assert hf.hamiltonian(hf.OB_Sim([1.0], [4.0], 0.0, [0.5], 1, 1, 2.0), ctx).chi == 8       # exchange: mirrored (triplet + pair levels)
     H = hf.hamiltonian(hf.OB_Sim([1.0], [4.0], 0.0, [0.0], 1, 1, 2.0), ctx)
     psi = hf.initialize_mps(H, 1, 50, False, ctx)
     rc = _lib.lib.htn_idmrg2(ctx.h, 1, None, None, None, None, None, 1e-2, 1e-6, 1, 30, 1e-8, 0, None, None, None, 0)
