@@ -535,11 +535,13 @@ def main():
     # ---- ncu-measured DRAM traffic of the dominant kernels (committed capture; per apply) --------
     traffic = None
     traffic_note = None
+    traffic_by_kernel = None
     try:
         with open(os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")) as f:
             ri = json.load(f)
         if args.D == 1024 and args.chi == 96 and args.sym == 0:
-            traffic = ri["gemm_traffic_bytes_per_launch"]
+            traffic_by_kernel = ri["gemm_traffic_bytes_per_launch"]
+            traffic = traffic_by_kernel["stack_gemm_kernel"]      # the dominant launch (stage L + W), bytes per launch
             traffic_note = ri.get("note")
     except Exception:
         traffic = None
@@ -592,7 +594,7 @@ def main():
             "roofline": {
                 "bound": "tensor", "kernel": "stack_gemm_kernel (stage L, the stage-W mix rides along) + grouped_gemm_kernel (stage R)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": traffic_note,
+                "traffic_note": traffic_note, "traffic_by_kernel": traffic_by_kernel,
                 "launches": [
                     {"kernel": "stack_gemm_kernel (stage L: T = GL.x, the stage-W recoupling mix fused in)",
                      "algorithmic_flop": st["flops_L"], "ms": prof["stage_L_ms"],
