@@ -134,6 +134,20 @@ int32_t inv_bond(htn_ctx* ctx, const htn_tensor* C, htn_tensor** out) {
   return htn_upload_locked(*out, inv.data(), C->hsize);
 }
 
+// temporaries of one bond update: destroyed on every early return, handed over with release() once they replace state
+struct Temps {
+  std::vector<htn_tensor**> slots;
+  void own(htn_tensor** t) { slots.push_back(t); }
+  void release(htn_tensor** t) { slots.erase(std::remove(slots.begin(), slots.end(), t), slots.end()); }
+  ~Temps() {
+    for (htn_tensor** t : slots)
+      if (*t) {
+        htn_tensor_destroy(*t);
+        *t = nullptr;
+      }
+  }
+};
+
 void replace(htn_tensor*& slot, htn_tensor* nw) {
   if (slot && slot != nw) htn_tensor_destroy(slot);
   slot = nw;
@@ -321,9 +335,16 @@ struct Idmrg {
   // standard bond update (sites i, i+1 inside the cell)
   int32_t update_bond(int i, const htn_tensor* A1, const htn_tensor* A2) {
     htn_tensor *al = nullptr, *c = nullptr, *ar = nullptr, *ac1 = nullptr, *ac2 = nullptr;
+    Temps tmp;
+    tmp.own(&al);
+    tmp.own(&c);
+    tmp.own(&ar);
+    tmp.own(&ac1);
+    tmp.own(&ac2);
     RC(solve_and_split(i, i + 1, A1, A2, &al, &c, &ar));
     RC(mul_bond(ctx, al, c, true, &ac1));
     RC(mul_bond(ctx, ar, c, false, &ac2));
+    tmp.slots.clear();  // from here on the state owns them
     replace(AL[i], al);
     replace(C[i], c);
     replace(AR[i + 1], ar);
@@ -409,17 +430,16 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
       // ---- edge (sites L-1, 0) ----
       {
         htn_tensor *ci = nullptr, *left = nullptr, *right = nullptr, *al = nullptr, *c = nullptr, *ar = nullptr;
+        htn_tensor *ac1 = nullptr, *ac0 = nullptr, *c0i = nullptr, *al0 = nullptr;
+        Temps tmp;
+        for (htn_tensor** t : {&ci, &left, &right, &al, &c, &ar, &ac1, &ac0, &c0i, &al0}) tmp.own(t);
         RC(inv_bond(ctx, D.C[L - 1], &ci));
         RC(mul_bond(ctx, D.AC[L - 1], ci, true, &left));
         RC(mul_bond(ctx, D.AL[0], D.C[0], true, &right));
-        htn_tensor_destroy(ci);
-        int32_t r2 = D.solve_and_split(L - 1, 0, left, right, &al, &c, &ar);
-        htn_tensor_destroy(left);
-        htn_tensor_destroy(right);
-        RC(r2);
-        htn_tensor *ac1 = nullptr, *ac0 = nullptr, *c0i = nullptr, *al0 = nullptr;
+        RC(D.solve_and_split(L - 1, 0, left, right, &al, &c, &ar));
         RC(mul_bond(ctx, al, c, true, &ac1));
         RC(mul_bond(ctx, ar, c, false, &ac0));
+        for (htn_tensor** t : {&al, &c, &ar, &ac1, &ac0}) tmp.release(t);  // the state owns them from here on
         replace(D.AL[L - 1], al);
         replace(D.C[L - 1], c);
         replace(D.AR[0], ar);
@@ -427,7 +447,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
         replace(D.AC[0], ac0);
         RC(inv_bond(ctx, D.C[0], &c0i));
         RC(mul_bond(ctx, D.AC[0], c0i, true, &al0));
-        htn_tensor_destroy(c0i);
+        tmp.release(&al0);
         replace(D.AL[0], al0);
         RC(D.grow_left(L - 1));
         RC(D.grow_right(0));
@@ -437,17 +457,16 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
       // ---- edge again ----
       {
         htn_tensor *ci = nullptr, *left = nullptr, *right = nullptr, *al = nullptr, *c = nullptr, *ar = nullptr;
+        htn_tensor *ac1 = nullptr, *ac0 = nullptr, *cmi = nullptr, *arl = nullptr;
+        Temps tmp;
+        for (htn_tensor** t : {&ci, &left, &right, &al, &c, &ar, &ac1, &ac0, &cmi, &arl}) tmp.own(t);
         RC(inv_bond(ctx, D.C[L - 1], &ci));
         RC(mul_bond(ctx, D.AC[0], ci, false, &right));
         RC(mul_bond(ctx, D.AR[L - 1], D.C[L - 2], false, &left));
-        htn_tensor_destroy(ci);
-        int32_t r2 = D.solve_and_split(L - 1, 0, left, right, &al, &c, &ar);
-        htn_tensor_destroy(left);
-        htn_tensor_destroy(right);
-        RC(r2);
-        htn_tensor *ac1 = nullptr, *ac0 = nullptr, *cmi = nullptr, *arl = nullptr;
+        RC(D.solve_and_split(L - 1, 0, left, right, &al, &c, &ar));
         RC(mul_bond(ctx, al, c, true, &ac1));
         RC(mul_bond(ctx, ar, c, false, &ac0));
+        for (htn_tensor** t : {&al, &c, &ar, &ac1, &ac0}) tmp.release(t);
         replace(D.AL[L - 1], al);
         replace(D.C[L - 1], c);
         replace(D.AR[0], ar);
@@ -455,7 +474,7 @@ int32_t htn_idmrg2(htn_ctx* ctx, int32_t nsites, htn_tensor** AL, htn_tensor** A
         replace(D.AC[0], ac0);
         RC(inv_bond(ctx, D.C[L - 2], &cmi));
         RC(mul_bond(ctx, D.AC[L - 1], cmi, false, &arl));
-        htn_tensor_destroy(cmi);
+        tmp.release(&arl);
         replace(D.AR[L - 1], arl);
         RC(D.grow_left(L - 1));
         RC(D.grow_right(0));
