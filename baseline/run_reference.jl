@@ -18,6 +18,13 @@ configs = Dict(
     "OB_U0" => () -> hf.OB_Sim([1.0], [0.0], 0.0, 1, 1, 2.0),                      # test/OB.jl:21
     "OB_U5" => () -> hf.OB_Sim([1.0], [5.0], 0.0, 1, 1, 2.0),                      # test/OB.jl:44
     "C2"   => () -> hf.OB_Sim([1.0, 0.2], [6.0], 0.0, 1, 1, 5.0),
+    # exchange terms: no reference test pins a model with J != 0; these two settle the sign convention of HF:445-450 /
+    # 563-616 that this repo could only take from the second-quantised operators (hubbardfunctions.mb_terms docstring):
+    # compare with tests/test_gpu_groundstate.py::test_polyacetylene_model_with_exchange_both_symmetries
+    "OB_J"  => () -> hf.OB_Sim([1.0], [4.0], 0.0, [0.5], 1, 1, 2.0),
+    "C4_polyacetylene" => () -> hf.MB_Sim([0.000 3.803 -0.548 0.000; 3.803 0.000 2.977 -0.501],
+                                          [10.317 6.264 0.000 0.000; 6.264 10.317 6.162 0.000],
+                                          [0.000 0.123 0.000 0.000; 0.123 0.000 0.113 0.000], 1, 1, 2.5, 20; code = "c4_polyacetylene"),
 )
 
 out = Dict{String,Any}()
