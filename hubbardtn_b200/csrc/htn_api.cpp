@@ -91,6 +91,7 @@ int32_t htn_ctx_destroy(htn_ctx* ctx) {
   if (!ctx) return HTN_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  htn_drop_krylov_graphs(ctx);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->red) cudaFree(ctx->red);
   if (ctx->red_host) cudaFreeHost(ctx->red_host);

@@ -78,6 +78,9 @@ struct htn_ctx {
   double* kry_scal_host = nullptr;  // pinned mirror
   double* kry_partial = nullptr;
   int64_t kry_partial_cap = 0;
+  // instantiated CUDA graphs of the Lanczos orthogonalisation step, keyed by (block table, basis, length, step, chunks,
+  // variant); dropped whenever the Krylov buffers move (htn_linalg.cpp)
+  std::map<std::array<long long, 6>, void*> kry_graphs;
   int* d_status = nullptr;  // device-side failure flags (QR rank deficiency, ...)
   int sm_count = 148;
   int32_t fail(int32_t code, const std::string& msg) {

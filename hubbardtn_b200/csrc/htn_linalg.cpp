@@ -185,10 +185,16 @@ int32_t t_qr_inplace(htn_tensor* A, htn_tensor* R) {
   return cuda_rc(ctx, "qr");
 }
 
+void htn_drop_krylov_graphs(htn_ctx* ctx) {
+  for (auto& kv : ctx->kry_graphs) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(kv.second));
+  ctx->kry_graphs.clear();
+}
+
 int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunks) {
   const int64_t need = nvec * stride;
   if (ctx->kry_cap < need) {
     cudaStreamSynchronize(ctx->stream);
+    htn_drop_krylov_graphs(ctx);
     if (ctx->kry_V) cudaFree(ctx->kry_V);
     ctx->kry_V = nullptr;
     ctx->kry_cap = 0;
@@ -198,6 +204,7 @@ int32_t ensure_krylov(htn_ctx* ctx, int64_t nvec, int64_t stride, int64_t nchunk
   const int64_t pneed = (nchunks + 1) * MD_MAXVEC_HOST;
   if (ctx->kry_partial_cap < pneed) {
     cudaStreamSynchronize(ctx->stream);
+    htn_drop_krylov_graphs(ctx);
     if (ctx->kry_partial) cudaFree(ctx->kry_partial);
     ctx->kry_partial = nullptr;
     ctx->kry_partial_cap = 0;
@@ -286,6 +293,62 @@ static void jacobi_eigh(int n, std::vector<double>& A, std::vector<double>& V, s
 // <x0, x_out> >= 0).  x0 may alias x_out.
 // Semi-eager: the coefficients of every step are parked in device arrays and read back (one synchronisation)
 // only every LANCZOS_CHECK steps, so the launches queue up instead of paying a host round trip per step.
+// One Lanczos step behind the apply: two rounds of classical Gram-Schmidt of w against V[0..j], beta^2 = <w,w>, the three
+// coefficients parked for the host, and (scale_after) w <- w / beta.  Twelve tiny launches: at D_red <= 256 they, not the
+// apply, set the pace of the eigensolver, so the sequence is captured once per (vector structure, j) into a CUDA graph
+// and replayed (HTN_LANCZOS_GRAPH=0 switches back to plain launches).
+static void lanczos_ortho_launches(htn_ctx* ctx, const htn_tensor* like, double* V, int64_t n, int j, double* w, bool scale_after) {
+  double* sc = ctx->kry_scal;
+  cudaStream_t st = ctx->stream;
+  launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H, st);
+  launch_multiaxpy(V, n, j + 1, sc + S_H, -1.0, w, n, st);
+  launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
+  launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
+  launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
+  cudaMemcpyAsync(sc + S_A1 + j, sc + S_H + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(sc + S_A2 + j, sc + S_H2 + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(sc + S_B + j, sc + S_BETA, sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if (scale_after) launch_scale_dev(w, sc + S_BETA, 3, w, n, st);  // next basis vector (0 on breakdown)
+}
+
+static int32_t lanczos_ortho_step(htn_ctx* ctx, const htn_tensor* like, double* V, int64_t n, int j, double* w, bool scale_after) {
+  static int use_graph = -1;
+  if (use_graph < 0) {
+    const char* e = getenv("HTN_LANCZOS_GRAPH");
+    use_graph = e ? atoi(e) : 0;
+  }
+  if (!use_graph || like->nchunks <= 0) {
+    lanczos_ortho_launches(ctx, like, V, n, j, w, scale_after);
+    return HTN_OK;
+  }
+  const std::array<long long, 6> key{(long long)(intptr_t)like->dblocks, (long long)(intptr_t)V, (long long)n, (long long)j,
+                                     (long long)like->nchunks, (long long)((intptr_t)like->dchunks ^ (scale_after ? 1 : 0))};
+  auto it = ctx->kry_graphs.find(key);
+  if (it == ctx->kry_graphs.end()) {
+    cudaStream_t st = ctx->stream;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      lanczos_ortho_launches(ctx, like, V, n, j, w, scale_after);
+      return HTN_OK;
+    }
+    lanczos_ortho_launches(ctx, like, V, n, j, w, scale_after);
+    if (cudaStreamEndCapture(st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      use_graph = 0;  // capture is not available: plain launches from here on (the captured work was NOT executed)
+      lanczos_ortho_launches(ctx, like, V, n, j, w, scale_after);
+      return HTN_OK;
+    }
+    cudaGraphDestroy(g);
+    if (ctx->kry_graphs.size() > 4096) htn_drop_krylov_graphs(ctx);
+    it = ctx->kry_graphs.emplace(key, (void*)ex).first;
+  }
+  if (cudaGraphLaunch(static_cast<cudaGraphExec_t>(it->second), ctx->stream) != cudaSuccess) return cuda_rc(ctx, "lanczos graph");
+  return HTN_OK;
+}
+
 int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const double* x0, double* x_out, int krylovdim,
                        double tol, int maxiter, KrylovInfo* info) {
   htn_ctx* ctx = like->ctx;
@@ -314,19 +377,9 @@ int32_t lanczos_lowest(const htn_tensor* like, const ApplyFn& apply, const doubl
       double* w = V + (int64_t)(j + 1) * n;
       if ((rc = apply(V + (int64_t)j * n, w))) return rc;
       ++applies;
-      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H, st);
-      launch_multiaxpy(V, n, j + 1, sc + S_H, -1.0, w, n, st);
-      launch_multidot(like->dblocks, like->dchunks, like->nchunks, V, n, j + 1, w, ctx->kry_partial, sc + S_H2, st);
-      launch_multiaxpy(V, n, j + 1, sc + S_H2, -1.0, w, n, st);
-      launch_multidot(like->dblocks, like->dchunks, like->nchunks, w, 0, 1, w, ctx->kry_partial, sc + S_BETA, st);
-      cudaMemcpyAsync(sc + S_A1 + j, sc + S_H + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
-      cudaMemcpyAsync(sc + S_A2 + j, sc + S_H2 + j, sizeof(double), cudaMemcpyDeviceToDevice, st);
-      cudaMemcpyAsync(sc + S_B + j, sc + S_BETA, sizeof(double), cudaMemcpyDeviceToDevice, st);
       const bool check = ((j - j0) % LANCZOS_CHECK) == LANCZOS_CHECK - 1 || j == kd - 1;
-      if (!check) {
-        launch_scale_dev(w, sc + S_BETA, 3, w, n, st);  // next basis vector (0 on breakdown)
-        continue;
-      }
+      if ((rc = lanczos_ortho_step(ctx, like, V, n, j, w, !check))) return rc;
+      if (!check) continue;
       cudaMemcpyAsync(sh + S_A1, sc + S_A1, 192 * sizeof(double), cudaMemcpyDeviceToHost, st);
       if (cudaStreamSynchronize(st) != cudaSuccess) return cuda_rc(ctx, "lanczos");
       m = j + 1;

@@ -14,6 +14,7 @@ struct KrylovInfo {
 };
 typedef std::function<int32_t(const double* x, double* y)> ApplyFn;
 
+void htn_drop_krylov_graphs(htn_ctx* ctx);
 int32_t t_copy(const htn_tensor* src, htn_tensor* dst);
 int32_t t_transpose(const htn_tensor* src, htn_tensor* dst, int mode);
 int32_t t_fill_level(htn_tensor* env, int level, int mode);
